@@ -1,0 +1,128 @@
+/*
+ * ptb200.h — C ABI of libptb200.so: a B200 (sm_100a) CUDA replacement for the path-tracing pass of
+ * BoyBaykiller/OpenTK-PathTracer, i.e. res/shaders/PathTracing/compute.glsl plus the dispatch in
+ * src/Render/PathTracer.cs.  The reference has no FFI: the seam is the C# class `PathTracer` and the GL
+ * binding points it consumes.  Each entry point below names the reference member it replaces
+ * (paths relative to OpenTK-PathTracer/).  INTEGRATION.md shows the [DllImport] shim.
+ *
+ * Conventions: every call returns 0 on success or a negative PTB_E_* code; ptb_last_error() returns a
+ * thread-local message.  Nothing throws or aborts across the ABI.  A context is bound to one CUDA device and
+ * is not re-entrant (the reference drives everything from the single GameWindow thread, Program.cs:13).
+ * All pointers are host pointers unless the name says `device`.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_OK 0
+#define PTB_E_INVALID -1   /* bad argument / range */
+#define PTB_E_CUDA -2      /* a CUDA runtime call failed */
+#define PTB_E_STATE -3     /* call order (e.g. render before an environment map was set) */
+#define PTB_E_NOMEM -4
+
+/* Kernel variants.  PTB_KERNEL_MEGA is the product; PTB_KERNEL_NAIVE is the labelled "GL-compute proxy"
+ * (one thread per pixel, 8x8 groups, scene read from the raw UBO bytes — how the GLSL dispatch is organised,
+ * PathTracer.cs:121 / compute.glsl:8), kept only as a baseline to time beside the product. */
+#define PTB_KERNEL_MEGA 0
+#define PTB_KERNEL_NAIVE 1
+
+typedef struct ptb_ctx ptb_ctx;
+
+const char* ptb_last_error(void);
+int ptb_version(void);
+
+/* new PathTracer(env, width, height, ...) — PathTracer.cs:96-110; UBO capacities MainWindow.cs:17,195-201.
+ * device = CUDA ordinal.  The result image is zero-initialised (GL leaves it undefined, Texture.cs:184). */
+int ptb_create(ptb_ctx** out, int width, int height, int max_spheres, int max_cuboids, int device);
+void ptb_destroy(ptb_ctx* ctx);
+
+/* PathTracer.SetSize — PathTracer.cs:131-135 (re-allocates Result, frame counter = 0). */
+int ptb_set_size(ptb_ctx* ctx, int width, int height);
+/* PathTracer.ResetRenderer — PathTracer.cs:137-140 (frame counter = 0; image not cleared). */
+int ptb_reset(ptb_ctx* ctx);
+
+/* Property setters RayDepth / SPP / FocalLength / ApertureDiameter — PathTracer.cs:37-83
+ * (uniforms rayDepth, SPP, focalLength, apertureDiameter, compute.glsl:90-94). */
+int ptb_set_ray_depth(ptb_ctx* ctx, int ray_depth);
+int ptb_set_spp(ptb_ctx* ctx, int spp);
+int ptb_set_focal_length(ptb_ctx* ctx, float focal_length);
+int ptb_set_aperture_diameter(ptb_ctx* ctx, float aperture_diameter);
+/* NumSpheres / NumCuboids — PathTracer.cs:11-34 (uniform vec2 uboGameObjectsSize, compute.glsl:88). */
+int ptb_set_num_spheres(ptb_ctx* ctx, int n);
+int ptb_set_num_cuboids(ptb_ctx* ctx, int n);
+
+/* BufferObject.SubData on UBO binding 0 (BasicDataUBO, 144 B: InvProjection @0, InvView @64, ViewPos @128)
+ * — BufferObject.cs:37-48 as called from MainWindow.cs:131-132,279. */
+int ptb_basic_data_subdata(ptb_ctx* ctx, int offset, int size, const void* data);
+/* BufferObject.SubData on UBO binding 1 (GameObjectsUBO: Sphere[max_spheres] stride 80 @0, Cuboid[max_cuboids]
+ * stride 96 @ max_spheres*80) — BaseSTD140Compatible.cs:12-16, Sphere.cs:20, Cuboid.cs:21. */
+int ptb_game_objects_subdata(ptb_ctx* ctx, int offset, int size, const void* data);
+
+/* PathTracer.EnvironmentMap = <RGBA32F cubemap> — PathTracer.cs:85,118.  six_faces = 6*face_size^2*4 floats,
+ * faces +X,-X,+Y,-Y,+Z,-Z, row-major with row index = t.  Sampled LINEAR + seamless (compute.glsl:177). */
+int ptb_set_environment_rgba32f(ptb_ctx* ctx, int face_size, const float* six_faces);
+/* AtmosphericScatterer(size).Render() into the environment map, on the GPU — AtmosphericScatterer.cs:63-113,
+ * AtmosphericScattering/compute.glsl.  ubo = AtmosphericDataUBO bytes (InvProjection + 6 InvView, 448 B used);
+ * light_pos / light_intensity / i_steps / j_steps are that shader's uniforms. */
+int ptb_generate_atmosphere(ptb_ctx* ctx, int face_size, const void* ubo, int ubo_size, const float* light_pos,
+                            float light_intensity, int i_steps, int j_steps);
+/* Copies the current environment map (unpadded, 6*face_size^2*4 floats) back to the host. */
+int ptb_read_environment(ptb_ctx* ctx, float* six_faces);
+int ptb_environment_size(ptb_ctx* ctx);
+
+/* PathTracer.Render() — PathTracer.cs:114-129: one dispatch, then thisRenderNumFrame++.  Asynchronous on the
+ * context's stream. */
+int ptb_render(ptb_ctx* ctx);
+/* n consecutive Render() calls (n dispatches, same results), enqueued back to back. */
+int ptb_render_frames(ptb_ctx* ctx, int n);
+/* PathTracer.Samples — PathTracer.cs:112 (thisRenderNumFrame * SPP). */
+int ptb_samples(ptb_ctx* ctx);
+int ptb_frame(ptb_ctx* ctx);
+int ptb_set_frame(ptb_ctx* ctx, int frame); /* checkpoint/resume of a progressive render */
+
+/* PathTracer.Result readback (the reference hands the GL texture to ScreenEffect, MainWindow.cs:51). */
+int ptb_read_result(ptb_ctx* ctx, float* rgba32f);            /* synchronous: W*H*4 floats, row 0 = y 0 */
+int ptb_read_result_async(ptb_ctx* ctx, float* pinned_rgba32f); /* enqueued; pair with ptb_synchronize */
+int ptb_write_result(ptb_ctx* ctx, const float* rgba32f);     /* restore an accumulation image */
+int ptb_synchronize(ptb_ctx* ctx);
+
+/* Device-side access for hosts that own CUDA memory / streams (PyTorch, CUDA-GL interop). */
+int ptb_result_device_ptr(ptb_ctx* ctx, void** device_ptr, size_t* bytes);
+int ptb_set_stream(ptb_ctx* ctx, void* cuda_stream);
+int ptb_width(ptb_ctx* ctx);
+int ptb_height(ptb_ctx* ctx);
+
+/* Pixel-tile partition for one-process-per-GPU rendering: this context renders only the rows y with
+ * (y / stripe_rows) % world == rank, stored compactly (local row order) in its result image; seeds use global
+ * pixel coordinates (compute.glsl:104-106) so the union over ranks is bit-identical to a single-GPU render. */
+int ptb_set_tile(ptb_ctx* ctx, int rank, int world, int stripe_rows);
+int ptb_local_rows(ptb_ctx* ctx);
+/* Scatter rank-major gathered stripe buffers (world x max_local_rows x W x 4, device) into a full row-major
+ * image (H x W x 4, device) — the de-interleave after the per-frame NCCL gather. */
+int ptb_deinterleave_device(ptb_ctx* ctx, const void* gathered_device, void* full_device);
+int ptb_max_local_rows(ptb_ctx* ctx);
+
+/* Kernel selection and introspection. */
+int ptb_set_kernel(ptb_ctx* ctx, int kernel);
+int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
+float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
+/* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */
+int ptb_set_stats(ptb_ctx* ctx, int enabled);
+int ptb_read_stats(ptb_ctx* ctx, unsigned long long* counters3);
+
+/* Unit-level probes used by the parity tests: evaluate device functions on arrays (host in, host out).
+ * op: 0 sincos (in n, out 2n)  1 exp (n -> n)  2 pcg stream (in: 1 seed as uint32 bits, out n floats)
+ *     3 texture(samplerCube) (in 3n dirs, out 3n)  4 RayTrace fold over the current scene (in 6n rays, out 12n)
+ *     5 min/max/rcp/sqrt probe (in 2n, out 4n) */
+int ptb_debug_eval(ptb_ctx* ctx, int op, const float* in, int n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,526 @@
+// ptb_abi.cu — the C ABI of libptb200.so (see include/ptb200.h for the reference member each entry replaces).
+// Host side: owns the device copies of the two UBOs, the padded environment cubemap, the accumulation image,
+// the packed scene block, and launches the kernels of ptb_kernels.cuh on the context's stream.
+#include "../../include/ptb200.h"
+#include "ptb_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace ptb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(PTB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kBasicBytes = 144;   // MainWindow.cs:196
+constexpr int kMaxSmem = 227 * 1024;
+
+} // namespace
+
+struct ptb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int width = 0, height = 0;
+    int max_spheres = 0, max_cuboids = 0;
+    int n_spheres = 0, n_cuboids = 0;
+    int ray_depth = 13, spp = 1;
+    float focal_length = 20.0f, aperture_diameter = 0.14f;
+    int frame = 0;
+    int kernel = PTB_KERNEL_MEGA;
+    int rank = 0, world = 1, stripe_rows = 8, local_rows = 0;
+    // host mirrors
+    unsigned char basic[kBasicBytes] = {};
+    std::vector<unsigned char> objects;    // GameObjectsUBO bytes
+    bool scene_dirty = true;
+    // device
+    unsigned char* d_objects = nullptr;
+    float4* d_block = nullptr;
+    size_t block_capacity = 0;
+    int off_aux = 0, off_cmin = 0, off_cmax = 0, off_mat = 0, block_bytes = 0;
+    float4* d_env_faces = nullptr;   // unpadded 6*N*N
+    float4* d_env = nullptr;         // padded 6*(N+2)^2
+    int env_size = 0;
+    float4* d_image = nullptr;
+    size_t image_bytes = 0;
+    unsigned int* d_counters = nullptr;
+    unsigned long long* d_stats = nullptr;
+    bool stats_on = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int launches = 0;
+    int mega_smem_set = -1;
+    int mega_grid = 0;
+};
+
+namespace {
+
+int compute_local_rows(int height, int rank, int world, int stripe_rows)
+{
+    int rows = 0;
+    const int stripes = (height + stripe_rows - 1) / stripe_rows;
+    for (int s = rank; s < stripes; s += world) rows += (s * stripe_rows + stripe_rows <= height) ? stripe_rows : height - s * stripe_rows;
+    return rows;
+}
+
+int alloc_image(ptb_ctx* c)
+{
+    CU(cudaSetDevice(c->device));
+    c->local_rows = compute_local_rows(c->height, c->rank, c->world, c->stripe_rows);
+    // capacity = the largest local image any rank holds, so gathered buffers are uniform
+    const int max_rows = compute_local_rows(c->height, 0, c->world, c->stripe_rows);
+    const size_t bytes = (size_t)(max_rows > 0 ? max_rows : 1) * c->width * sizeof(float4);
+    if (c->d_image) { CU(cudaFree(c->d_image)); c->d_image = nullptr; }
+    CU(cudaMalloc(&c->d_image, bytes));
+    CU(cudaMemsetAsync(c->d_image, 0, bytes, c->stream));
+    c->image_bytes = bytes;
+    return PTB_OK;
+}
+
+void layout_block(ptb_ctx* c)
+{
+    const int nS = c->n_spheres, nC = c->n_cuboids;
+    c->off_aux = nS;                              // float4 units
+    c->off_cmin = c->off_aux + (nS + 3) / 4;
+    c->off_cmax = c->off_cmin + nC;
+    c->off_mat = c->off_cmax + nC;
+    c->block_bytes = (c->off_mat + (nS + nC) * 4) * 16;
+    if (c->block_bytes < 16) c->block_bytes = 16;
+}
+
+int sync_scene(ptb_ctx* c)
+{
+    if (!c->scene_dirty) return PTB_OK;
+    layout_block(c);
+    if (c->block_bytes > kMaxSmem - 1024)
+        return fail(PTB_E_INVALID, "scene block of %d bytes does not fit shared memory (%d spheres, %d cuboids)", c->block_bytes, c->n_spheres, c->n_cuboids);
+    if ((size_t)c->block_bytes > c->block_capacity) {
+        if (c->d_block) CU(cudaFree(c->d_block));
+        c->d_block = nullptr;
+        CU(cudaMalloc(&c->d_block, (size_t)c->block_bytes));
+        c->block_capacity = (size_t)c->block_bytes;
+    }
+    CU(cudaMemcpyAsync(c->d_objects, c->objects.data(), c->objects.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_block, 0, (size_t)c->block_bytes, c->stream));
+    const int n = c->n_spheres + c->n_cuboids;
+    if (n > 0) {
+        pack_scene_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_objects, c->max_spheres, c->n_spheres, c->n_cuboids, c->d_block, c->off_aux,
+                                                                  c->off_cmin, c->off_cmax, c->off_mat);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    c->scene_dirty = false;
+    return PTB_OK;
+}
+
+void fill_params(ptb_ctx* c, RenderParams& P)
+{
+    memcpy(P.basic, c->basic, kBasicBytes);
+    P.width = c->width; P.height = c->height; P.frame = c->frame;
+    P.spp = c->spp; P.ray_depth = c->ray_depth;
+    P.focal_length = c->focal_length; P.aperture_diameter = c->aperture_diameter;
+    P.n_spheres = c->n_spheres; P.n_cuboids = c->n_cuboids;
+    P.env_size = c->env_size;
+    P.rank = c->rank; P.world = c->world; P.stripe_rows = c->stripe_rows; P.local_rows = c->local_rows;
+    P.off_aux = c->off_aux; P.off_cmin = c->off_cmin; P.off_cmax = c->off_cmax; P.off_mat = c->off_mat; P.block_bytes = c->block_bytes;
+    P.scene = c->d_block; P.env = c->d_env; P.image = c->d_image;
+    P.counters = c->d_counters; P.stats = c->d_stats;
+    P.raw_objects = c->d_objects; P.max_spheres = c->max_spheres;
+}
+
+int launch_frame(ptb_ctx* c)
+{
+    RenderParams P;
+    fill_params(c, P);
+    if (c->kernel == PTB_KERNEL_NAIVE) {
+        dim3 grid((c->width + 7) / 8, (c->local_rows + 7) / 8, 1), block(8, 8, 1);   // PathTracer.cs:121
+        if (grid.y > 0) naive_kernel<<<grid, block, 0, c->stream>>>(P);
+    } else {
+        const int smem = c->block_bytes;
+        if (c->mega_smem_set != smem) {
+            CU(cudaFuncSetAttribute(megakernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, megakernel<false>, kMegaThreads, smem));
+            if (per_sm < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
+            c->mega_grid = c->sm_count * per_sm;
+            c->mega_smem_set = smem;
+        }
+        if (c->local_rows > 0) {
+            if (c->stats_on) megakernel<true><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+            else megakernel<false><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+        }
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    c->frame++;   // PathTracer.cs:117 thisRenderNumFrame++
+    return PTB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ptb_last_error(void) { return g_err; }
+int ptb_version(void) { return 100; }
+
+int ptb_create(ptb_ctx** out, int width, int height, int max_spheres, int max_cuboids, int device)
+{
+    if (!out) return fail(PTB_E_INVALID, "out is null");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || max_spheres < 0 || max_cuboids < 0) return fail(PTB_E_INVALID, "bad size %dx%d / capacities %d,%d", width, height, max_spheres, max_cuboids);
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(PTB_E_INVALID, "device %d out of range (%d CUDA devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(PTB_E_CUDA, "libptb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    ptb_ctx* c = new (std::nothrow) ptb_ctx();
+    if (!c) return fail(PTB_E_NOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->width = width; c->height = height;
+    c->max_spheres = max_spheres; c->max_cuboids = max_cuboids;
+    c->objects.assign((size_t)max_spheres * kSphereStride + (size_t)max_cuboids * kCuboidStride + 16, 0);
+    int rc = PTB_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(PTB_E_CUDA, "cudaStreamCreate failed"); break; }
+        c->own_stream = true;
+        if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) { rc = fail(PTB_E_CUDA, "cudaEventCreate failed"); break; }
+        if (cudaMalloc(&c->d_objects, c->objects.size()) != cudaSuccess) { rc = fail(PTB_E_NOMEM, "cudaMalloc(objects) failed"); break; }
+        if (cudaMalloc(&c->d_counters, 2 * sizeof(unsigned int)) != cudaSuccess) { rc = fail(PTB_E_NOMEM, "cudaMalloc(counters) failed"); break; }
+        if (cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) { rc = fail(PTB_E_NOMEM, "cudaMalloc(stats) failed"); break; }
+        cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned int), c->stream);
+        cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream);
+        rc = alloc_image(c);
+    } while (0);
+    if (rc != PTB_OK) { ptb_destroy(c); return rc; }
+    *out = c;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_objects); cudaFree(c->d_block); cudaFree(c->d_env_faces); cudaFree(c->d_env);
+    cudaFree(c->d_image); cudaFree(c->d_counters); cudaFree(c->d_stats);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ptb_set_size(ptb_ctx* c, int width, int height)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (width <= 0 || height <= 0) return fail(PTB_E_INVALID, "bad size %dx%d", width, height);
+    CU(cudaStreamSynchronize(c->stream));
+    c->width = width; c->height = height;
+    c->frame = 0;                                    // PathTracer.cs:133
+    return alloc_image(c);
+}
+
+int ptb_reset(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    c->frame = 0;
+    return PTB_OK;
+}
+
+int ptb_set_ray_depth(ptb_ctx* c, int v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); if (v < 0) return fail(PTB_E_INVALID, "rayDepth %d < 0", v); c->ray_depth = v; return PTB_OK; }
+int ptb_set_spp(ptb_ctx* c, int v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); if (v < 1) return fail(PTB_E_INVALID, "SPP %d < 1", v); c->spp = v; return PTB_OK; }
+int ptb_set_focal_length(ptb_ctx* c, float v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); c->focal_length = v; return PTB_OK; }
+int ptb_set_aperture_diameter(ptb_ctx* c, float v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); c->aperture_diameter = v; return PTB_OK; }
+int ptb_set_num_spheres(ptb_ctx* c, int n)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (n < 0 || n > c->max_spheres) return fail(PTB_E_INVALID, "NumSpheres %d outside [0,%d]", n, c->max_spheres);
+    if (n != c->n_spheres) { c->n_spheres = n; c->scene_dirty = true; }
+    return PTB_OK;
+}
+int ptb_set_num_cuboids(ptb_ctx* c, int n)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (n < 0 || n > c->max_cuboids) return fail(PTB_E_INVALID, "NumCuboids %d outside [0,%d]", n, c->max_cuboids);
+    if (n != c->n_cuboids) { c->n_cuboids = n; c->scene_dirty = true; }
+    return PTB_OK;
+}
+
+int ptb_basic_data_subdata(ptb_ctx* c, int offset, int size, const void* data)
+{
+    if (!c || !data) return fail(PTB_E_INVALID, "null argument");
+    if (offset < 0 || size < 0 || offset + size > kBasicBytes) return fail(PTB_E_INVALID, "BasicDataUBO SubData [%d,%d) outside 144 bytes", offset, offset + size);
+    memcpy(c->basic + offset, data, (size_t)size);
+    return PTB_OK;
+}
+
+int ptb_game_objects_subdata(ptb_ctx* c, int offset, int size, const void* data)
+{
+    if (!c || !data) return fail(PTB_E_INVALID, "null argument");
+    const size_t cap = (size_t)c->max_spheres * kSphereStride + (size_t)c->max_cuboids * kCuboidStride;
+    if (offset < 0 || size < 0 || (size_t)offset + (size_t)size > cap) return fail(PTB_E_INVALID, "GameObjectsUBO SubData [%d,%d) outside %zu bytes", offset, offset + size, cap);
+    memcpy(c->objects.data() + offset, data, (size_t)size);
+    c->scene_dirty = true;
+    return PTB_OK;
+}
+
+static int install_environment(ptb_ctx* c, int N)
+{
+    // d_env_faces already holds 6*N*N texels on the stream; (re)build the padded copy
+    const int P = N + 2;
+    if (c->d_env) { CU(cudaFree(c->d_env)); c->d_env = nullptr; }
+    CU(cudaMalloc(&c->d_env, (size_t)6 * P * P * sizeof(float4)));
+    dim3 block(16, 16, 1), grid((P + 15) / 16, (P + 15) / 16, 6);
+    pad_cubemap_kernel<<<grid, block, 0, c->stream>>>(c->d_env_faces, N, c->d_env);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->env_size = N;
+    return PTB_OK;
+}
+
+int ptb_set_environment_rgba32f(ptb_ctx* c, int face_size, const float* six_faces)
+{
+    if (!c || !six_faces) return fail(PTB_E_INVALID, "null argument");
+    if (face_size < 1 || face_size > 8192) return fail(PTB_E_INVALID, "face size %d outside [1,8192]", face_size);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t bytes = (size_t)6 * face_size * face_size * sizeof(float4);
+    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; }
+    CU(cudaMalloc(&c->d_env_faces, bytes));
+    CU(cudaMemcpyAsync(c->d_env_faces, six_faces, bytes, cudaMemcpyHostToDevice, c->stream));
+    return install_environment(c, face_size);
+}
+
+int ptb_generate_atmosphere(ptb_ctx* c, int face_size, const void* ubo, int ubo_size, const float* light_pos, float light_intensity, int i_steps, int j_steps)
+{
+    if (!c || !ubo || !light_pos) return fail(PTB_E_INVALID, "null argument");
+    if (face_size < 1 || face_size > 8192) return fail(PTB_E_INVALID, "face size %d outside [1,8192]", face_size);
+    if (ubo_size < 448) return fail(PTB_E_INVALID, "AtmosphericDataUBO needs 448 bytes, got %d", ubo_size);
+    if (i_steps < 0 || j_steps < 0) return fail(PTB_E_INVALID, "negative step count");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t bytes = (size_t)6 * face_size * face_size * sizeof(float4);
+    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; }
+    CU(cudaMalloc(&c->d_env_faces, bytes));
+    AtmosParams A;
+    memcpy(A.ubo, ubo, 448);
+    A.light[0] = light_pos[0]; A.light[1] = light_pos[1]; A.light[2] = light_pos[2];
+    A.intensity = light_intensity < 0.0f ? 0.0f : light_intensity;   // AtmosphericScatterer.cs:52
+    A.i_steps = i_steps; A.j_steps = j_steps; A.size = face_size;
+    dim3 block(8, 8, 1), grid((face_size + 7) / 8, (face_size + 7) / 8, 6);   // AtmosphericScatterer.cs:109
+    atmosphere_kernel<<<grid, block, 0, c->stream>>>(A, c->d_env_faces);
+    c->launches++;
+    CU(cudaGetLastError());
+    return install_environment(c, face_size);
+}
+
+int ptb_read_environment(ptb_ctx* c, float* six_faces)
+{
+    if (!c || !six_faces) return fail(PTB_E_INVALID, "null argument");
+    if (!c->d_env_faces) return fail(PTB_E_STATE, "no environment map set");
+    CU(cudaMemcpyAsync(six_faces, c->d_env_faces, (size_t)6 * c->env_size * c->env_size * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+int ptb_environment_size(ptb_ctx* c) { return c ? c->env_size : fail(PTB_E_INVALID, "ctx is null"); }
+
+int ptb_render_frames(ptb_ctx* c, int n)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (n < 0) return fail(PTB_E_INVALID, "n < 0");
+    if (!c->d_env) return fail(PTB_E_STATE, "Render() before an EnvironmentMap was set");
+    CU(cudaSetDevice(c->device));
+    int rc = sync_scene(c);
+    if (rc != PTB_OK) return rc;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < n; ++i) {
+        rc = launch_frame(c);
+        if (rc != PTB_OK) return rc;
+    }
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    return PTB_OK;
+}
+int ptb_render(ptb_ctx* c) { return ptb_render_frames(c, 1); }
+
+int ptb_samples(ptb_ctx* c) { return c ? c->frame * c->spp : fail(PTB_E_INVALID, "ctx is null"); }
+int ptb_frame(ptb_ctx* c) { return c ? c->frame : fail(PTB_E_INVALID, "ctx is null"); }
+int ptb_set_frame(ptb_ctx* c, int frame)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (frame < 0) return fail(PTB_E_INVALID, "frame < 0");
+    c->frame = frame;
+    return PTB_OK;
+}
+
+int ptb_read_result_async(ptb_ctx* c, float* dst)
+{
+    if (!c || !dst) return fail(PTB_E_INVALID, "null argument");
+    CU(cudaMemcpyAsync(dst, c->d_image, (size_t)c->local_rows * c->width * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    return PTB_OK;
+}
+int ptb_read_result(ptb_ctx* c, float* dst)
+{
+    const int rc = ptb_read_result_async(c, dst);
+    if (rc != PTB_OK) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+int ptb_write_result(ptb_ctx* c, const float* src)
+{
+    if (!c || !src) return fail(PTB_E_INVALID, "null argument");
+    CU(cudaMemcpyAsync(c->d_image, src, (size_t)c->local_rows * c->width * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+int ptb_synchronize(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_result_device_ptr(ptb_ctx* c, void** p, size_t* bytes)
+{
+    if (!c || !p) return fail(PTB_E_INVALID, "null argument");
+    *p = c->d_image;
+    if (bytes) *bytes = c->image_bytes;
+    return PTB_OK;
+}
+int ptb_set_stream(ptb_ctx* c, void* s)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return PTB_OK;
+}
+int ptb_width(ptb_ctx* c) { return c ? c->width : fail(PTB_E_INVALID, "ctx is null"); }
+int ptb_height(ptb_ctx* c) { return c ? c->height : fail(PTB_E_INVALID, "ctx is null"); }
+
+int ptb_set_tile(ptb_ctx* c, int rank, int world, int stripe_rows)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (world < 1 || rank < 0 || rank >= world || stripe_rows < 1) return fail(PTB_E_INVALID, "bad tile rank=%d world=%d stripe_rows=%d", rank, world, stripe_rows);
+    CU(cudaStreamSynchronize(c->stream));
+    c->rank = rank; c->world = world; c->stripe_rows = stripe_rows;
+    c->frame = 0;
+    return alloc_image(c);
+}
+int ptb_local_rows(ptb_ctx* c) { return c ? c->local_rows : fail(PTB_E_INVALID, "ctx is null"); }
+int ptb_max_local_rows(ptb_ctx* c) { return c ? compute_local_rows(c->height, 0, c->world, c->stripe_rows) : fail(PTB_E_INVALID, "ctx is null"); }
+
+int ptb_deinterleave_device(ptb_ctx* c, const void* gathered, void* full)
+{
+    if (!c || !gathered || !full) return fail(PTB_E_INVALID, "null argument");
+    dim3 block(256, 1, 1), grid((c->width + 255) / 256, c->height, 1);
+    deinterleave_kernel<<<grid, block, 0, c->stream>>>((const float4*)gathered, (float4*)full, c->width, c->height, c->world, c->stripe_rows,
+                                                       compute_local_rows(c->height, 0, c->world, c->stripe_rows));
+    c->launches++;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_set_kernel(ptb_ctx* c, int k)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (k != PTB_KERNEL_MEGA && k != PTB_KERNEL_NAIVE) return fail(PTB_E_INVALID, "unknown kernel %d", k);
+    c->kernel = k;
+    return PTB_OK;
+}
+int ptb_kernel_launches(ptb_ctx* c) { return c ? c->launches : fail(PTB_E_INVALID, "ctx is null"); }
+float ptb_last_render_ms(ptb_ctx* c)
+{
+    if (!c || !c->timed) return -1.0f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+int ptb_set_stats(ptb_ctx* c, int enabled)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    c->stats_on = enabled != 0;
+    CU(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    return PTB_OK;
+}
+int ptb_read_stats(ptb_ctx* c, unsigned long long* out3)
+{
+    if (!c || !out3) return fail(PTB_E_INVALID, "null argument");
+    CU(cudaMemcpyAsync(out3, c->d_stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
+{
+    if (!c || !in || !out || n < 0) return fail(PTB_E_INVALID, "bad argument");
+    if (n == 0) return PTB_OK;
+    CU(cudaSetDevice(c->device));
+    size_t in_f = 0, out_f = 0;
+    switch (op) {
+    case 0: in_f = n; out_f = 2 * (size_t)n; break;
+    case 1: in_f = n; out_f = n; break;
+    case 2: in_f = 1; out_f = n; break;
+    case 3: in_f = 3 * (size_t)n; out_f = 3 * (size_t)n; break;
+    case 4: case 6: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
+    case 5: in_f = 2 * (size_t)n; out_f = 4 * (size_t)n; break;
+    default: return fail(PTB_E_INVALID, "unknown debug op %d", op);
+    }
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, in_f * sizeof(float)));
+    CU(cudaMalloc(&d_out, out_f * sizeof(float)));
+    int rc = PTB_OK;
+    do {
+        if (cudaMemcpyAsync(d_in, in, in_f * sizeof(float), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(PTB_E_CUDA, "H2D failed"); break; }
+        const int tb = 128, gb = (n + tb - 1) / tb;
+        if (op == 0) dbg_sincos_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
+        else if (op == 1) dbg_exp_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
+        else if (op == 2) { uint32_t seed; memcpy(&seed, in, 4); dbg_pcg_kernel<<<1, 32, 0, c->stream>>>(seed, n, d_out); }
+        else if (op == 3) {
+            if (!c->d_env) { rc = fail(PTB_E_STATE, "no environment map set"); break; }
+            dbg_env_kernel<<<gb, tb, 0, c->stream>>>(c->d_env, c->env_size, d_in, n, d_out);
+        } else if (op == 4 || op == 6) {
+            rc = sync_scene(c);
+            if (rc != PTB_OK) break;
+            RenderParams P;
+            fill_params(c, P);
+            const int smem = op == 4 ? c->block_bytes : 0;
+            if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->block_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
+            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : 0);
+        } else if (op == 5) dbg_arith_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(PTB_E_CUDA, "debug kernel launch failed"); break; }
+        if (cudaMemcpyAsync(out, d_out, out_f * sizeof(float), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = fail(PTB_E_CUDA, "D2H failed"); break; }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(PTB_E_CUDA, "debug kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+} // extern "C"

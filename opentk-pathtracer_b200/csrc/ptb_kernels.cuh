@@ -1,0 +1,720 @@
+// ptb_kernels.cuh — device code of libptb200: the path-tracing megakernel and its helpers (sm_100a).
+//
+// What it replaces: res/shaders/PathTracing/compute.glsl (cited below as pt:LINE) dispatched by
+// src/Render/PathTracer.cs:114-129.  This is a re-design, not a translation:
+//   * a persistent grid (CTAs resident on every SM) pulls pixels from one atomic work counter;
+//   * each warp keeps 32 paths in registers and, after every bounce, refills the lanes whose pixel finished
+//     (ballot + prefix-popcount slot assignment), so lanes at different bounce depths stay in one coherent
+//     trace->shade loop instead of idling until the longest path of an 8x8 group ends;
+//   * the scene is repacked once per edit into an SoA block (sphere centre + r^2, slab bounds, 1/r, materials)
+//     and staged HBM -> shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA;
+//   * the closest-hit fold keeps only (T, primitive, fromInside); position / normal / material are produced once
+//     for the winner;
+//   * the cubemap is stored with a 1-texel seamless border so a miss is four aligned 128-bit loads and three lerps;
+//   * results leave as 128-bit stores.
+// Arithmetic is the evaluation model of ptb_math.cuh (bit-exact against the CPU oracle in tests/).
+#pragma once
+#include "ptb_math.cuh"
+
+namespace ptb {
+
+constexpr float kFloatMax = 3.4028235e+38f;   // pt:2
+constexpr float kFloatMin = -3.4028235e+38f;  // pt:3
+constexpr float kEps = 0.001f;                // pt:4
+constexpr float kPi = 3.14159265f;            // pt:5
+
+constexpr int kSphereStride = 80;   // Sphere.cs:8
+constexpr int kCuboidStride = 96;   // Cuboid.cs:8
+constexpr int kMegaThreads = 256;
+
+// ------------------------------------------------------------------------------------------------------------
+// Launch parameters (by value: they live in the constant bank; UBO 0 is small enough to ride along).
+struct RenderParams {
+    float basic[36];          // BasicDataUBO: InvProjection @0, InvView @16, ViewPos @32  (pt:59-64)
+    int width, height;        // imageSize(ImgResult) — the FULL image, also for tiles
+    int frame;                // thisRendererFrame (pt:96)
+    int spp, ray_depth;       // pt:90-91
+    float focal_length, aperture_diameter;  // pt:93-94
+    int n_spheres, n_cuboids; // uboGameObjectsSize (pt:88)
+    int env_size;             // cubemap face edge N (padded faces are (N+2)^2)
+    int rank, world, stripe_rows, local_rows;  // pixel-tile partition (rows y with (y/stripe_rows)%world==rank)
+    // packed scene block (float4 units from the block base)
+    int off_aux, off_cmin, off_cmax, off_mat, block_bytes;
+    const float4* scene;      // packed scene block in HBM
+    const float4* env;        // padded cubemap
+    float4* image;            // local accumulation image: local_rows x width
+    unsigned int* counters;   // [0] work counter, [1] finished-CTA counter
+    unsigned long long* stats;// optional: samples, traces, hits
+    const unsigned char* raw_objects; // raw GameObjectsUBO bytes (naive proxy only)
+    int max_spheres;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Scene views.  Both expose the same accessors; the fold and the shader are written once against them.
+struct PackedScene {           // SoA block in shared memory
+    const float4* base;
+    int nS, nC, off_aux, off_cmin, off_cmax, off_mat;
+    __device__ __forceinline__ float4 sphere(int i) const { return base[i]; }                 // (c, r*r)
+    __device__ __forceinline__ float sphere_rcp_r(int i) const { return reinterpret_cast<const float*>(base + off_aux)[i]; }
+    __device__ __forceinline__ float4 cmin(int i) const { return base[off_cmin + i]; }
+    __device__ __forceinline__ float4 cmax(int i) const { return base[off_cmax + i]; }
+    __device__ __forceinline__ float4 mat(int prim, int k) const { return base[off_mat + prim * 4 + k]; }
+};
+struct RawScene {              // the std140 bytes exactly as the host uploaded them (naive proxy)
+    const unsigned char* ubo;
+    int nS, nC, max_spheres;
+    __device__ __forceinline__ float4 sphere(int i) const
+    {
+        float4 s = __ldg(reinterpret_cast<const float4*>(ubo + (size_t)i * kSphereStride));
+        s.w = s.w * s.w;
+        return s;
+    }
+    __device__ __forceinline__ float sphere_rcp_r(int i) const
+    {
+        return rcp(__ldg(reinterpret_cast<const float4*>(ubo + (size_t)i * kSphereStride)).w);
+    }
+    __device__ __forceinline__ const unsigned char* cub(int i) const { return ubo + (size_t)max_spheres * kSphereStride + (size_t)i * kCuboidStride; }
+    __device__ __forceinline__ float4 cmin(int i) const { return __ldg(reinterpret_cast<const float4*>(cub(i))); }
+    __device__ __forceinline__ float4 cmax(int i) const { return __ldg(reinterpret_cast<const float4*>(cub(i) + 16)); }
+    __device__ __forceinline__ float4 mat(int prim, int k) const
+    {
+        const unsigned char* p = prim < nS ? ubo + (size_t)prim * kSphereStride + 16 : cub(prim - nS) + 32;
+        return __ldg(reinterpret_cast<const float4*>(p) + k);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// pt:226-294 — the order-dependent closest-hit fold (spheres, then cuboids; accept on hit && t2>0 && t1<T).
+template <class Scene>
+__device__ __forceinline__ void trace(const Scene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
+{
+    T = kFloatMax;
+    prim = -1;
+    inside = false;
+#pragma unroll 4
+    for (int i = 0; i < sc.nS; ++i) {
+        const float4 s = sc.sphere(i);
+        const V3 v = mk(o.x - s.x, o.y - s.y, o.z - s.z);
+        const float b = dot(d, v);
+        const float c = dot(v, v) - s.w;
+        const float disc = b * b - c;
+        if (!(disc < 0.0f)) {
+            const float sq = fsqrt(disc);
+            const float t1 = -b - sq;
+            const float t2 = -b + sq;
+            if (t1 <= t2 && t2 > 0.0f && t1 < T) {
+                T = t1 < 0.0f ? t2 : t1;
+                inside = (T == t2);
+                prim = i;
+            }
+        }
+    }
+    const float ix = rcp(d.x), iy = rcp(d.y), iz = rcp(d.z);
+#pragma unroll 2
+    for (int i = 0; i < sc.nC; ++i) {
+        const float4 lo = sc.cmin(i), hi = sc.cmax(i);
+        const float ax = (lo.x - o.x) * ix, ay = (lo.y - o.y) * iy, az = (lo.z - o.z) * iz;
+        const float bx = (hi.x - o.x) * ix, by = (hi.y - o.y) * iy, bz = (hi.z - o.z) * iz;
+        const float t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
+        const float t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
+        if (t1 <= t2 && t2 > 0.0f && t1 < T) {
+            T = t1 < 0.0f ? t2 : t1;
+            inside = (T == t2);
+            prim = sc.nS + i;
+        }
+    }
+}
+
+// pt:316-332 — surface normal of the winning primitive.
+template <class Scene>
+__device__ __forceinline__ V3 surface_normal(const Scene& sc, int prim, V3 pos)
+{
+    if (prim < sc.nS) {
+        const float4 s = sc.sphere(prim);
+        return mk(pos.x - s.x, pos.y - s.y, pos.z - s.z) * sc.sphere_rcp_r(prim);
+    }
+    const float4 lo = sc.cmin(prim - sc.nS), hi = sc.cmax(prim - sc.nS);
+    const V3 half = mk(hi.x - lo.x, hi.y - lo.y, hi.z - lo.z) * 0.5f;
+    const V3 cs = pos - mk(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z) * 0.5f;
+    V3 n;
+    n.x = 0.0f + signf(cs.x) * stepf(fabsf(fabsf(cs.x) - half.x), kEps);
+    n.y = 0.0f + signf(cs.y) * stepf(fabsf(fabsf(cs.y) - half.y), kEps);
+    n.z = 0.0f + signf(cs.z) * stepf(fabsf(fabsf(cs.z) - half.z), kEps);
+    return normalize(n);
+}
+
+// pt:297-307
+__device__ __forceinline__ V3 cosine_hemisphere(V3 n, uint32_t& rng)
+{
+    const float z = rand01(rng) * 2.0f - 1.0f;
+    const float a = rand01(rng) * 2.0f * kPi;
+    const float r = fsqrt(1.0f - z * z);
+    float sn, cs;
+    sincos_(a, sn, cs);
+    return normalize(n + mk(r * cs, r * sn, z));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// texture(SamplerEnvironment, dir).rgb (pt:177): GL 4.5 cube face selection, LINEAR magnification, seamless.
+// The border of each padded face already holds the neighbouring faces' texels (pad_cubemap_kernel).
+__device__ __forceinline__ V3 env_lookup(const float4* __restrict__ env, int N, V3 r)
+{
+    const float ax = fabsf(r.x), ay = fabsf(r.y), az = fabsf(r.z);
+    // non-finite or zero direction: defined to fetch 0 (a texture unit never returns NaN for NaN coords)
+    if (!(ax <= kFloatMax && ay <= kFloatMax && az <= kFloatMax) || (ax == 0.0f && ay == 0.0f && az == 0.0f))
+        return mk(0.0f, 0.0f, 0.0f);
+    int f;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { ma = ax; f = r.x >= 0.0f ? 0 : 1; sc = r.x >= 0.0f ? -r.z : r.z; tc = -r.y; }
+    else if (ay >= ax && ay >= az) { ma = ay; f = r.y >= 0.0f ? 2 : 3; sc = r.x; tc = r.y >= 0.0f ? r.z : -r.z; }
+    else { ma = az; f = r.z >= 0.0f ? 4 : 5; sc = r.z >= 0.0f ? r.x : -r.x; tc = -r.y; }
+    const float ima = rcp(ma);
+    const float s = 0.5f * (sc * ima + 1.0f);
+    const float t = 0.5f * (tc * ima + 1.0f);
+    const float u = s * (float)N - 0.5f;
+    const float v = t * (float)N - 0.5f;
+    const float fu = floorf(u), fv = floorf(v);
+    const float alpha = u - fu, beta = v - fv;
+    int i0 = __float2int_rz(fu), j0 = __float2int_rz(fv);
+    i0 = max(-1, min(N - 1, i0));
+    j0 = max(-1, min(N - 1, j0));
+    const int P = N + 2;
+    const float4* p = env + ((size_t)f * P + (j0 + 1)) * P + (i0 + 1);
+    const float4 t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + P), t11 = __ldg(p + P + 1);
+    const V3 top = mix(mk(t00.x, t00.y, t00.z), mk(t10.x, t10.y, t10.z), alpha);
+    const V3 bot = mix(mk(t01.x, t01.y, t01.z), mk(t11.x, t11.y, t11.z), alpha);
+    return mix(top, bot, beta);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One lane's path state.
+struct Path {
+    V3 o, d;            // current ray
+    V3 thr, rad;        // throughput, radiance of the current sample
+    V3 irr;             // sum of finished samples of this pixel (pt:109,123)
+    uint32_t rng;       // rndSeed (pt:98) — one stream per pixel, continuous across samples and bounces
+    int px, py;         // global pixel coordinates (gl_GlobalInvocationID.xy)
+    int lrow;           // row inside this rank's local image
+    int sample, depth;
+};
+
+// pt:110-121 — jitter, pinhole ray, thin-lens origin / direction.  Draw order: jitter.x, jitter.y, angle, radius.
+__device__ __forceinline__ void primary_ray(const RenderParams& P, Path& p)
+{
+    const float ox = rand01(p.rng);
+    const float oy = rand01(p.rng);
+    const float ndcx = ((float)p.px + ox) * rcp((float)P.width) * 2.0f - 1.0f;
+    const float ndcy = ((float)p.py + oy) * rcp((float)P.height) * 2.0f - 1.0f;
+    const float* IP = P.basic;
+    const float* IV = P.basic + 16;
+    const float ex = mat_row(IP, 0, ndcx, ndcy, -1.0f, 0.0f);
+    const float ey = mat_row(IP, 1, ndcx, ndcy, -1.0f, 0.0f);
+    const V3 dir = normalize(mk(mat_row(IV, 0, ex, ey, -1.0f, 0.0f), mat_row(IV, 1, ex, ey, -1.0f, 0.0f), mat_row(IV, 2, ex, ey, -1.0f, 0.0f)));
+    const V3 view = mk(P.basic[32], P.basic[33], P.basic[34]);
+    const V3 focal = view + dir * P.focal_length;
+    const float angle = rand01(p.rng) * 2.0f * kPi;
+    const float rr = fsqrt(rand01(p.rng));
+    float sn, cs;
+    sincos_(angle, sn, cs);
+    const float hk = P.aperture_diameter * 0.5f;
+    const float offx = hk * (cs * rr), offy = hk * (sn * rr);
+    p.o = mk(mat_row(IV, 0, offx, offy, 0.0f, 1.0f), mat_row(IV, 1, offx, offy, 0.0f, 1.0f), mat_row(IV, 2, offx, offy, 0.0f, 1.0f));
+    p.d = normalize(focal - p.o);
+    p.thr = mk(1.0f, 1.0f, 1.0f);
+    p.rad = mk(0.0f, 0.0f, 0.0f);
+    p.depth = 0;
+}
+
+// pt:140-180 — one iteration of the bounce loop for one lane.  Returns true while the sample continues.
+template <class Scene>
+__device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, Path& p, unsigned long long* stats)
+{
+    float T;
+    int prim;
+    bool inside;
+    trace(sc, p.o, p.d, T, prim, inside);
+    if (stats) atomicAdd(stats + 1, 1ull);
+    if (T != kFloatMax) {
+        if (stats) atomicAdd(stats + 2, 1ull);
+        const V3 pos = p.o + p.d * T;
+        V3 n = surface_normal(sc, prim, pos);
+        const float4 m0 = sc.mat(prim, 0), m1 = sc.mat(prim, 1), m2 = sc.mat(prim, 2), m3 = sc.mat(prim, 3);
+        const float ior = m3.y;
+        if (inside) {                                        // pt:145-149 Beer's law
+            n = -n;
+            p.thr = p.thr * mk(exp_(-m2.x * T), exp_(-m2.y * T), exp_(-m2.z * T));
+        }
+        // ---- BSDF, pt:184-224
+        float spec = m0.w, refr = m2.w;
+        if (spec > 0.0f) {
+            const float n1 = inside ? ior : 1.0f, n2 = !inside ? ior : 1.0f;
+            float r0 = fdiv(n1 - n2, n1 + n2);
+            r0 *= r0;
+            const float fres = r0 + (1.0f - r0) * pow5(1.0f - dot(-p.d, n));   // pt:359-364
+            spec = mixf(spec, 1.0f, fres);
+            const float diffuse_chance = 1.0f - spec - refr;
+            refr = 1.0f - spec - diffuse_chance;
+        }
+        const V3 diffuse = cosine_hemisphere(n, p.rng);
+        const float roll = rand01(p.rng);
+        bool refractive = false;
+        float prob;
+        V3 nd;
+        if (spec > roll) {
+            nd = normalize(mix(reflect(p.d, n), diffuse, m1.w * m1.w));
+            prob = spec;
+        } else if (spec + refr > roll) {
+            const V3 rdir = refract(p.d, n, inside ? fdiv(ior, 1.0f) : fdiv(1.0f, ior));
+            const V3 hemi = cosine_hemisphere(-n, p.rng);
+            nd = normalize(mix(rdir, hemi, m3.x * m3.x));
+            prob = refr;
+            refractive = true;
+        } else {
+            nd = diffuse;
+            prob = 1.0f - spec - refr;
+        }
+        p.d = nd;
+        p.o = pos + nd * kEps;
+        prob = fmax_(prob, kEps);
+        // ---- pt:156-173
+        p.rad = p.rad + mk(m1.x, m1.y, m1.z) * p.thr;
+        if (!refractive) p.thr = p.thr * mk(m0.x, m0.y, m0.z);
+        p.thr = p.thr * rcp(prob);
+        const float q = fmax_(p.thr.x, fmax_(p.thr.y, p.thr.z));
+        if (rand01(p.rng) > q) return false;
+        p.thr = p.thr * rcp(q);
+        return ++p.depth < P.ray_depth;
+    }
+    p.rad = p.rad + env_lookup(P.env, P.env_size, p.d) * p.thr;          // pt:177
+    return false;
+}
+
+// pt:125-129 — mean over SPP, running mean over frames, store.  Frame 0 does not read the image: the reference
+// multiplies the stale value by exactly 0 there (mix(x, y, 1.0)), so a zero stands in for it.
+__device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p)
+{
+    const V3 irr = p.irr * rcp((float)P.spp);
+    float4* px = P.image + (size_t)p.lrow * P.width + p.px;
+    V3 last = mk(0.0f, 0.0f, 0.0f);
+    if (P.frame > 0) {
+        const float4 l = *px;
+        last = mk(l.x, l.y, l.z);
+    }
+    const float a = fdiv(1.0f, (float)(P.frame + 1));
+    const V3 out = mix(last, irr, a);
+    *px = make_float4(out.x, out.y, out.z, 1.0f);
+}
+
+// local row -> global y for the stripe partition
+__device__ __forceinline__ int global_row(const RenderParams& P, int lrow)
+{
+    const int ls = lrow / P.stripe_rows;
+    return (ls * P.world + P.rank) * P.stripe_rows + (lrow - ls * P.stripe_rows);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// TMA bulk copy helpers (cp.async.bulk global -> shared, completion on an mbarrier).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PTB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PTB_DONE;\n"
+        "bra PTB_WAIT;\n"
+        "PTB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The megakernel.  Work item = one pixel (all its SPP samples, RNG stream intact).  Work index -> pixel through
+// 8x4 tiles so a freshly filled warp starts on a compact footprint.
+template <bool kStats>
+__global__ void __launch_bounds__(kMegaThreads, 2) megakernel(const __grid_constant__ RenderParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    float4* sblock = reinterpret_cast<float4*>(smem_raw);
+
+    // ---- stage the packed scene: one elected thread arms the barrier and issues the bulk copies
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)P.block_bytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.scene);
+        for (int off = 0; off < P.block_bytes; off += 32768) {
+            const int n = min(32768, P.block_bytes - off);
+            tma_bulk_g2s(smem_raw + off, src + off, (uint32_t)n, &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    PackedScene sc;
+    sc.base = sblock; sc.nS = P.n_spheres; sc.nC = P.n_cuboids;
+    sc.off_aux = P.off_aux; sc.off_cmin = P.off_cmin; sc.off_cmax = P.off_cmax; sc.off_mat = P.off_mat;
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int tiles_x = (P.width + 7) >> 3;
+    const int tiles_y = (P.local_rows + 3) >> 2;
+    const unsigned total = (unsigned)(tiles_x * tiles_y) * 32u;
+    unsigned long long* stats = kStats ? P.stats : nullptr;
+
+    Path p;
+    bool alive = false;         // lane owns an unfinished pixel
+    bool fresh = false;         // lane needs a primary ray (new pixel or next sample)
+    bool exhausted = false;     // warp-uniform: the work counter ran past the end
+
+    while (true) {
+        // ---- refill dead lanes with new pixels (ballot + prefix popcount slot assignment)
+        const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+        if (dead != 0u && !exhausted) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(P.counters, (unsigned)__popc(dead));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned)__popc(dead) >= total) exhausted = true;
+            if (!alive) {
+                const unsigned idx = base + (unsigned)__popc(dead & lt_mask);
+                if (idx < total) {
+                    const unsigned tile = idx >> 5, in = idx & 31u;
+                    const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile - (unsigned)ty * (unsigned)tiles_x);
+                    const int x = tx * 8 + (int)(in & 7u), lr = ty * 4 + (int)(in >> 3);
+                    if (x < P.width && lr < P.local_rows) {
+                        p.px = x; p.lrow = lr; p.py = global_row(P, lr);
+                        if (p.py < P.height) {
+                            p.rng = ((uint32_t)p.px * 1973u + (uint32_t)p.py * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
+                            p.irr = mk(0.0f, 0.0f, 0.0f);
+                            p.sample = 0;
+                            alive = true;
+                            fresh = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) {
+            if (exhausted) break;
+            continue;   // this batch held only padding pixels; fetch again
+        }
+        if (alive && fresh) {
+            primary_ray(P, p);
+            fresh = false;
+            if (kStats) atomicAdd(stats, 1ull);
+        }
+        // ---- one bounce for every live lane
+        if (alive) {
+            const bool go = P.ray_depth > 0 ? bounce(P, sc, p, stats) : false;
+            if (!go) {
+                p.irr = p.irr + p.rad;                // pt:123
+                if (++p.sample < P.spp) fresh = true;
+                else { finish_pixel(P, p); alive = false; }
+            }
+        }
+    }
+
+    // ---- last CTA out re-arms the counters for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(P.counters + 1, 1u) == gridDim.x - 1) { P.counters[0] = 0u; P.counters[1] = 0u; __threadfence(); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The labelled GL-compute proxy: the reference's own launch shape (8x8 groups, one invocation per pixel,
+// ceil(W/8) x ceil(H/8) groups — PathTracer.cs:121, pt:8) reading the raw std140 UBO bytes.  Baseline only.
+__global__ void __launch_bounds__(64) naive_kernel(const __grid_constant__ RenderParams P)
+{
+    const int x = blockIdx.x * 8 + threadIdx.x, lr = blockIdx.y * 8 + threadIdx.y;
+    if (x >= P.width || lr >= P.local_rows) return;      // GL discards out-of-bounds image stores
+    RawScene sc;
+    sc.ubo = P.raw_objects; sc.nS = P.n_spheres; sc.nC = P.n_cuboids; sc.max_spheres = P.max_spheres;
+    Path p;
+    p.px = x; p.lrow = lr; p.py = global_row(P, lr);
+    if (p.py >= P.height) return;
+    p.rng = ((uint32_t)p.px * 1973u + (uint32_t)p.py * 9277u + (uint32_t)P.frame * 2699u) | 1u;
+    p.irr = mk(0.0f, 0.0f, 0.0f);
+    for (p.sample = 0; p.sample < P.spp; ++p.sample) {
+        primary_ray(P, p);
+        if (P.ray_depth > 0)
+            while (bounce(P, sc, p, nullptr)) {}
+        p.irr = p.irr + p.rad;
+    }
+    finish_pixel(P, p);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Scene repack: std140 GameObjectsUBO bytes -> SoA block (run once per scene edit, one thread per primitive).
+__global__ void pack_scene_kernel(const unsigned char* __restrict__ ubo, int max_spheres, int nS, int nC, float4* __restrict__ block,
+                                  int off_aux, int off_cmin, int off_cmax, int off_mat)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nS) {
+        const float4* s = reinterpret_cast<const float4*>(ubo + (size_t)i * kSphereStride);
+        const float4 g = s[0];
+        block[i] = make_float4(g.x, g.y, g.z, g.w * g.w);
+        reinterpret_cast<float*>(block + off_aux)[i] = rcp(g.w);
+        for (int k = 0; k < 4; ++k) block[off_mat + i * 4 + k] = s[1 + k];
+    } else if (i < nS + nC) {
+        const int c = i - nS;
+        const float4* s = reinterpret_cast<const float4*>(ubo + (size_t)max_spheres * kSphereStride + (size_t)c * kCuboidStride);
+        block[off_cmin + c] = s[0];
+        block[off_cmax + c] = s[1];
+        for (int k = 0; k < 4; ++k) block[off_mat + i * 4 + k] = s[2 + k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Seamless cubemap padding.  Texel centres live on an integer lattice: face f, texel (i,j) -> coordinates
+// a = 2i+1-N, b = 2j+1-N on the face's (sc, tc) axes and +-N on its major axis (GL 4.5 Table 8.19).
+struct FaceAxes { int maj, msgn, sax, ssgn, tax, tsgn; };
+__device__ __forceinline__ FaceAxes face_axes(int f)
+{
+    switch (f) {
+    case 0: return {0, 1, 2, -1, 1, -1};
+    case 1: return {0, -1, 2, 1, 1, -1};
+    case 2: return {1, 1, 0, 1, 2, 1};
+    case 3: return {1, -1, 0, 1, 2, -1};
+    case 4: return {2, 1, 0, 1, 1, -1};
+    default: return {2, -1, 0, -1, 1, -1};
+    }
+}
+__device__ __forceinline__ float4 lattice_texel(const float4* __restrict__ faces, int N, const int q[3])
+{
+    int axis = 0;
+    if (q[1] == N || q[1] == -N) axis = 1;
+    if (q[2] == N || q[2] == -N) axis = 2;
+    if (q[0] == N || q[0] == -N) axis = 0;
+    const int f = 2 * axis + (q[axis] < 0 ? 1 : 0);
+    const FaceAxes A = face_axes(f);
+    const int a = A.ssgn * q[A.sax], b = A.tsgn * q[A.tax];
+    return faces[((size_t)f * N + (b + N - 1) / 2) * N + (a + N - 1) / 2];
+}
+__global__ void pad_cubemap_kernel(const float4* __restrict__ faces, int N, float4* __restrict__ padded)
+{
+    const int P = N + 2;
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x, pj = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (pi >= P || pj >= P) return;
+    const int i = pi - 1, j = pj - 1;
+    const bool oi = (i < 0 || i >= N), oj = (j < 0 || j >= N);
+    float4 out;
+    if (!oi && !oj) {
+        out = faces[((size_t)f * N + j) * N + i];
+    } else {
+        const FaceAxes A = face_axes(f);
+        if (oi && oj) {
+            // beyond a corner: mean of the three texels meeting there, summed in face order
+            const int ci = i < 0 ? 0 : N - 1, cj = j < 0 ? 0 : N - 1;
+            int c[3];
+            c[A.maj] = A.msgn * N; c[A.sax] = A.ssgn * (2 * ci + 1 - N); c[A.tax] = A.tsgn * (2 * cj + 1 - N);
+            float4 tex[6];
+            bool have[6] = {false, false, false, false, false, false};
+            for (int ax = 0; ax < 3; ++ax) {
+                int q[3];
+                for (int k = 0; k < 3; ++k) { const int sg = c[k] < 0 ? -1 : 1; q[k] = (k == ax) ? sg * N : sg * (N - 1); }
+                const int ff = 2 * ax + (q[ax] < 0 ? 1 : 0);
+                tex[ff] = lattice_texel(faces, N, q);
+                have[ff] = true;
+            }
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+            bool first = true;
+            for (int ff = 0; ff < 6; ++ff)
+                if (have[ff]) {
+                    if (first) { sx = tex[ff].x; sy = tex[ff].y; sz = tex[ff].z; first = false; }
+                    else { sx = sx + tex[ff].x; sy = sy + tex[ff].y; sz = sz + tex[ff].z; }
+                }
+            out = make_float4(sx * 0.333333343f, sy * 0.333333343f, sz * 0.333333343f, 1.0f);
+        } else {
+            // beyond one edge: fold over the shared edge onto the adjacent face
+            int q[3];
+            q[A.maj] = A.msgn * (N - 1);
+            const int a = 2 * i + 1 - N, b = 2 * j + 1 - N;
+            q[A.sax] = A.ssgn * (oi ? (a < 0 ? -N : N) : a);
+            q[A.tax] = A.tsgn * (oj ? (b < 0 ? -N : N) : b);
+            out = lattice_texel(faces, N, q);
+        }
+    }
+    padded[((size_t)f * P + pj) * P + pi] = out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Atmosphere cubemap producer: res/shaders/AtmosphericScattering/compute.glsl (cited as at:LINE).
+struct AtmosParams {
+    float ubo[16 * 7];   // InvProjection + InvView[6]  (at:12-16)
+    float light[3];      // lightPos (at:23)
+    float intensity;     // lightIntensity (at:25)
+    int i_steps, j_steps, size;
+};
+__device__ __forceinline__ void rsi(V3 r0, V3 rd, float sr, float& x, float& y)   // at:58-71
+{
+    const float a = dot(rd, rd);
+    const float b = 2.0f * dot(rd, r0);
+    const float c = dot(r0, r0) - (sr * sr);
+    const float d = (b * b) - 4.0f * a * c;
+    if (d < 0.0f) { x = 1e5f; y = -1e5f; return; }
+    const float sq = fsqrt(d);
+    x = fdiv(-b - sq, 2.0f * a);
+    y = fdiv(-b + sq, 2.0f * a);
+}
+__global__ void atmosphere_kernel(const __grid_constant__ AtmosParams A, float4* __restrict__ faces)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (x >= A.size || y >= A.size) return;                                     // at:34
+    const float isz = rcp((float)A.size);
+    const float nx = (float)x * isz * 2.0f - 1.0f, ny = (float)y * isz * 2.0f - 1.0f;   // at:37
+    const float* IP = A.ubo;
+    const float* IV = A.ubo + 16 + 16 * f;
+    const float ex = mat_row(IP, 0, nx, ny, -1.0f, 0.0f), ey = mat_row(IP, 1, nx, ny, -1.0f, 0.0f);
+    V3 r = normalize(mk(mat_row(IV, 0, ex, ey, -1.0f, 0.0f), mat_row(IV, 1, ex, ey, -1.0f, 0.0f), mat_row(IV, 2, ex, ey, -1.0f, 0.0f)));
+    // at:41-53 constants
+    const V3 r0 = mk(0.0f, 6376e3f, 0.0f);
+    const float rPlanet = 6371e3f, rAtmos = 6471e3f, kMie = 21e-6f, shRlh = 8e3f, shMie = 1.2e3f, g = 0.758f;
+    const V3 kRlh = mk(5.5e-6f, 13.0e-6f, 22.4e-6f);
+    // at:73-159
+    const V3 pSun = normalize(mk(A.light[0], A.light[1], A.light[2]));
+    r = normalize(r);
+    V3 col = mk(0.0f, 0.0f, 0.0f);
+    float px_, py_;
+    rsi(r0, r, rAtmos, px_, py_);
+    if (!(px_ > py_)) {
+        float qx, qy;
+        rsi(r0, r, rPlanet, qx, qy);
+        py_ = fmin_(py_, qx);
+        const float iStep = fdiv(py_ - px_, (float)A.i_steps);
+        float iTime = 0.0f, iOdR = 0.0f, iOdM = 0.0f;
+        V3 totR = mk(0.0f, 0.0f, 0.0f), totM = mk(0.0f, 0.0f, 0.0f);
+        const float mu = dot(r, pSun), mumu = mu * mu, gg = g * g;
+        const float pR = fdiv(3.0f, 16.0f * kPi) * (1.0f + mumu);
+        const float pM = fdiv(fdiv(3.0f, 8.0f * kPi) * ((1.0f - gg) * (mumu + 1.0f)), pow15(1.0f + gg - 2.0f * mu * g) * (2.0f + gg));
+        const float ishR = rcp(shRlh), ishM = rcp(shMie);
+        for (int i = 0; i < A.i_steps; ++i) {
+            const V3 iPos = r0 + r * (iTime + iStep * 0.5f);
+            const float iH = length(iPos) - rPlanet;
+            const float odR = exp_(-iH * ishR) * iStep;
+            const float odM = exp_(-iH * ishM) * iStep;
+            iOdR += odR;
+            iOdM += odM;
+            float jx, jy;
+            rsi(iPos, pSun, rAtmos, jx, jy);
+            const float jStep = fdiv(jy, (float)A.j_steps);
+            float jTime = 0.0f, jOdR = 0.0f, jOdM = 0.0f;
+            for (int j = 0; j < A.j_steps; ++j) {
+                const V3 jPos = iPos + pSun * (jTime + jStep * 0.5f);
+                const float jH = length(jPos) - rPlanet;
+                jOdR += exp_(-jH * ishR) * jStep;
+                jOdM += exp_(-jH * ishM) * jStep;
+                jTime += jStep;
+            }
+            const float m = kMie * (iOdM + jOdM);
+            const float rl = iOdR + jOdR;
+            const V3 attn = mk(exp_(-(m + kRlh.x * rl)), exp_(-(m + kRlh.y * rl)), exp_(-(m + kRlh.z * rl)));
+            totR = totR + attn * odR;
+            totM = totM + attn * odM;
+            iTime += iStep;
+        }
+        col = mk(A.intensity * (pR * kRlh.x * totR.x + pM * kMie * totM.x),
+                 A.intensity * (pR * kRlh.y * totR.y + pM * kMie * totM.y),
+                 A.intensity * (pR * kRlh.z * totR.z + pM * kMie * totM.z));
+    }
+    faces[((size_t)f * A.size + y) * A.size + x] = make_float4(col.x, col.y, col.z, 1.0f);   // at:55
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// De-interleave after the per-frame gather: rank-major stripe buffers -> full row-major image.
+__global__ void deinterleave_kernel(const float4* __restrict__ gathered, float4* __restrict__ full, int width, int height,
+                                    int world, int stripe_rows, int max_local_rows)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width || y >= height) return;
+    const int stripe = y / stripe_rows, r = stripe % world, ls = stripe / world;
+    const int lrow = ls * stripe_rows + (y - stripe * stripe_rows);
+    full[(size_t)y * width + x] = gathered[((size_t)r * max_local_rows + lrow) * width + x];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Unit probes for the parity tests (ptb_debug_eval).
+__global__ void dbg_sincos_kernel(const float* in, int n, float* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float s, c; sincos_(in[i], s, c); out[2 * i] = s; out[2 * i + 1] = c; }
+}
+__global__ void dbg_exp_kernel(const float* in, int n, float* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = exp_(in[i]);
+}
+__global__ void dbg_pcg_kernel(uint32_t seed, int n, float* out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) { uint32_t s = seed; for (int i = 0; i < n; ++i) out[i] = rand01(s); }
+}
+__global__ void dbg_env_kernel(const float4* env, int N, const float* dirs, int n, float* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const V3 t = env_lookup(env, N, mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])); out[3 * i] = t.x; out[3 * i + 1] = t.y; out[3 * i + 2] = t.z; }
+}
+template <class Scene>
+__device__ __forceinline__ void dbg_trace_one(const Scene& sc, const float* rays, int i, float* out)
+{
+    const V3 o = mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    float T; int prim; bool inside;
+    trace(sc, o, d, T, prim, inside);
+    float* q = out + 12 * i;
+    const bool hit = T != kFloatMax;
+    q[0] = hit ? 1.0f : 0.0f; q[1] = T; q[2] = (hit && inside) ? 1.0f : 0.0f; q[3] = 0.0f;
+    for (int k = 4; k < 12; ++k) q[k] = 0.0f;
+    if (hit) {
+        const V3 pos = o + d * T;
+        const V3 n = surface_normal(sc, prim, pos);
+        q[4] = pos.x; q[5] = pos.y; q[6] = pos.z; q[7] = n.x; q[8] = n.y; q[9] = n.z;
+        q[10] = sc.mat(prim, 0).x; q[11] = sc.mat(prim, 1).x;
+    }
+}
+__global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const float* rays, int n, float* out, int use_raw)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (!use_raw) {
+        const float4* src = P.scene;
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        for (int k = threadIdx.x; k < P.block_bytes / 16; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (use_raw) {
+        RawScene sc; sc.ubo = P.raw_objects; sc.nS = P.n_spheres; sc.nC = P.n_cuboids; sc.max_spheres = P.max_spheres;
+        dbg_trace_one(sc, rays, i, out);
+    } else {
+        PackedScene sc; sc.base = reinterpret_cast<const float4*>(smem_raw); sc.nS = P.n_spheres; sc.nC = P.n_cuboids;
+        sc.off_aux = P.off_aux; sc.off_cmin = P.off_cmin; sc.off_cmax = P.off_cmax; sc.off_mat = P.off_mat;
+        dbg_trace_one(sc, rays, i, out);
+    }
+}
+__global__ void dbg_arith_kernel(const float* in, int n, float* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float a = in[2 * i], b = in[2 * i + 1];
+        out[4 * i] = fmin_(a, b); out[4 * i + 1] = fmax_(a, b); out[4 * i + 2] = rcp(a); out[4 * i + 3] = fsqrt(b);
+    }
+}
+
+} // namespace ptb

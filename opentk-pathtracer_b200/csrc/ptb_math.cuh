@@ -1,0 +1,129 @@
+// ptb_math.cuh — fp32 evaluation of the GLSL built-ins the reference shaders use, for sm_100a.
+//
+// The reference's integrator (res/shaders/PathTracing/compute.glsl) is written against GLSL built-ins whose
+// precision is implementation-defined.  This header fixes one evaluation (DESIGN.md "evaluation model"):
+// IEEE binary32 everywhere, no implicit contraction (the TU is compiled with -fmad=false), explicit fma only
+// inside dot / mat*vec / mix / the polynomial kernels, a/b = a * rcp.rn(b), min/max = FMNMX.
+// Every Monte-Carlo path is chaotic, so a 1-ulp difference flips branches; fixing the evaluation is what makes
+// matched-seed parity testable at all.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptb {
+
+struct V3 { float x, y, z; };
+
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+
+__device__ __forceinline__ float rcp(float b) { return __frcp_rn(b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * __frcp_rn(b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }   // FMNMX: NaN loses, -0 < +0
+__device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float stepf(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+__device__ __forceinline__ float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+__device__ __forceinline__ float mixf(float x, float y, float a) { return __fmaf_rn(y, a, x * (1.0f - a)); }
+__device__ __forceinline__ float pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
+__device__ __forceinline__ float pow15(float x) { return x * __fsqrt_rn(x); }
+
+__device__ __forceinline__ float dot(V3 a, V3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float length(V3 a) { return __fsqrt_rn(dot(a, a)); }
+__device__ __forceinline__ V3 normalize(V3 a) { return a * __frcp_rn(__fsqrt_rn(dot(a, a))); }
+__device__ __forceinline__ V3 mix(V3 a, V3 b, float t) { return mk(mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t)); }
+
+// GLSL reflect: I - 2*dot(N,I)*N
+__device__ __forceinline__ V3 reflect(V3 I, V3 N)
+{
+    const float k = 2.0f * dot(N, I);
+    return mk(I.x - k * N.x, I.y - k * N.y, I.z - k * N.z);
+}
+// GLSL refract: k = 1 - eta^2 (1 - dot(N,I)^2); k < 0 -> 0 vector
+__device__ __forceinline__ V3 refract(V3 I, V3 N, float eta)
+{
+    const float d = dot(N, I);
+    const float k = 1.0f - (eta * eta) * (1.0f - d * d);
+    if (k < 0.0f) return mk(0.0f, 0.0f, 0.0f);
+    const float s = eta * d + __fsqrt_rn(k);
+    return mk(eta * I.x - s * N.x, eta * I.y - s * N.y, eta * I.z - s * N.z);
+}
+
+// Row r of (M * v) for a column-major mat4 held as 16 floats: fma chain over columns 0..3.
+__device__ __forceinline__ float mat_row(const float* __restrict__ M, int r, float x, float y, float z, float w)
+{
+    float acc = M[r] * x;
+    acc = __fmaf_rn(M[4 + r], y, acc);
+    acc = __fmaf_rn(M[8 + r], z, acc);
+    acc = __fmaf_rn(M[12 + r], w, acc);
+    return acc;
+}
+
+// sin & cos by 3-term Cody-Waite reduction modulo pi/2 and degree-7 / degree-8 minimax kernels.
+__device__ __forceinline__ void sincos_(float x, float& s, float& c)
+{
+    const float magic = 12582912.0f;                     // 1.5 * 2^23
+    const float t = __fmaf_rn(x, 0.636619747f, magic);   // round(x * 2/pi) in the low mantissa bits
+    const float q = t - magic;
+    const uint32_t qi = __float_as_uint(t);
+    float r = __fmaf_rn(q, -1.57079601e+00f, x);
+    r = __fmaf_rn(q, -3.13916473e-07f, r);
+    r = __fmaf_rn(q, -5.39030253e-15f, r);
+    const float r2 = r * r;
+    float ps = __fmaf_rn(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = __fmaf_rn(ps, r2, -1.6666654611e-1f);
+    const float sn = __fmaf_rn(r * r2, ps, r);
+    float pc = __fmaf_rn(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = __fmaf_rn(pc, r2, 4.166664568298827e-2f);
+    const float cs = __fmaf_rn(r2 * r2, pc, __fmaf_rn(r2, -0.5f, 1.0f));
+    const bool swap = qi & 1u;
+    float so = swap ? cs : sn;
+    float co = swap ? sn : cs;
+    if (qi & 2u) so = -so;
+    if ((qi + 1u) & 2u) co = -co;
+    s = so;
+    c = co;
+}
+
+// exp(x) = 2^k * e^r, k = round(x log2 e), r = x - k ln2 (two-term), degree-5 kernel on r^2, two-step scaling.
+__device__ __forceinline__ float exp_(float x)
+{
+    if (x != x) return x + x;
+    if (x > 88.7228394f) return __uint_as_float(0x7f800000u);
+    if (x < -103.972084f) return 0.0f;
+    const float magic = 12582912.0f;
+    const float t = __fmaf_rn(x, 1.44269502f, magic);
+    const float kf = t - magic;
+    float r = __fmaf_rn(kf, -6.93145752e-1f, x);
+    r = __fmaf_rn(kf, -1.42860677e-6f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float e = __fmaf_rn(p, r * r, r) + 1.0f;
+    const int k = __float2int_rz(kf);
+    const int k1 = k >> 1;
+    const int k2 = k - k1;
+    return (e * __uint_as_float((uint32_t)(k1 + 127) << 23)) * __uint_as_float((uint32_t)(k2 + 127) << 23);
+}
+
+// compute.glsl:334-344 — PCG-RXS-M-XS hash stream; float(h) / 2^32 (can return exactly 1.0).
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t& seed)
+{
+    seed = seed * 747796405u + 2891336453u;
+    const uint32_t word = ((seed >> ((seed >> 28u) + 4u)) ^ seed) * 277803737u;
+    return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ float rand01(uint32_t& seed)
+{
+    return __uint2float_rn(pcg_hash(seed)) * 2.3283064365386963e-10f;   // * 2^-32, exact
+}
+
+} // namespace ptb

@@ -1,0 +1,186 @@
+/*
+ * oracle/glsl_model.h — TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * The "GLSL evaluation model": how this oracle evaluates the GLSL 4.50 built-ins
+ * and operators the reference shaders use
+ *   res/shaders/PathTracing/compute.glsl            (the integrator)
+ *   res/shaders/AtmosphericScattering/compute.glsl  (the environment producer)
+ * GLSL leaves the precision of these implementation-defined (GLSL 4.50 §4.7.1),
+ * and nothing of the reference can execute in the build container, so the oracle
+ * fixes ONE admissible evaluation, in IEEE-754 binary32, that a CPU (gcc,
+ * -ffp-contract=off -mfma) and a GPU (nvcc, -fmad=false) reproduce bit for bit.
+ * The product (csrc/ptb_math.cuh) is a separate, hand-written CUDA implementation
+ * of the same model; tests/ compare the two bitwise.
+ *
+ *   a+b a-b a*b        IEEE RNE, denormals kept, never contracted
+ *   a/b                a * rcp(b), rcp = correctly rounded 1/b   (GLSL: 2.5 ULP)
+ *   sqrt               correctly rounded
+ *   dot(a,b)           fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))      (FMUL,FFMA,FFMA)
+ *   mat4*vec4          per row: fma chain over columns 0,1,2,3
+ *   length / normalize sqrt(dot(v,v)) ; v * rcp(sqrt(dot(v,v)))  (0 -> NaN)
+ *   mix(x,y,a)         fma(y, a, x*(1-a))
+ *   reflect / refract  GLSL 4.50 §8.5 formulas, evaluated literally
+ *   pow(x,5.0)         ((x*x)*(x*x))*x   total, sign preserving   
+ *   pow(x,1.5)         x*sqrt(x)
+ *   min/max            IEEE minNum/maxNum (NaN loses), -0 < +0      (FMNMX)
+ *   step, sign, abs    GLSL definitions
+ *   sin, cos, exp      the fixed polynomial algorithms below
+ *   float(uint)        RNE;  f2i = truncation, NaN -> 0, saturating
+ * PARITY UNPINNED: the reference has no tests, fixtures or golden vectors for
+ * this path and cannot run here; the pins are the integer
+ * KATs in tests/golden/ derived from compute.glsl:106,334-344.
+ */
+#ifndef PTO_GLSL_MODEL_H
+#define PTO_GLSL_MODEL_H
+
+#include <stdint.h>
+#include <string.h>
+
+typedef struct { float x, y, z; } vec3;
+typedef struct { float x, y, z, w; } vec4;
+
+static inline uint32_t g_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float g_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static inline float g_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+static inline float g_rcp(float b) { return 1.0f / b; }
+static inline float g_div(float a, float b) { return a * g_rcp(b); }
+static inline float g_sqrt(float a) { return __builtin_sqrtf(a); }
+static inline float g_abs(float a) { return g_float(g_bits(a) & 0x7fffffffu); }
+static inline int g_isnan(float a) { return a != a; }
+
+/* minNum / maxNum with -0 < +0 (what FMNMX does). */
+static inline float g_min(float a, float b)
+{
+    if (g_isnan(a)) return b;
+    if (g_isnan(b)) return a;
+    if (a == b) return (g_bits(a) >> 31) ? a : b;
+    return b < a ? b : a;
+}
+static inline float g_max(float a, float b)
+{
+    if (g_isnan(a)) return b;
+    if (g_isnan(b)) return a;
+    if (a == b) return (g_bits(a) >> 31) ? b : a;
+    return a < b ? b : a;
+}
+static inline float g_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+static inline float g_sign(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }
+static inline float g_mix(float x, float y, float a) { return g_fma(y, a, x * (1.0f - a)); }
+static inline float g_pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
+static inline float g_pow15(float x) { return x * g_sqrt(x); }
+
+/* float -> int: truncate; NaN -> 0; saturate to +-2^30 (indices are clamped by callers anyway). */
+static inline int g_f2i(float x)
+{
+    if (g_isnan(x)) return 0;
+    if (x >= 1073741824.0f) return 1073741824;
+    if (x <= -1073741824.0f) return -1073741824;
+    return (int)x;
+}
+/* floor as float, via truncation fix-up (|x| < 2^30 assumed by callers; otherwise x itself). */
+static inline float g_floor(float x)
+{
+    if (g_isnan(x)) return x;
+    if (!(g_abs(x) < 1073741824.0f)) return x;
+    float t = (float)(int)x;
+    return t > x ? t - 1.0f : t;
+}
+
+/* ---- vec3 helpers ---------------------------------------------------------------- */
+static inline vec3 v3(float x, float y, float z) { vec3 r = { x, y, z }; return r; }
+static inline vec3 v_add(vec3 a, vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline vec3 v_sub(vec3 a, vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline vec3 v_mul(vec3 a, vec3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline vec3 v_scale(vec3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+static inline vec3 v_neg(vec3 a) { return v3(-a.x, -a.y, -a.z); }
+static inline float v_dot(vec3 a, vec3 b) { return g_fma(a.z, b.z, g_fma(a.y, b.y, a.x * b.x)); }
+static inline float v_length(vec3 a) { return g_sqrt(v_dot(a, a)); }
+static inline vec3 v_normalize(vec3 a) { return v_scale(a, g_rcp(g_sqrt(v_dot(a, a)))); }
+static inline vec3 v_mix(vec3 a, vec3 b, float t)
+{
+    return v3(g_mix(a.x, b.x, t), g_mix(a.y, b.y, t), g_mix(a.z, b.z, t));
+}
+/* reflect(I,N) = I - 2*dot(N,I)*N */
+static inline vec3 v_reflect(vec3 I, vec3 N)
+{
+    float k = 2.0f * v_dot(N, I);
+    return v3(I.x - k * N.x, I.y - k * N.y, I.z - k * N.z);
+}
+/* refract(I,N,eta): k = 1 - eta*eta*(1 - dot(N,I)^2); k<0 -> 0; else eta*I - (eta*dot(N,I)+sqrt(k))*N */
+static inline vec3 v_refract(vec3 I, vec3 N, float eta)
+{
+    float d = v_dot(N, I);
+    float k = 1.0f - (eta * eta) * (1.0f - d * d);
+    if (k < 0.0f) return v3(0.0f, 0.0f, 0.0f);
+    float s = eta * d + g_sqrt(k);
+    return v3(eta * I.x - s * N.x, eta * I.y - s * N.y, eta * I.z - s * N.z);
+}
+/* (M * v).row r for a column-major mat4 stored as 16 floats (GLSL std140 / OpenTK row-major bytes). */
+static inline float m4_row(const float *M, int r, float x, float y, float z, float w)
+{
+    float acc = M[0 + r] * x;
+    acc = g_fma(M[4 + r], y, acc);
+    acc = g_fma(M[8 + r], z, acc);
+    acc = g_fma(M[12 + r], w, acc);
+    return acc;
+}
+
+/* ---- transcendental algorithms ---------------------------------------------------- */
+#define G_MAGIC 12582912.0f /* 1.5 * 2^23: adding it rounds to an integer (RNE) */
+
+/* sin and cos of x by Cody-Waite reduction to [-pi/4, pi/4] (three-term pi/2) and the
+ * classic single-precision minimax kernels.  Exact same operation sequence on both sides. */
+static inline void g_sincos(float x, float *s_out, float *c_out)
+{
+    float t = g_fma(x, 0.636619747f, G_MAGIC);       /* x * 2/pi, rounded to integer */
+    float q = t - G_MAGIC;
+    uint32_t qi = g_bits(t);                          /* low mantissa bits hold q mod 4 */
+    float r = g_fma(q, -1.57079601e+00f, x);          /* pi/2 split: hi */
+    r = g_fma(q, -3.13916473e-07f, r);                /* mid */
+    r = g_fma(q, -5.39030253e-15f, r);                /* lo */
+    float r2 = r * r;
+    /* sin kernel: r + r*r2*(S1 + r2*(S2 + r2*S3)) */
+    float ps = g_fma(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = g_fma(ps, r2, -1.6666654611e-1f);
+    float sn = g_fma(r * r2, ps, r);
+    /* cos kernel: 1 - r2/2 + r2*r2*(C1 + r2*(C2 + r2*C3)) */
+    float pc = g_fma(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = g_fma(pc, r2, 4.166664568298827e-2f);
+    float cs = g_fma(r2 * r2, pc, g_fma(r2, -0.5f, 1.0f));
+    float s = (qi & 1u) ? cs : sn;
+    float c = (qi & 1u) ? sn : cs;
+    if (qi & 2u) s = -s;
+    if ((qi + 1u) & 2u) c = -c;
+    *s_out = s;
+    *c_out = c;
+}
+static inline float g_sin(float x) { float s, c; g_sincos(x, &s, &c); return s; }
+static inline float g_cos(float x) { float s, c; g_sincos(x, &s, &c); return c; }
+
+/* exp(x): k = rint(x*log2(e)); r = x - k*ln2 (two-term); e^r = 1 + r + r^2*P(r); scale by 2^k in two steps. */
+static inline float g_exp(float x)
+{
+    if (g_isnan(x)) return x + x;
+    if (x > 88.7228394f) return g_float(0x7f800000u);
+    if (x < -103.972084f) return 0.0f;
+    float t = g_fma(x, 1.44269502f, G_MAGIC);
+    float kf = t - G_MAGIC;
+    float r = g_fma(kf, -6.93145752e-1f, x);
+    r = g_fma(kf, -1.42860677e-6f, r);
+    float p = 1.9875691500e-4f;
+    p = g_fma(p, r, 1.3981999507e-3f);
+    p = g_fma(p, r, 8.3334519073e-3f);
+    p = g_fma(p, r, 4.1665795894e-2f);
+    p = g_fma(p, r, 1.6666665459e-1f);
+    p = g_fma(p, r, 5.0000001201e-1f);
+    float e = g_fma(p, r * r, r) + 1.0f;
+    int k = (int)kf;
+    int k1 = k >> 1;              /* arithmetic shift: floor(k/2) */
+    int k2 = k - k1;
+    float s1 = g_float((uint32_t)(k1 + 127) << 23);
+    float s2 = g_float((uint32_t)(k2 + 127) << 23);
+    return (e * s1) * s2;
+}
+
+#endif
