@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s of the path-tracing pass on the default demo scene at 1920x1080 (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one PathTracer.Render() of the whole frame (one dispatch in the reference, PathTracer.cs:114-129): 1920*1080
+pixels x SPP 1 = 2 073 600 samples, rayDepth 13, focal 20, aperture 0.14, default camera, 256^2 atmosphere cubemap.
+At N > 1 the same frame is cut into interleaved 8-row stripes (one process per GPU), and every step ends with the one
+exchange the path has: a gather of the stripe buffers to rank 0 + de-interleave.  Fixed total work => "strong" scaling.
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launching stream, inputs resident in HBM, L2
+flushed before every timed step; `e2e` goes through the same public API with host buffers: the per-frame camera UBO
+upload the C# host does (MainWindow.cs:131-132) and a read-back of the accumulation image into pinned host memory.
+`--impl reference` times the CPU oracle (the reference has no CPU path and cannot run without .NET + OpenGL 4.5; the
+oracle is the restatement of its shader) on all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+RAY_DEPTH, SPP, FOCAL, APERTURE = 13, 1, 20.0, 0.14
+WORKLOAD = "default demo scene (48 spheres + 7 cuboids), 1920x1080, SPP 1 per frame, rayDepth 13, 256^2 atmosphere env (BASELINE configs[1])"
+STRIPE_ROWS = 8
+L2_FLUSH_BYTES = 256 << 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_summary():
+    """Per-launch DRAM traffic of the megakernel from the committed `ncu --set full` capture (profiles/), if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return {}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "n": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ================================================================================================ reference arm
+def run_reference(args, rank, world):
+    """The reference's algorithm on the host CPUs: the oracle (kind "port"), all threads, a bounded sample per step."""
+    if rank != 0:
+        return
+    import ptb200
+    from oracle import oracle as O
+    sc = ptb200.scene
+    threads = O.max_threads()
+    env = O.atmosphere(256, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 50, 15)
+    scene, cam = sc.load_default_scene(), sc.default_camera()
+    basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+    img = np.zeros((H, W, 4), np.float32)
+    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7)
+    # calibrate on one full frame, then bound the per-step sample so warmup + steps stay under ~150 s
+    t = time.perf_counter()
+    O.render(img, basic, ubo, env, frame=0, **kw)
+    full_s = time.perf_counter() - t
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_bands = 45                                  # 45 bands of 24 rows
+    use = max(1, min(n_bands, int(n_bands * budget / full_s)))
+    sel = np.linspace(0, n_bands - 1, use).round().astype(int)       # bands spread over sky, spheres and floor
+    bands = [(int(b) * 24, int(b) * 24 + 24) for b in sorted(set(sel.tolist()))]
+    px_per_step = sum(b[1] - b[0] for b in bands) * W
+
+    def step(frame):
+        for b in bands:
+            O.render(img, basic, ubo, env, frame=frame, rows=b, **kw)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = px_per_step * SPP * args.steps / dt / 1e6
+    sample = f"{len(bands)} of 45 24-row bands of the 1920x1080 frame per step ({px_per_step} samples/step), spread evenly top to bottom"
+    line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference_kind": "CPU oracle (C restatement of compute.glsl); the reference itself needs .NET + OpenGL 4.5, absent here"},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ================================================================================================ our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import ptb200
+    from importlib import import_module
+    D = import_module("opentk-pathtracer_b200.distributed")
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sc = ptb200.scene
+    scene, cam = sc.load_default_scene(), sc.default_camera()
+    pt = ptb200.PathTracer(None, W, H, RAY_DEPTH, SPP, FOCAL, APERTURE, device=local_rank)
+    pt.SetStream(torch.cuda.current_stream(dev).cuda_stream)
+    pt.GenerateAtmosphere(256, 50, 15, 0.5, 15.0)      # the default EnvironmentMap, produced on the GPU (MainWindow.cs:174-175)
+    pt.LoadScene(scene)
+    pt.SetCamera(cam)
+    tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev) if world > 1 else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    inv_view = sc.matrix_bytes(sc.inverted(cam.View))
+    view_pos = np.append(np.asarray(cam.Position, np.float32), np.float32(0)).tobytes()
+    rows_local = pt.Result.shape[0]
+    host_img = torch.empty((H if rank == 0 else 1, W, 4), dtype=torch.float32).pin_memory()
+    local_view = None
+    if world == 1:
+        ptr, _ = pt.ResultDevicePtr()
+        local_view = torch.as_tensor(D._DeviceBuffer(ptr, (H, W, 4)), device=dev)
+
+    def step_device():
+        if tiled is None:
+            pt.Render()
+        else:
+            tiled.render()
+            tiled.gather()
+
+    def step_e2e():
+        # what the C# host does every frame: camera UBO writes (host memory -> the library), Render(), and here the
+        # accumulation image read back into pinned host memory (the reference hands it to the display pass instead)
+        pt.BasicDataUBO.SubData(64, 64, inv_view)
+        pt.BasicDataUBO.SubData(128, 16, view_pos)
+        if tiled is None:
+            pt.Render()
+            host_img.copy_(local_view, non_blocking=True)
+        else:
+            tiled.render()
+            full = tiled.gather()
+            if rank == 0:
+                host_img.copy_(full, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, flush_l2):
+        """K steps, each bracketed by CUDA events on the launching stream; the L2 flush sits outside the events."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        wall0 = time.perf_counter()
+        for a, b in evs:
+            if flush_l2:
+                flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    launches0 = pt.KernelLaunches
+    with ClockSampler(physical_gpu_index(local_rank)) as clocks:
+        ms_total, _ = timed(step_device, args.steps, True)
+    launches = pt.KernelLaunches - launches0
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "note": "not a bench value"}), flush=True)
+        pt.Dispose()
+        return
+    # back-to-back (image stays L2-resident between frames, as in the interactive app) and the end-to-end path
+    ms_b2b, _ = timed(step_device, args.steps, False)
+    for _ in range(3):
+        step_e2e()
+    e2e_steps = max(5, min(args.steps, 200))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    # kernel-only duration for the roofline (device time of the megakernel launches alone, max over ranks)
+    pt.Render(3); pt.Synchronize()
+    pt.Render(20)
+    kern_ms = pt.LastRenderMs() / 20
+    if world > 1:
+        t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kern_ms = float(t.item())
+
+    samples_per_step = W * H * SPP
+    value = samples_per_step * args.steps / (ms_total * 1e-3) / 1e6
+    peak, peak_src = measured_peaks()
+    algo_bytes = rows_local * W * 32            # 16 B load of the previous mean + 16 B store per pixel per dispatch
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    ncu = ncu_summary()
+    line = {
+        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "flushed before every timed step (256 MiB memset outside the CUDA events)",
+                   "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); one gather to rank 0 per frame" if world > 1 else "single GPU, no collective",
+                   "kernel": "persistent megakernel (ptb::megakernel), 1 launch per frame"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "ptb::megakernel<false>",
+                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                     "note": "the pass is FP32-issue-bound, not HBM-bound: ~3.4k lane-instructions per 32 B of image traffic (DESIGN.md); see issue_*",
+                     "issue_active_pct": ncu.get("smsp_issue_active_pct"), "inst_executed_per_launch": ncu.get("inst_executed_per_launch")},
+        "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 80 + 144,
+                "d2h_bytes_per_step": W * H * 16, "steps": e2e_steps,
+                "note": "per step: InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), full RGBA32F image to pinned host memory, sync"},
+        "back_to_back": {"value": samples_per_step * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_b2b / args.steps,
+                         "note": "same steps without the L2 flush"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline(pt)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    pt.Dispose()
+
+
+def cpu_baseline(pt):
+    """The oracle on this box's host cores, a bounded sample of the same workload (rank 0, N = 1 only)."""
+    import ptb200
+    from oracle import oracle as O
+    sc = ptb200.scene
+    env = pt.ReadEnvironment()
+    scene, cam = sc.load_default_scene(), sc.default_camera()
+    basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+    img = np.zeros((H, W, 4), np.float32)
+    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7)
+    O.render(img, basic, ubo, env, frame=0, **kw)                 # warm-up / thread pool start
+    frames, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 10.0 and frames < 64:
+        frames += 1
+        O.render(img, basic, ubo, env, frame=frames, **kw)
+    dt = time.perf_counter() - t0
+    return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": O.max_threads(), "kind": "port",
+            "sample": f"{frames} full 1920x1080 frames at SPP 1 ({dt:.1f} s), OpenMP over rows"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="profiling aid: only warm-up + timed steps (for runs under ncu); prints no bench line")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        print(json.dumps({"error": "launch with torch.distributed.run --nproc-per-node N for --gpus N > 1"}))
+        sys.exit(2)
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""Pixel-tile partition across GPUs and the per-frame gather (one process per GPU, torch.distributed plumbing).
+
+The reference has no multi-GPU code.  Pixels are independent — each reads only its own previous
+value and a seed that is a function of the *global* pixel coordinate (compute.glsl:104-106,126-129) — so the
+image is cut into interleaved stripes of `stripe_rows` rows, stripe s belonging to rank s % world.  Interleaving
+(rather than one contiguous band per rank) balances sky rows (1 bounce) against interior rows (many bounces).
+Every rank keeps its stripes resident (the progressive mean is local); one collective per frame — a gather of the
+rank-major stripe buffers to rank 0 — followed by a de-interleave rebuilds the row-major image.
+
+The partition arithmetic here is the host mirror of compute_local_rows()/global_row() in csrc; tests check the two
+against each other and, on CPU with gloo at world_size 2, the whole gather path against an unpartitioned render.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DEFAULT_STRIPE_ROWS = 8
+
+
+def local_rows_of(rank: int, world: int, stripe_rows: int, height: int) -> np.ndarray:
+    """Global row index of every local row of `rank`, in local order."""
+    rows = []
+    n_stripes = (height + stripe_rows - 1) // stripe_rows
+    for s in range(rank, n_stripes, world):
+        rows.extend(range(s * stripe_rows, min((s + 1) * stripe_rows, height)))
+    return np.asarray(rows, dtype=np.int64)
+
+
+def local_row_count(rank: int, world: int, stripe_rows: int, height: int) -> int:
+    return int(local_rows_of(rank, world, stripe_rows, height).size)
+
+
+def max_local_rows(world: int, stripe_rows: int, height: int) -> int:
+    """Rank 0 always holds the most rows; every rank's buffer is padded to this so the gather is uniform."""
+    return local_row_count(0, world, stripe_rows, height)
+
+
+def deinterleave_host(gathered: np.ndarray, height: int, world: int, stripe_rows: int) -> np.ndarray:
+    """gathered: (world, max_local_rows, W, C) rank-major stripe buffers -> (height, W, C) row-major image."""
+    out = np.empty((height,) + gathered.shape[2:], dtype=gathered.dtype)
+    for r in range(world):
+        rows = local_rows_of(r, world, stripe_rows, height)
+        out[rows] = gathered[r, :rows.size]
+    return out
+
+
+def gather_stripes(local, world: int, dst: int = 0, group=None, async_op: bool = False):
+    """One collective: gather every rank's (max_local_rows, W, 4) stripe buffer to `dst`.
+    `local` is a torch tensor (CUDA with nccl, CPU with gloo).  Returns (gathered or None, work or None)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    if world == 1:
+        return local.unsqueeze(0), None
+    if rank == dst:
+        gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        work = dist.gather(local, list(gathered.unbind(0)), dst=dst, group=group, async_op=async_op)
+        return gathered, work
+    work = dist.gather(local, None, dst=dst, group=group, async_op=async_op)
+    return None, work
+
+
+class _DeviceBuffer:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class TiledPathTracer:
+    """One rank's share of a frame: a PathTracer restricted to this rank's stripes + the per-frame gather.
+
+    Usage (one process per GPU, torch.distributed initialised with nccl):
+        tp = TiledPathTracer(tracer, rank, world); tp.render(); full = tp.gather()   # full image on rank 0
+    """
+
+    def __init__(self, tracer, rank: int, world: int, stripe_rows: int = DEFAULT_STRIPE_ROWS, device=None):
+        import torch
+
+        self.tracer, self.rank, self.world, self.stripe_rows = tracer, rank, world, stripe_rows
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        # kernels and collectives share torch's current stream, so stream order is the only synchronisation needed
+        tracer.SetStream(torch.cuda.current_stream(self.device).cuda_stream)
+        tracer.SetTile(rank, world, stripe_rows)
+        self.width, self.height = tracer.Width, tracer.Height
+        self.max_rows = max_local_rows(world, stripe_rows, self.height)
+        ptr, nbytes = tracer.ResultDevicePtr()
+        assert nbytes >= self.max_rows * self.width * 16
+        self._holder = _DeviceBuffer(ptr, (self.max_rows, self.width, 4))
+        self.local = torch.as_tensor(self._holder, device=self.device)
+        self.staging = torch.empty_like(self.local)
+        self.full = torch.empty((self.height, self.width, 4), dtype=torch.float32, device=self.device) if rank == 0 else None
+        self._pending = None
+
+    def render(self, frames: int = 1) -> None:
+        self.tracer.Render(frames)
+
+    def gather_async(self):
+        """Snapshot the local stripes (so the next frame may overwrite them) and start the gather."""
+        self.staging.copy_(self.local, non_blocking=True)
+        gathered, work = gather_stripes(self.staging, self.world, dst=0, async_op=True)
+        self._pending = (gathered, work)
+
+    def finish_gather(self):
+        """Wait for the outstanding gather; on rank 0 de-interleave into the row-major image and return it."""
+        import ctypes as C
+
+        from . import _lib
+
+        if self._pending is None:
+            return self.full
+        gathered, work = self._pending
+        self._pending = None
+        if work is not None:
+            work.wait()
+        if self.rank == 0:
+            _lib.check(self.tracer._L.ptb_deinterleave_device(self.tracer._ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(self.full.data_ptr())))
+        return self.full
+
+    def gather(self):
+        self.gather_async()
+        return self.finish_gather()

@@ -1,0 +1,248 @@
+"""CPU tests of the host side: scene byte producers, the C-ABI surface, error behaviour, the tile partition and its
+gather (gloo, world_size 2).  No compute calls into the CUDA library are made here."""
+import ctypes as C
+import json
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, f32_same
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PINS = json.load(open(os.path.join(GOLD, "layout_pins.json")))
+
+
+# ------------------------------------------------------------------------------- std140 layout
+def test_layout_pins(ptb):
+    sc = ptb.scene
+    assert sc.MATERIAL_SIZE == PINS["material"] and sc.SPHERE_SIZE == PINS["sphere"] and sc.CUBOID_SIZE == PINS["cuboid"]
+    assert sc.BASIC_DATA_SIZE == PINS["basic_data_ubo"]
+    scene = sc.load_default_scene()
+    assert scene.ubo_size == PINS["game_objects_ubo"]
+    assert scene.cuboids[0].BufferOffset == PINS["cuboid_base"]
+    assert scene.spheres[3].BufferOffset == 3 * 80 and scene.cuboids[2].BufferOffset == 20480 + 2 * 96
+    assert len(sc.atmosphere_ubo_bytes()) == PINS["atmosphere_ubo"]
+
+
+def test_material_packing_and_clamps(ptb):
+    sc = ptb.scene
+    m = sc.Material.new((0.1, 0.2, 0.3), (1, 2, 3), (4, 5, 6), specularChance=1.5, specularRoughness=0.25, indexOfRefraction=0.5,
+                        refractionChance=0.9, refractionRoughnes=0.75)
+    assert m.SpecularChance == 1.0 and m.IOR == 1.0 and m.RefractionChance == 0.0      # Material.cs:26-29
+    d = m.GetGPUFriendlyData()
+    assert d.shape == (4, 4) and d.dtype == np.float32
+    assert d[0].tolist() == [np.float32(0.1), np.float32(0.2), np.float32(0.3), 1.0]    # Albedo, SpecularChance
+    assert d[1].tolist() == [1.0, 2.0, 3.0, 0.25]                                          # Emissiv, SpecularRoughness
+    assert d[2].tolist() == [4.0, 5.0, 6.0, 0.0]                                           # Absorbance, RefractionChance
+    assert d[3].tolist() == [0.75, 1.0, 0.0, 0.0]                                          # RefractionRoughness, IOR
+    z = sc.Material.Zero()
+    z.SpecularChance = np.float32(7.0)    # field writes bypass the ctor clamps, as in MainWindow.cs:225-229
+    assert z.GetGPUFriendlyData()[0, 3] == 7.0
+
+
+def test_default_scene_pins(ptb):
+    scene = ptb.load_default_scene()
+    assert len(scene.spheres) == PINS["default_spheres"] and len(scene.cuboids) == PINS["default_cuboids"]
+    grid = scene.spheres[:36]
+    assert all(s.Position[2] == -5 and s.Radius == np.float32(1.3) for s in grid)
+    assert grid[0].Material.SpecularChance == 0.0 and grid[35].Material.SpecularChance == 1.0
+    assert grid[7].Material.SpecularChance == np.float32(1) / np.float32(5) and grid[7].Material.SpecularRoughness == np.float32(1) / np.float32(5)
+    glass = scene.spheres[36:]
+    assert all(s.Position[2] == -20 for s in glass) and {float(s.Position[1]) for s in glass} == {3.0, -6.0}
+    assert all(s.Material.RefractionChance == np.float32(0.98) and s.Material.SpecularChance == np.float32(0.02) for s in glass)
+    light = scene.cuboids[1]
+    assert np.allclose(light.Material.Emissiv, np.array([0.917, 0.945, 0.513], np.float32) * np.float32(5))
+    assert abs(float(light.Position[1]) - 18.49) < 1e-5
+    assert scene.cuboids[3].Material.IOR == 1.0 and scene.cuboids[3].Material.RefractionChance == np.float32(0.954)    # glass front wall
+    assert scene.cuboids[4].Material.SpecularChance == 1.0                                                                # mirror-ish right wall
+    # Min/Max, not position/dimensions, are uploaded (Cuboid.cs:23-30)
+    d = scene.cuboids[6].GetGPUFriendlyData()
+    assert np.allclose(d[0, :3], [-16.5, -13.495, -16.5]) and np.allclose(d[1, :3], [-13.5, -7.495, -13.5])
+
+
+def test_scene_bytes_match_golden(ptb):
+    ubo = np.frombuffer(ptb.load_default_scene().ubo_bytes(), dtype=np.uint8)
+    assert (ubo[:48 * 80] == np.load(os.path.join(GOLD, "default_scene_ubo.npy"))).all()
+    assert (ubo[20480:20480 + 7 * 96] == np.load(os.path.join(GOLD, "default_scene_cuboids.npy"))).all()
+    assert (ubo[48 * 80:20480] == 0).all()
+    basic = np.frombuffer(ptb.scene.basic_data_bytes(ptb.default_camera(), 64, 64), dtype=np.uint8)
+    assert (basic == np.load(os.path.join(GOLD, "default_basic_ubo_64x64.npy"))).all()
+
+
+def test_synthetic_scene_is_deterministic_and_sized(ptb):
+    a = ptb.synthetic_scene(64, 16, seed=1234)
+    b = ptb.synthetic_scene(64, 16, seed=1234)
+    assert a.ubo_bytes() == b.ubo_bytes()
+    assert len(a.spheres) == 64 and len(a.cuboids) == 16 and a.ubo_size == 64 * 80 + 16 * 96
+    assert a.cuboids[0].BufferOffset == 64 * 80      # cuboid base follows the sphere CAPACITY (Cuboid.cs:21)
+    assert all(s.Material.RefractionRoughnes >= np.float32(0.05) for s in a.spheres)
+    assert all(0 <= s.Material.RefractionChance <= 1 - s.Material.SpecularChance for s in a.spheres)
+
+
+def test_host_buffer_subdata_semantics(ptb):
+    buf = ptb.scene.HostBuffer(32)
+    buf.SubData(8, 8, np.array([1.0, 2.0], np.float32))
+    assert np.frombuffer(buf.bytes(), np.float32)[2:4].tolist() == [1.0, 2.0]
+    buf.SubData(0, 16, np.array([7.0, 8.0, 9.0], np.float32))      # the ViewPos write passes 12 bytes with size 16 (MainWindow.cs:132)
+    assert np.frombuffer(buf.bytes(), np.float32)[:4].tolist() == [7.0, 8.0, 9.0, 0.0]
+    with pytest.raises(ValueError):
+        buf.SubData(24, 16, b"\0" * 16)
+
+
+# ------------------------------------------------------------------------------- OpenTK math restatement
+def test_opentk_matrices(ptb):
+    sc = ptb.scene
+    cam = ptb.default_camera()
+    v = cam.View
+    assert np.allclose(v[:3, :3] @ v[:3, :3].T, np.eye(3), atol=1e-6)           # orthonormal basis
+    assert np.allclose(sc.inverted(v) @ v, np.eye(4), atol=1e-5)
+    p = sc.create_perspective_fov(sc.degrees_to_radians(90.0), 1.0, 0.1, 10.0)
+    assert np.allclose([p[0, 0], p[1, 1]], [1.0, 1.0], atol=1e-6) and p[2, 3] == -1 and p[3, 3] == 0
+    assert np.allclose(sc.inverted(p) @ p, np.eye(4), atol=1e-5)
+    # row-vector convention: the eye maps to the origin, the view direction to -z
+    eye = np.append(cam.Position, 1).astype(np.float32)
+    assert np.allclose(eye @ v, [0, 0, 0, 1], atol=1e-5)
+    ahead = np.append(cam.Position + cam.ViewDir, 1).astype(np.float32)
+    assert np.allclose(ahead @ v, [0, 0, -1, 1], atol=1e-5)
+    with pytest.raises(ValueError):
+        sc.inverted(np.zeros((4, 4), np.float32))
+
+
+def test_atmosphere_inputs(ptb):
+    lp = ptb.scene.atmosphere_light_pos(0.5)
+    assert lp[0] == 0 and abs(lp[2] + 1.496e11) < 1e5 and abs(lp[1]) < 2e4     # sun on the -z horizon
+    ubo = np.frombuffer(ptb.scene.atmosphere_ubo_bytes(), np.float32)
+    inv_view_px = ubo[16:32].reshape(4, 4)
+    d = np.array([0, 0, -1, 0], np.float32) @ inv_view_px                       # the +X face looks down +x
+    assert np.allclose(d[:3], [1, 0, 0], atol=1e-6)
+
+
+# ------------------------------------------------------------------------------- C ABI surface
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(ptb):
+    from importlib import import_module
+    _lib = import_module("opentk-pathtracer_b200._lib")
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    assert sorted(_lib.SIGNATURES) == syms           # the ctypes binding declares exactly the header's entry points
+    L = _lib.load()
+    for s in syms:
+        assert hasattr(L, s), f"libptb200.so does not export {s}"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (ptb_[a-z0-9_]+)", out))
+    assert exported == set(syms)                      # and nothing undeclared leaks out
+    assert L.ptb_version() == 100
+
+
+def test_library_has_sm100a_code_only(ptb):
+    from importlib import import_module
+    _lib = import_module("opentk-pathtracer_b200._lib")
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "opentk-pathtracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pt_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_fails_loudly_without_a_gpu(ptb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ptb.PtbError) as e:
+        ptb.PathTracer(None, 64, 64, 13, 1, 20.0, 0.14)
+    assert "error -2" in str(e.value)          # PTB_E_CUDA, no silent CPU fallback
+    L = ptb.load_library()
+    assert L.ptb_set_spp(None, 1) == -1 and b"null" in L.ptb_last_error()
+
+
+# ------------------------------------------------------------------------------- tile partition + gather
+def test_partition_covers_every_row_once(ptb):
+    from importlib import import_module
+    D = import_module("opentk-pathtracer_b200.distributed")
+    for height, world, stripe in [(1080, 8, 8), (1080, 3, 8), (2160, 8, 16), (123, 4, 8), (7, 8, 8), (64, 1, 8)]:
+        rows = np.concatenate([D.local_rows_of(r, world, stripe, height) for r in range(world)])
+        assert sorted(rows.tolist()) == list(range(height))
+        assert D.max_local_rows(world, stripe, height) == max(D.local_row_count(r, world, stripe, height) for r in range(world))
+        g = np.zeros((world, D.max_local_rows(world, stripe, height), 5, 1), np.float32)
+        for r in range(world):
+            lr = D.local_rows_of(r, world, stripe, height)
+            g[r, :lr.size, :, 0] = lr[:, None]
+        full = D.deinterleave_host(g, height, world, stripe)
+        assert (full[:, 0, 0] == np.arange(height)).all()
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import ptb200
+from importlib import import_module
+D = import_module("opentk-pathtracer_b200.distributed")
+from oracle import oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+sc = ptb200.scene
+W, H, stripe = 40, 52, 8
+env = O.atmosphere(8, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 4, 2)
+scene, cam = sc.load_default_scene(), sc.default_camera()
+basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+rows = D.local_rows_of(rank, world, stripe, H)
+local = np.zeros((D.max_local_rows(world, stripe, H), W, 4), np.float32)
+scratch = np.zeros((H, W, 4), np.float32)
+for frame in range(3):
+    # this rank renders ONLY its stripes (global pixel coordinates seed the RNG), keeping its running mean locally
+    scratch[rows] = local[:rows.size]
+    for s in range(0, rows.size, stripe):
+        O.render(scratch, basic, ubo, env, frame=frame, spp=1, ray_depth=13, focal_length=20.0, aperture_diameter=0.14,
+                 n_spheres=48, n_cuboids=7, rows=(int(rows[s]), int(rows[min(s + stripe, rows.size) - 1]) + 1), n_threads=1)
+    local[:rows.size] = scratch[rows]
+    gathered, work = D.gather_stripes(torch.from_numpy(local), world, dst=0)
+    if rank == 0:
+        full = D.deinterleave_host(gathered.numpy(), H, world, stripe)
+if rank == 0:
+    ref = np.zeros((H, W, 4), np.float32)
+    for frame in range(3):
+        O.render(ref, basic, ubo, env, frame=frame, spp=1, ray_depth=13, focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+    assert (full.view(np.uint32) == ref.view(np.uint32)).all(), "gathered tiles differ from the single-process render"
+    print("GATHER_OK")
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_two_rank_gloo_gather_equals_single_render(tmp_path):
+    """The N>1 host path on CPU: two processes, gloo, each rendering its own stripes (the oracle stands in for the GPU
+    kernel), one gather per frame, de-interleave on rank 0 == unpartitioned render, bitwise."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "GATHER_OK" in outs[0]

@@ -1,0 +1,367 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): the CUDA path, called through the C ABI (ctypes -> libptb200.so),
+against the CPU oracle on the same seeded inputs.  The bar is BIT-EXACT float32 (any NaN == any NaN): a Monte-Carlo
+path is chaotic, so anything looser would hide real divergence.  Tolerance stated once: 0 ulp.
+Nothing here reads /root/reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import f32_same, oracle_render
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def make_tracer(ptb, env, W, H, scene, camera, *, spp=1, depth=13, focal=20.0, aperture=0.14, kernel=0):
+    pt = ptb.PathTracer(env, W, H, depth, spp, focal, aperture, max_spheres=scene.max_spheres, max_cuboids=scene.max_cuboids)
+    pt.LoadScene(scene)
+    pt.SetCamera(camera)
+    pt.SetKernel(kernel)
+    return pt
+
+
+def assert_same(got, ref, what=""):
+    bad = ~f32_same(got, ref)
+    assert not bad.any(), f"{what}: {int(bad.any(axis=-1).sum())} differing pixels; first at {np.argwhere(bad)[0].tolist()}"
+
+
+@pytest.fixture(scope="module")
+def tracer256(ptb, env256, default_scene, camera):
+    pt = make_tracer(ptb, env256, 256, 256, default_scene, camera)
+    yield pt
+    pt.Dispose()
+
+
+# ------------------------------------------------------------------------------- the library actually loaded
+def test_native_library_is_loaded(ptb):
+    L = ptb.load_library()
+    assert L.ptb_version() == 100
+    maps = open("/proc/self/maps").read()
+    assert "libptb200.so" in maps
+
+
+# ------------------------------------------------------------------------------- unit probes (ptb_debug_eval)
+def test_pcg_stream_matches_golden(tracer256, oracle):
+    import json
+    for k in json.load(open(os.path.join(GOLD, "pcg_kats.json"))):
+        seed = np.array([k["seed"]], np.uint32).view(np.float32)
+        got = tracer256.DebugEval(2, seed, 8, 8)
+        assert [int(v) for v in got.view(np.uint32)] == k["floats_hex"]
+
+
+def test_transcendentals_bit_exact(tracer256, oracle):
+    x = np.concatenate([np.linspace(0, 6.2831855, 1000003, dtype=np.float32), np.linspace(-50, 50, 100001, dtype=np.float32)])
+    s, c = oracle.sincos(x)
+    d = tracer256.DebugEval(0, x, x.size, 2 * x.size).reshape(-1, 2)
+    assert_same(d[:, 0], s, "sin")
+    assert_same(d[:, 1], c, "cos")
+    x = np.concatenate([np.linspace(-110, 90, 1000003, dtype=np.float32), np.array([np.nan, np.inf, -np.inf, 0.0, -0.0], np.float32)])
+    assert_same(tracer256.DebugEval(1, x, x.size, x.size), oracle.exp(x), "exp")
+
+
+def test_min_max_rcp_sqrt_model(tracer256):
+    rng = np.random.default_rng(1)
+    ab = (rng.standard_normal((200000, 2)) * 10.0 ** rng.integers(-30, 30, (200000, 2))).astype(np.float32)
+    ab[:8] = np.array([[0.0, -0.0], [-0.0, 0.0], [np.nan, 1], [1, np.nan], [np.inf, 1], [0.0, 4.0], [-0.0, 0.0], [np.nan, np.nan]], np.float32)
+    r = tracer256.DebugEval(5, ab, ab.shape[0], 4 * ab.shape[0]).reshape(-1, 4)
+    # min/max: NaN loses, -0 < +0 (the oracle's g_min/g_max)
+    assert r[0, 0].view(np.uint32) == 0x80000000 and r[1, 0].view(np.uint32) == 0x80000000
+    assert r[0, 1].view(np.uint32) == 0 and r[1, 1].view(np.uint32) == 0
+    assert r[2, 0] == 1 and r[3, 0] == 1 and r[2, 1] == 1 and r[3, 1] == 1 and np.isnan(r[7, 0])
+    with np.errstate(all="ignore"):
+        assert_same(r[:, 2], np.float32(1) / ab[:, 0], "rcp")       # correctly rounded reciprocal
+        assert_same(r[:, 3], np.sqrt(ab[:, 1]), "sqrt")
+
+
+def test_cubemap_lookup_bit_exact(tracer256, oracle, env256):
+    rng = np.random.default_rng(2)
+    dirs = rng.standard_normal((300000, 3)).astype(np.float32)
+    dirs[:6] = np.eye(3, dtype=np.float32).repeat(2, 0) * np.array([1, -1] * 3, np.float32)[:, None]
+    dirs[6:14] = np.array([[sx, sy, sz] for sx in (1, -1) for sy in (1, -1) for sz in (1, -1)], np.float32)   # corners
+    e = rng.standard_normal((3000, 3)).astype(np.float32)
+    e[:, 0] = np.sign(e[:, 0]); e[:, 1] = np.sign(e[:, 1])                                                     # exact edges
+    dirs[14:3014] = e
+    dirs[3014] = np.nan; dirs[3015] = 0; dirs[3016] = (np.inf, 1, 1)
+    got = tracer256.DebugEval(3, dirs, dirs.shape[0], 3 * dirs.shape[0]).reshape(-1, 3)
+    assert_same(got, oracle.texture_cube(env256, dirs), "texture(samplerCube)")
+
+
+def test_small_cubemaps_bit_exact(ptb, oracle, default_scene, camera):
+    rng = np.random.default_rng(4)
+    dirs = rng.standard_normal((20000, 3)).astype(np.float32)
+    for n in (1, 2, 3, 16):
+        env = rng.random((6, n, n, 4)).astype(np.float32)
+        pt = make_tracer(ptb, env, 16, 16, default_scene, camera)
+        got = pt.DebugEval(3, dirs, dirs.shape[0], 3 * dirs.shape[0]).reshape(-1, 3)
+        assert_same(got, oracle.texture_cube(env, dirs), f"cubemap N={n}")
+        pt.Dispose()
+
+
+def test_closest_hit_fold_bit_exact(tracer256, oracle, default_scene):
+    rng = np.random.default_rng(3)
+    n = 200000
+    o = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.array([40, 25, 25], np.float32) + np.array([0, 0, -10], np.float32)
+    o[:20000] = default_scene.spheres[40].Position + (rng.random((20000, 3)).astype(np.float32) - np.float32(0.5)) * np.float32(1.5)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[:100, 0] = 0   # axis-parallel components: inf slabs
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    ref = oracle.ray_trace(rays, default_scene.ubo_bytes(), 256, 48, 7)
+    assert ref[:, 2].sum() > 5000
+    for op, name in ((4, "packed scene (megakernel view)"), (6, "raw UBO (proxy view)")):
+        got = tracer256.DebugEval(op, rays, n, 12 * n).reshape(-1, 12)
+        assert_same(got, ref, name)
+
+
+# ------------------------------------------------------------------------------- image parity
+CASES = [
+    # name, W, H, frames, kwargs
+    ("C1 default 256x256", 256, 256, 8, {}),
+    ("ragged size (not a multiple of 8)", 251, 123, 3, {}),
+    ("SPP 4 (one RNG stream across samples)", 128, 128, 3, dict(spp=4)),
+    ("rayDepth 1", 128, 128, 2, dict(depth=1)),
+    ("rayDepth 50 (GUI maximum)", 96, 96, 2, dict(depth=50)),
+    ("wide aperture, short focal length", 160, 120, 2, dict(focal=5.0, aperture=0.5)),
+    ("pinhole (aperture 0)", 160, 120, 2, dict(aperture=0.0)),
+    ("1x1 image", 1, 1, 2, {}),
+]
+
+
+@pytest.mark.parametrize("name,W,H,frames,kw", CASES, ids=[c[0] for c in CASES])
+def test_image_parity(ptb, oracle, env256, default_scene, camera, name, W, H, frames, kw):
+    pt = make_tracer(ptb, env256, W, H, default_scene, camera, **kw)
+    ref = np.zeros((H, W, 4), np.float32)
+    for f in range(frames):
+        pt.Render()
+        oracle_render(oracle, ptb.scene, default_scene, camera, env256, W, H, 1, first_frame=f, image=ref, **kw)
+        assert_same(pt.Result, ref, f"{name}, frame {f}")
+    assert pt.Samples == frames * kw.get("spp", 1) and pt.Frame == frames
+    pt.Dispose()
+
+
+def test_golden_image(ptb, default_scene, camera):
+    env16 = np.load(os.path.join(GOLD, "env16.npy"))
+    pt = make_tracer(ptb, env16, 64, 64, default_scene, camera)
+    pt.Render()
+    assert_same(pt.Result, np.load(os.path.join(GOLD, "c1_64x64_f0.npy")), "golden frame 0")
+    pt.Render(3)
+    assert_same(pt.Result, np.load(os.path.join(GOLD, "c1_64x64_f0_3.npy")), "golden frames 0..3")
+    pt.Dispose()
+
+
+def test_1080p_crop_parity(ptb, oracle, env256, default_scene, camera):
+    """C2 at full size: the oracle renders three 24-row bands (sky, mid, floor); the GPU renders everything."""
+    W, H = 1920, 1080
+    pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+    ref = np.zeros((H, W, 4), np.float32)
+    bands = [(0, 24), (528, 552), (1056, 1080)]
+    for f in range(2):
+        pt.Render()
+        for b in bands:
+            oracle_render(oracle, ptb.scene, default_scene, camera, env256, W, H, 1, first_frame=f, image=ref, rows=b)
+    got = pt.Result
+    for b in bands:
+        assert_same(got[b[0]:b[1]], ref[b[0]:b[1]], f"1080p rows {b}")
+    pt.Dispose()
+
+
+def test_dof_sweep_parity(ptb, oracle, env256, default_scene, camera):
+    """C5: ApertureDiameter x FocalLength grid at reduced size."""
+    W, H = 96, 54
+    for aperture in (0.0, 0.05, 0.3, 0.5):
+        for focal in (1.0, 5.0, 50.0):
+            pt = make_tracer(ptb, env256, W, H, default_scene, camera, focal=focal, aperture=aperture)
+            pt.Render()
+            ref = oracle_render(oracle, ptb.scene, default_scene, camera, env256, W, H, 1, focal=focal, aperture=aperture)
+            assert_same(pt.Result, ref, f"aperture {aperture} focal {focal}")
+            pt.Dispose()
+
+
+def test_synthetic_scene_parity(ptb, oracle, env256, camera):
+    """C3: 1024 spheres + 256 cuboids, rayDepth 8 (capacities 1024/256 move the cuboid base to 81 920)."""
+    syn = ptb.synthetic_scene(1024, 256)
+    W, H = 160, 90
+    pt = make_tracer(ptb, env256, W, H, syn, camera, depth=8)
+    ref = np.zeros((H, W, 4), np.float32)
+    for f in range(2):
+        pt.Render()
+        oracle_render(oracle, ptb.scene, syn, camera, env256, W, H, 1, first_frame=f, image=ref, depth=8)
+        assert_same(pt.Result, ref, f"C3 frame {f}")
+    pt.Dispose()
+
+
+def test_empty_scene_and_zero_depth(ptb, oracle, env256, camera):
+    empty = ptb.Scene()
+    pt = make_tracer(ptb, env256, 64, 48, empty, camera)
+    pt.Render()
+    assert_same(pt.Result, oracle_render(oracle, ptb.scene, empty, camera, env256, 64, 48, 1), "empty scene")
+    pt.RayDepth = 0
+    pt.ResetRenderer()
+    pt.Render()
+    out = pt.Result
+    assert (out[..., :3] == 0).all() and (out[..., 3] == 1).all()
+    pt.Dispose()
+
+
+def test_object_count_below_uploaded(ptb, oracle, env256, default_scene, camera):
+    """NumSpheres/NumCuboids smaller than what the UBO holds: only the first n are traced (compute.glsl:231,244)."""
+    pt = make_tracer(ptb, env256, 96, 96, default_scene, camera)
+    pt.NumSpheres = 10
+    pt.NumCuboids = 3
+    pt.Render()
+    sc = ptb.scene
+    ref = np.zeros((96, 96, 4), np.float32)
+    oracle.render(ref, sc.basic_data_bytes(camera, 96, 96), default_scene.ubo_bytes(), env256, frame=0, spp=1, ray_depth=13,
+                  focal_length=20.0, aperture_diameter=0.14, n_spheres=10, n_cuboids=3)
+    assert_same(pt.Result, ref, "partial counts")
+    pt.Dispose()
+
+
+def test_object_edit_through_subdata(ptb, oracle, env256, camera):
+    """Gui.cs:212-216: editing one object re-uploads just its 80/96 bytes."""
+    scene = ptb.load_default_scene()
+    pt = make_tracer(ptb, env256, 96, 96, scene, camera)
+    pt.Render()
+    scene.spheres[5].Material.Emissiv = np.array([2.0, 1.0, 0.5], np.float32)
+    scene.spheres[5].Upload(pt.GameObjectsUBO)
+    scene.cuboids[6].Dimensions = np.array([5.0, 4.0, 3.0], np.float32)
+    scene.cuboids[6].Upload(pt.GameObjectsUBO)
+    pt.ResetRenderer()
+    pt.Render()
+    assert_same(pt.Result, oracle_render(oracle, ptb.scene, scene, camera, env256, 96, 96, 1), "after SubData edits")
+    pt.Dispose()
+
+
+# ------------------------------------------------------------------------------- schedule / partition invariance
+def test_megakernel_equals_proxy_at_1080p(ptb, env256, default_scene, camera):
+    """Two different schedules (persistent + refill vs one thread per pixel) must give the same bits at full size."""
+    imgs = []
+    for kernel in (ptb.KERNEL_MEGA, ptb.KERNEL_NAIVE):
+        pt = make_tracer(ptb, env256, 1920, 1080, default_scene, camera, kernel=kernel)
+        pt.Render(3)
+        imgs.append(pt.Result)
+        pt.Dispose()
+    assert_same(imgs[0], imgs[1], "megakernel vs proxy")
+    assert np.isfinite(imgs[0]).all() and (imgs[0][..., 3] == 1).all()
+
+
+def test_render_is_deterministic(ptb, env256, default_scene, camera):
+    a = make_tracer(ptb, env256, 640, 360, default_scene, camera)
+    b = make_tracer(ptb, env256, 640, 360, default_scene, camera)
+    a.Render(4); b.Render(2); b.Render(2)
+    assert_same(a.Result, b.Result, "two contexts, different call batching")
+    a.Dispose(); b.Dispose()
+
+
+@pytest.mark.parametrize("world,stripe", [(2, 8), (3, 8), (8, 16), (4, 5)])
+def test_tile_union_equals_full_render(ptb, env256, default_scene, camera, world, stripe):
+    """P3: the union of every rank's stripes (global seeds) is bit-identical to the single-GPU image; the device
+    de-interleave reproduces the host one."""
+    from importlib import import_module
+    D = import_module("opentk-pathtracer_b200.distributed")
+    W, H = 320, 203
+    full = make_tracer(ptb, env256, W, H, default_scene, camera)
+    full.Render(2)
+    ref = full.Result
+    maxr = D.max_local_rows(world, stripe, H)
+    gathered = np.zeros((world, maxr, W, 4), np.float32)
+    for r in range(world):
+        pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+        pt.SetTile(r, world, stripe)
+        rows = D.local_rows_of(r, world, stripe, H)
+        assert pt.Result.shape[0] == rows.size
+        pt.Render(2)
+        gathered[r, :rows.size] = pt.Result
+        pt.Dispose()
+    assert_same(D.deinterleave_host(gathered, H, world, stripe), ref, f"world {world}")
+    # device de-interleave through the ABI
+    import torch
+    g = torch.from_numpy(gathered).cuda()
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    full.SetTile(0, world, stripe)
+    rc = full._L.ptb_deinterleave_device(full._ctx, C.c_void_p(g.data_ptr()), C.c_void_p(out.data_ptr()))
+    assert rc == 0
+    full.Synchronize()
+    assert_same(out.cpu().numpy(), ref, "device de-interleave")
+    full.Dispose()
+
+
+# ------------------------------------------------------------------------------- PathTracer class semantics
+def test_reset_setsize_and_resume(ptb, oracle, env256, default_scene, camera):
+    pt = make_tracer(ptb, env256, 128, 96, default_scene, camera)
+    pt.Render(3)
+    assert pt.Samples == 3
+    pt.ResetRenderer()                       # PathTracer.cs:137-140: counter only; frame 0 then overwrites the image
+    assert pt.Samples == 0
+    pt.Render()
+    f0 = oracle_render(oracle, ptb.scene, default_scene, camera, env256, 128, 96, 1)
+    assert_same(pt.Result, f0, "frame 0 after ResetRenderer")
+    # checkpoint / resume: save image + frame, restore into a new context, continue
+    pt.Render(2)
+    saved, frame = pt.Result, pt.Frame
+    other = make_tracer(ptb, env256, 128, 96, default_scene, camera)
+    other.WriteResult(saved); other.SetFrame(frame)
+    pt.Render(2); other.Render(2)
+    assert_same(pt.Result, other.Result, "resumed accumulation")
+    other.Dispose()
+    pt.SetSize(64, 80)                       # PathTracer.cs:131-135
+    assert pt.Samples == 0 and pt.Width == 64 and pt.Height == 80
+    pt.SetCamera(camera)                     # MainWindow.OnResize re-uploads the projection (aspect changed)
+    pt.Render()
+    assert_same(pt.Result, oracle_render(oracle, ptb.scene, default_scene, camera, env256, 64, 80, 1), "after SetSize")
+    pt.Dispose()
+
+
+def test_error_codes(ptb, env256):
+    L = ptb.load_library()
+    ctx = C.c_void_p()
+    assert L.ptb_create(C.byref(ctx), 0, 10, 256, 64, 0) == -1
+    assert L.ptb_create(C.byref(ctx), 16, 16, 256, 64, 99) == -1 and b"device" in L.ptb_last_error()
+    assert L.ptb_create(C.byref(ctx), 16, 16, 256, 64, 0) == 0
+    assert L.ptb_render(ctx) == -3 and b"EnvironmentMap" in L.ptb_last_error()      # PTB_E_STATE
+    assert L.ptb_set_num_spheres(ctx, 257) == -1 and L.ptb_set_num_cuboids(ctx, -1) == -1
+    assert L.ptb_set_spp(ctx, 0) == -1 and L.ptb_set_ray_depth(ctx, -1) == -1
+    buf = C.create_string_buffer(256)
+    assert L.ptb_basic_data_subdata(ctx, 140, 16, buf) == -1
+    assert L.ptb_game_objects_subdata(ctx, 256 * 80 + 64 * 96 - 8, 16, buf) == -1
+    assert L.ptb_game_objects_subdata(ctx, 256 * 80 + 64 * 96 - 16, 16, buf) == 0
+    assert L.ptb_set_tile(ctx, 2, 2, 8) == -1 and L.ptb_set_kernel(ctx, 7) == -1
+    L.ptb_destroy(ctx)
+    # a scene too large for shared memory is refused, not silently truncated
+    big = ptb.PathTracer(env256, 16, 16, 4, 1, 20.0, 0.14, max_spheres=4096, max_cuboids=64)
+    big.NumSpheres = 4096
+    with pytest.raises(ptb.PtbError):
+        big.Render()
+    big.Dispose()
+
+
+# ------------------------------------------------------------------------------- atmosphere producer on the GPU
+def test_atmosphere_kernel_bit_exact(ptb, oracle, env256, default_scene, camera):
+    pt = ptb.PathTracer(None, 32, 32, 13, 1, 20.0, 0.14)
+    pt.GenerateAtmosphere(256, 50, 15, 0.5, 15.0)
+    assert_same(pt.ReadEnvironment(), env256, "atmosphere 256, 50x15")
+    sc = ptb.scene
+    pt.GenerateAtmosphere(33, 7, 3, 0.3, 22.0)
+    assert_same(pt.ReadEnvironment(), oracle.atmosphere(33, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.3), 22.0, 7, 3), "atmosphere 33, 7x3")
+    # and it is usable as the environment map
+    pt.LoadScene(default_scene); pt.SetCamera(camera)
+    pt.Render()
+    ref = oracle_render(oracle, sc, default_scene, camera, oracle.atmosphere(33, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.3), 22.0, 7, 3), 32, 32, 1)
+    assert_same(pt.Result, ref, "render with generated atmosphere")
+    pt.Dispose()
+
+
+def test_statistics_counters(ptb, oracle, env256, default_scene, camera):
+    pt = make_tracer(ptb, env256, 128, 128, default_scene, camera)
+    pt.SetStats(True)
+    pt.Render()
+    st = pt.ReadStats()
+    sc = ptb.scene
+    img = np.zeros((128, 128, 4), np.float32)
+    ref = oracle.render(img, sc.basic_data_bytes(camera, 128, 128), default_scene.ubo_bytes(), env256, frame=0, spp=1, ray_depth=13,
+                        focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7, want_stats=True)
+    assert st["samples"] == ref["samples"] and st["bounces"] == ref["bounces"] and st["hits"] == ref["hits"]
+    pt.Dispose()
