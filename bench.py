@@ -135,15 +135,12 @@ def run_reference(args, rank, world):
     O.render(img, basic, ubo, env, frame=0, **kw)
     full_s = time.perf_counter() - t
     budget = 150.0 / max(1, args.steps + args.warmup)
-    n_bands = 45                                  # 45 bands of 24 rows
-    use = max(1, min(n_bands, int(n_bands * budget / full_s)))
-    sel = np.linspace(0, n_bands - 1, use).round().astype(int)       # bands spread over sky, spheres and floor
-    bands = [(int(b) * 24, int(b) * 24 + 24) for b in sorted(set(sel.tolist()))]
-    px_per_step = sum(b[1] - b[0] for b in bands) * W
+    y_step = max(1, min(64, int(np.ceil(full_s / budget))))          # every y_step-th row: spread over sky, spheres and floor
+    rows_per_step = len(range(0, H, y_step))
+    px_per_step = rows_per_step * W
 
     def step(frame):
-        for b in bands:
-            O.render(img, basic, ubo, env, frame=frame, rows=b, **kw)
+        O.render(img, basic, ubo, env, frame=frame, y_step=y_step, **kw)
 
     for i in range(args.warmup):
         step(i)
@@ -152,7 +149,7 @@ def run_reference(args, rank, world):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     value = px_per_step * SPP * args.steps / dt / 1e6
-    sample = f"{len(bands)} of 45 24-row bands of the 1920x1080 frame per step ({px_per_step} samples/step), spread evenly top to bottom"
+    sample = f"every {y_step}-th row of the 1920x1080 frame per step ({rows_per_step} rows, {px_per_step} samples/step)" if y_step > 1 else "the full 1920x1080 frame per step"
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",

@@ -19,7 +19,7 @@ class Params(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("frame", C.c_int), ("spp", C.c_int), ("ray_depth", C.c_int),
                 ("focal_length", C.c_float), ("aperture_diameter", C.c_float),
                 ("n_spheres", C.c_float), ("n_cuboids", C.c_float), ("max_spheres", C.c_int), ("env_size", C.c_int),
-                ("y0", C.c_int), ("y1", C.c_int), ("x0", C.c_int), ("x1", C.c_int), ("n_threads", C.c_int)]
+                ("y0", C.c_int), ("y1", C.c_int), ("x0", C.c_int), ("x1", C.c_int), ("n_threads", C.c_int), ("y_step", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -75,7 +75,7 @@ def max_threads() -> int:
 
 def render(image: np.ndarray, basic_ubo: bytes, objects_ubo: bytes, env: np.ndarray, *, frame: int, spp: int,
            ray_depth: int, focal_length: float, aperture_diameter: float, n_spheres: int, n_cuboids: int,
-           max_spheres: int = 256, rows=None, cols=None, n_threads: int = 0, want_stats: bool = False):
+           max_spheres: int = 256, rows=None, cols=None, n_threads: int = 0, want_stats: bool = False, y_step: int = 1):
     """One dispatch over `image` (H x W x 4 float32, updated in place: running mean, compute.glsl:126-129)."""
     assert image.dtype == np.float32 and image.ndim == 3 and image.shape[2] == 4 and image.flags.c_contiguous
     assert env.dtype == np.float32 and env.ndim == 4 and env.shape[0] == 6 and env.shape[3] == 4 and env.flags.c_contiguous
@@ -83,7 +83,7 @@ def render(image: np.ndarray, basic_ubo: bytes, objects_ubo: bytes, env: np.ndar
     y0, y1 = rows if rows is not None else (0, h)
     x0, x1 = cols if cols is not None else (0, w)
     p = Params(w, h, frame, spp, ray_depth, focal_length, aperture_diameter, float(n_spheres), float(n_cuboids),
-               max_spheres, env.shape[1], y0, y1, x0, x1, n_threads)
+               max_spheres, env.shape[1], y0, y1, x0, x1, n_threads, y_step)
     st = Stats() if want_stats else None
     b0 = C.create_string_buffer(bytes(basic_ubo), len(basic_ubo))
     b1 = C.create_string_buffer(bytes(objects_ubo), len(objects_ubo))

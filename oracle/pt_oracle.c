@@ -50,6 +50,7 @@ typedef struct {
     int y0, y1;                  /* rows [y0,y1) to render (crop); others untouched */
     int x0, x1;                  /* columns [x0,x1) */
     int n_threads;               /* OpenMP threads; <=0 = all */
+    int y_step;                  /* render rows y0, y0+y_step, ... (<=1 = every row): an evenly spread sample */
 } pto_params;
 
 typedef struct {
@@ -482,8 +483,9 @@ int pto_render(const pto_params *p, const void *basic_ubo, const void *objects_u
         Ctx c;
         c.p = p; c.basic = (const float *)basic_ubo; c.objects = (const uint8_t *)objects_ubo;
         c.env = env; c.rndSeed = 0; c.st = per ? &per[tid] : NULL;
+        const int ys = p->y_step > 1 ? p->y_step : 1;
 #pragma omp for schedule(dynamic, 4)
-        for (int y = y0; y < y1; y++)
+        for (int y = y0; y < y1; y += ys)
             for (int x = x0; x < x1; x++)
                 shade_pixel(&c, x, y, image);
     }
