@@ -7,7 +7,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libptb200.so")
+# PTB_LIB points the loader at an alternative build (kernel A/B experiments, tools/build_variants.py); never set in tests/bench
+LIB = os.environ.get("PTB_LIB") or os.path.join(HERE, "libptb200.so")
 SOURCES = ["ptb_abi.cu"]
 DEPS = ["ptb_abi.cu", "ptb_kernels.cuh", "ptb_math.cuh", os.path.join("..", "..", "include", "ptb200.h")]
 
@@ -24,15 +25,18 @@ def nvcc() -> str:
 
 
 def is_stale() -> bool:
+    if os.environ.get("PTB_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if force or is_stale():
-        cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    out = out or LIB
+    if force or is_stale() or out != LIB:
+        cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *SOURCES]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -44,4 +48,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         if verbose:
             print(res.stderr)
-    return LIB
+    return out

@@ -71,6 +71,7 @@ struct ptb_ctx {
     int launches = 0;
     int mega_smem_set = -1;
     int mega_grid = 0;
+    bool mega_ring = true;
 };
 
 namespace {
@@ -146,6 +147,14 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.scene = c->d_block; P.env = c->d_env; P.image = c->d_image;
     P.counters = c->d_counters; P.stats = c->d_stats;
     P.raw_objects = c->d_objects; P.max_spheres = c->max_spheres;
+    P.inv_width = 1.0f / (float)c->width;
+    P.inv_height = 1.0f / (float)c->height;
+    P.inv_spp = 1.0f / (float)c->spp;
+    P.blend = 1.0f * (1.0f / (float)(c->frame + 1));   // 1.0 / (thisRendererFrame + 1), compute.glsl:128, as a * rcp(b)
+    P.tiles_x = (unsigned)((c->width + 7) / 8);
+    P.tiles_total = P.tiles_x * (unsigned)((c->local_rows + 3) / 4);
+    // umulhi(n, ceil(2^32/d)) == n / d exactly while n * d < 2^32 (error term n*e/(d*2^32) < 1/d); d == 1 needs no division
+    P.tiles_magic = (P.tiles_x > 1 && (unsigned long long)P.tiles_total * P.tiles_x < (1ull << 32)) ? (unsigned)(((1ull << 32) + P.tiles_x - 1) / P.tiles_x) : 0u;
 }
 
 int launch_frame(ptb_ctx* c)
@@ -158,17 +167,26 @@ int launch_frame(ptb_ctx* c)
     } else {
         const int smem = c->block_bytes;
         if (c->mega_smem_set != smem) {
-            CU(cudaFuncSetAttribute(megakernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            int per_sm = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, megakernel<false>, kMegaThreads, smem));
-            if (per_sm < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
-            c->mega_grid = c->sm_count * per_sm;
+            CU(cudaFuncSetAttribute(megakernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int with_ring = 0, without = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true>, kMegaThreads, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false>, kMegaThreads, smem));
+            if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
+            c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
+            c->mega_grid = c->sm_count * (c->mega_ring ? with_ring : without);
             c->mega_smem_set = smem;
         }
         if (c->local_rows > 0) {
-            if (c->stats_on) megakernel<true><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
-            else megakernel<false><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+            if (c->mega_ring) {
+                if (c->stats_on) megakernel<true, true><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+                else megakernel<false, true><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+            } else {
+                if (c->stats_on) megakernel<true, false><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+                else megakernel<false, false><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
+            }
         }
     }
     c->launches++;
@@ -188,7 +206,7 @@ int ptb_create(ptb_ctx** out, int width, int height, int max_spheres, int max_cu
 {
     if (!out) return fail(PTB_E_INVALID, "out is null");
     *out = nullptr;
-    if (width <= 0 || height <= 0 || max_spheres < 0 || max_cuboids < 0) return fail(PTB_E_INVALID, "bad size %dx%d / capacities %d,%d", width, height, max_spheres, max_cuboids);
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535 || max_spheres < 0 || max_cuboids < 0) return fail(PTB_E_INVALID, "bad size %dx%d (1..65535) / capacities %d,%d", width, height, max_spheres, max_cuboids);
     int count = 0;
     CU(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(PTB_E_INVALID, "device %d out of range (%d CUDA devices)", device, count);
@@ -236,7 +254,7 @@ void ptb_destroy(ptb_ctx* c)
 int ptb_set_size(ptb_ctx* c, int width, int height)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
-    if (width <= 0 || height <= 0) return fail(PTB_E_INVALID, "bad size %dx%d", width, height);
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(PTB_E_INVALID, "bad size %dx%d (1..65535)", width, height);
     CU(cudaStreamSynchronize(c->stream));
     c->width = width; c->height = height;
     c->frame = 0;                                    // PathTracer.cs:133

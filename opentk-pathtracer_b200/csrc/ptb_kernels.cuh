@@ -25,7 +25,20 @@ constexpr float kPi = 3.14159265f;            // pt:5
 
 constexpr int kSphereStride = 80;   // Sphere.cs:8
 constexpr int kCuboidStride = 96;   // Cuboid.cs:8
-constexpr int kMegaThreads = 256;
+#ifndef PTB_THREADS
+#define PTB_THREADS 256
+#endif
+#ifndef PTB_MIN_BLOCKS
+#define PTB_MIN_BLOCKS 2
+#endif
+#ifndef PTB_REFILL_MIN
+#define PTB_REFILL_MIN 1      // refill as soon as this many lanes of a warp are idle
+#endif
+// (Round-1 experiment, removed: FADD2/FMUL2/FFMA2 packed fp32x2 in the fold, two spheres per instruction.  Bit-identical,
+//  but on B200 +3 % on the default scene and -15 % on the 1280-primitive scene — the packed ops issue at half rate — and
+//  the pair layout alone cost the scalar loop 20 % on the large scene.  See profiles/r01_experiments.md.)
+constexpr int kMegaThreads = PTB_THREADS;
+constexpr int kQueue = 64;          // primary-ray ring entries per warp (two tiles)
 
 // ------------------------------------------------------------------------------------------------------------
 // Launch parameters (by value: they live in the constant bank; UBO 0 is small enough to ride along).
@@ -47,6 +60,10 @@ struct RenderParams {
     unsigned long long* stats;// optional: samples, traces, hits
     const unsigned char* raw_objects; // raw GameObjectsUBO bytes (naive proxy only)
     int max_spheres;
+    // host-precomputed, correctly rounded (1.0f / x on the host == rcp.rn on the device)
+    float inv_width, inv_height, inv_spp, blend;   // 1/W, 1/H, 1/SPP, 1/(frame+1)
+    unsigned tiles_x, tiles_total;                  // 8x4 work tiles
+    unsigned tiles_magic;                           // ceil(2^32 / tiles_x): tile / tiles_x == umulhi(tile, magic) while tile * tiles_x < 2^32 (0 = divide)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -125,6 +142,9 @@ __device__ __forceinline__ void trace(const Scene& sc, V3 o, V3 d, float& T, int
     }
 }
 
+__device__ __forceinline__ void trace_any(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside) { trace(sc, o, d, T, prim, inside); }
+__device__ __forceinline__ void trace_any(const RawScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside) { trace(sc, o, d, T, prim, inside); }
+
 // pt:316-332 — surface normal of the winning primitive.
 template <class Scene>
 __device__ __forceinline__ V3 surface_normal(const Scene& sc, int prim, V3 pos)
@@ -140,7 +160,11 @@ __device__ __forceinline__ V3 surface_normal(const Scene& sc, int prim, V3 pos)
     n.x = 0.0f + signf(cs.x) * stepf(fabsf(fabsf(cs.x) - half.x), kEps);
     n.y = 0.0f + signf(cs.y) * stepf(fabsf(fabsf(cs.y) - half.y), kEps);
     n.z = 0.0f + signf(cs.z) * stepf(fabsf(fabsf(cs.z) - half.z), kEps);
-    return normalize(n);
+    // normalize(n) with n in {-1,0,1}^3: dot(n,n) is exactly 0..3, so rcp(sqrt(.)) is one of four constants
+    // (inf for the zero vector: 0 * inf = NaN, as normalize(vec3(0)) gives).  0x3f3504f3 = rcp(sqrt(2)), 0x3f13cd3a = rcp(sqrt(3)).
+    const float k = dot(n, n);
+    const float inv = k == 1.0f ? 1.0f : (k == 2.0f ? __uint_as_float(0x3f3504f3u) : (k == 3.0f ? __uint_as_float(0x3f13cd3au) : rcp(fsqrt(k))));
+    return n * inv;
 }
 
 // pt:297-307
@@ -203,8 +227,8 @@ __device__ __forceinline__ void primary_ray(const RenderParams& P, Path& p)
 {
     const float ox = rand01(p.rng);
     const float oy = rand01(p.rng);
-    const float ndcx = ((float)p.px + ox) * rcp((float)P.width) * 2.0f - 1.0f;
-    const float ndcy = ((float)p.py + oy) * rcp((float)P.height) * 2.0f - 1.0f;
+    const float ndcx = ((float)p.px + ox) * P.inv_width * 2.0f - 1.0f;
+    const float ndcy = ((float)p.py + oy) * P.inv_height * 2.0f - 1.0f;
     const float* IP = P.basic;
     const float* IV = P.basic + 16;
     const float ex = mat_row(IP, 0, ndcx, ndcy, -1.0f, 0.0f);
@@ -232,7 +256,7 @@ __device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, P
     float T;
     int prim;
     bool inside;
-    trace(sc, p.o, p.d, T, prim, inside);
+    trace_any(sc, p.o, p.d, T, prim, inside);
     if (stats) atomicAdd(stats + 1, 1ull);
     if (T != kFloatMax) {
         if (stats) atomicAdd(stats + 2, 1ull);
@@ -293,21 +317,21 @@ __device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, P
 // multiplies the stale value by exactly 0 there (mix(x, y, 1.0)), so a zero stands in for it.
 __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p)
 {
-    const V3 irr = p.irr * rcp((float)P.spp);
+    const V3 irr = p.irr * P.inv_spp;
     float4* px = P.image + (size_t)p.lrow * P.width + p.px;
     V3 last = mk(0.0f, 0.0f, 0.0f);
     if (P.frame > 0) {
         const float4 l = *px;
         last = mk(l.x, l.y, l.z);
     }
-    const float a = fdiv(1.0f, (float)(P.frame + 1));
-    const V3 out = mix(last, irr, a);
+    const V3 out = mix(last, irr, P.blend);
     *px = make_float4(out.x, out.y, out.z, 1.0f);
 }
 
 // local row -> global y for the stripe partition
 __device__ __forceinline__ int global_row(const RenderParams& P, int lrow)
 {
+    if (P.world == 1) return lrow;
     const int ls = lrow / P.stripe_rows;
     return (ls * P.world + P.rank) * P.stripe_rows + (lrow - ls * P.stripe_rows);
 }
@@ -348,8 +372,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // ------------------------------------------------------------------------------------------------------------
 // The megakernel.  Work item = one pixel (all its SPP samples, RNG stream intact).  Work index -> pixel through
 // 8x4 tiles so a freshly filled warp starts on a compact footprint.
-template <bool kStats>
-__global__ void __launch_bounds__(kMegaThreads, 2) megakernel(const __grid_constant__ RenderParams P)
+// kRing: stage primary rays through the per-warp shared-memory ring (costs 2 KB per warp; the host turns it off when the
+// scene block is so large that the ring would lower the number of resident CTAs).
+template <bool kStats, bool kRing>
+__global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const __grid_constant__ RenderParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -374,48 +400,105 @@ __global__ void __launch_bounds__(kMegaThreads, 2) megakernel(const __grid_const
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int tiles_x = (P.width + 7) >> 3;
-    const int tiles_y = (P.local_rows + 3) >> 2;
-    const unsigned total = (unsigned)(tiles_x * tiles_y) * 32u;
     unsigned long long* stats = kStats ? P.stats : nullptr;
+
+    // Per-warp ring of ready-made primary rays.  Ray generation (4 RNG draws, 2 normalisations, sin/cos, 8 matrix rows)
+    // runs with all 32 lanes converged on one 8x4 pixel tile and is amortised over 32 pixels, instead of running for the
+    // ~12 lanes that happen to be idle in every iteration of the bounce loop.
+    constexpr int kQ = kRing ? kQueue : 1;
+    __shared__ float q_f[kRing ? kMegaThreads / 32 : 1][6][kQ];       // origin xyz, direction xyz
+    __shared__ uint32_t q_u[kRing ? kMegaThreads / 32 : 1][2][kQ];    // rng state after the 4 primary draws; px | lrow << 16
+    const unsigned w = threadIdx.x >> 5;
+    unsigned q_head = 0, q_count = 0;                          // warp-uniform
 
     Path p;
     bool alive = false;         // lane owns an unfinished pixel
-    bool fresh = false;         // lane needs a primary ray (new pixel or next sample)
-    bool exhausted = false;     // warp-uniform: the work counter ran past the end
+    bool fresh = false;         // lane needs a primary ray for the NEXT sample of its pixel (SPP > 1 only)
+    bool exhausted = false;     // warp-uniform: the tile counter ran past the end
 
     while (true) {
-        // ---- refill dead lanes with new pixels (ballot + prefix popcount slot assignment)
         const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-        if (dead != 0u && !exhausted) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(P.counters, (unsigned)__popc(dead));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned)__popc(dead) >= total) exhausted = true;
-            if (!alive) {
+        const unsigned n_dead = (unsigned)__popc(dead);
+        if constexpr (kRing) {
+            // ---- top up the ring: one whole tile per visit, all lanes generating
+            if (n_dead > q_count && !exhausted && q_count <= kQueue - 32 && (n_dead >= (unsigned)PTB_REFILL_MIN || dead == 0xffffffffu)) {
+                unsigned tile = 0;
+                if (lane == 0) tile = atomicAdd(P.counters, 1u);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile >= P.tiles_total) {
+                    exhausted = true;
+                } else {
+                    const unsigned tyu = P.tiles_magic ? __umulhi(tile, P.tiles_magic) : tile / P.tiles_x;
+                    const int x = (int)(tile - tyu * P.tiles_x) * 8 + (int)(lane & 7u), lr = (int)tyu * 4 + (int)(lane >> 3);
+                    const int y = lr < P.local_rows ? global_row(P, lr) : P.height;
+                    const bool valid = x < P.width && y < P.height;
+                    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        Path g;
+                        g.px = x; g.py = y;
+                        g.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
+                        primary_ray(P, g);
+                        const unsigned slot = (q_head + q_count + (unsigned)__popc(vmask & lt_mask)) & (kQueue - 1);
+                        q_f[w][0][slot] = g.o.x; q_f[w][1][slot] = g.o.y; q_f[w][2][slot] = g.o.z;
+                        q_f[w][3][slot] = g.d.x; q_f[w][4][slot] = g.d.y; q_f[w][5][slot] = g.d.z;
+                        q_u[w][0][slot] = g.rng; q_u[w][1][slot] = (uint32_t)x | ((uint32_t)lr << 16);
+                    }
+                    q_count += (unsigned)__popc(vmask);
+                    __syncwarp();
+                }
+            }
+            // ---- idle lanes pop ready rays (prefix-popcount slot assignment)
+            if (n_dead != 0u && q_count != 0u) {
+                const unsigned take = min(n_dead, q_count);
+                const unsigned rank = (unsigned)__popc(dead & lt_mask);
+                if (!alive && rank < take) {
+                    const unsigned slot = (q_head + rank) & (kQueue - 1);
+                    p.o = mk(q_f[w][0][slot], q_f[w][1][slot], q_f[w][2][slot]);
+                    p.d = mk(q_f[w][3][slot], q_f[w][4][slot], q_f[w][5][slot]);
+                    p.rng = q_u[w][0][slot];
+                    const uint32_t xy = q_u[w][1][slot];
+                    p.px = (int)(xy & 0xffffu); p.lrow = (int)(xy >> 16);
+                    p.thr = mk(1.0f, 1.0f, 1.0f); p.rad = mk(0.0f, 0.0f, 0.0f); p.irr = mk(0.0f, 0.0f, 0.0f);
+                    p.depth = 0; p.sample = 0;
+                    alive = true;
+                    if (kStats) atomicAdd(stats, 1ull);
+                }
+                q_head = (q_head + take) & (kQueue - 1);
+                q_count -= take;
+                __syncwarp();
+            }
+        } else {
+            // ---- no ring: idle lanes take pixels straight from the counter and generate their ray in place
+            if (!exhausted && n_dead != 0u && (n_dead >= (unsigned)PTB_REFILL_MIN || dead == 0xffffffffu)) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(P.counters, n_dead);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned total = P.tiles_total * 32u;
+                if (base + n_dead >= total) exhausted = true;
                 const unsigned idx = base + (unsigned)__popc(dead & lt_mask);
-                if (idx < total) {
+                if (!alive && idx < total) {
                     const unsigned tile = idx >> 5, in = idx & 31u;
-                    const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile - (unsigned)ty * (unsigned)tiles_x);
-                    const int x = tx * 8 + (int)(in & 7u), lr = ty * 4 + (int)(in >> 3);
-                    if (x < P.width && lr < P.local_rows) {
-                        p.px = x; p.lrow = lr; p.py = global_row(P, lr);
-                        if (p.py < P.height) {
-                            p.rng = ((uint32_t)p.px * 1973u + (uint32_t)p.py * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
-                            p.irr = mk(0.0f, 0.0f, 0.0f);
-                            p.sample = 0;
-                            alive = true;
-                            fresh = true;
-                        }
+                    const unsigned tyu = P.tiles_magic ? __umulhi(tile, P.tiles_magic) : tile / P.tiles_x;
+                    const int x = (int)(tile - tyu * P.tiles_x) * 8 + (int)(in & 7u), lr = (int)tyu * 4 + (int)(in >> 3);
+                    const int y = lr < P.local_rows ? global_row(P, lr) : P.height;
+                    if (x < P.width && y < P.height) {
+                        p.px = x; p.lrow = lr; p.py = y;
+                        p.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
+                        primary_ray(P, p);
+                        p.irr = mk(0.0f, 0.0f, 0.0f);
+                        p.sample = 0;
+                        alive = true;
+                        if (kStats) atomicAdd(stats, 1ull);
                     }
                 }
             }
         }
         if (!__any_sync(0xffffffffu, alive)) {
-            if (exhausted) break;
-            continue;   // this batch held only padding pixels; fetch again
+            if (exhausted && q_count == 0u) break;
+            continue;   // the tile held only padding pixels; fetch again
         }
-        if (alive && fresh) {
+        if (alive && fresh) {      // SPP > 1: the next sample continues this pixel's RNG stream, so it is generated in place
+            p.py = global_row(P, p.lrow);
             primary_ray(P, p);
             fresh = false;
             if (kStats) atomicAdd(stats, 1ull);
@@ -676,7 +759,7 @@ __device__ __forceinline__ void dbg_trace_one(const Scene& sc, const float* rays
 {
     const V3 o = mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
     float T; int prim; bool inside;
-    trace(sc, o, d, T, prim, inside);
+    trace_any(sc, o, d, T, prim, inside);
     float* q = out + 12 * i;
     const bool hit = T != kFloatMax;
     q[0] = hit ? 1.0f : 0.0f; q[1] = T; q[2] = (hit && inside) ? 1.0f : 0.0f; q[3] = 0.0f;

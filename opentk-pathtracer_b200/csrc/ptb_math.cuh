@@ -126,4 +126,14 @@ __device__ __forceinline__ float rand01(uint32_t& seed)
     return __uint2float_rn(pcg_hash(seed)) * 2.3283064365386963e-10f;   // * 2^-32, exact
 }
 
+// ---- packed fp32x2 (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE binary32 lanes per instruction, same rounding as the
+// scalar ops, half the issue slots.  NOTE: ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2 even with
+// --fmad=false, so a product that must be rounded before an add (e.g. b*b - c) is kept scalar by the callers.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 } // namespace ptb
