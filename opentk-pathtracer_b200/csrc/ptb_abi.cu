@@ -268,8 +268,8 @@ int ptb_reset(ptb_ctx* c)
     return PTB_OK;
 }
 
-int ptb_set_ray_depth(ptb_ctx* c, int v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); if (v < 0) return fail(PTB_E_INVALID, "rayDepth %d < 0", v); c->ray_depth = v; return PTB_OK; }
-int ptb_set_spp(ptb_ctx* c, int v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); if (v < 1) return fail(PTB_E_INVALID, "SPP %d < 1", v); c->spp = v; return PTB_OK; }
+int ptb_set_ray_depth(ptb_ctx* c, int v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); if (v < 0 || v > 4095) return fail(PTB_E_INVALID, "rayDepth %d outside [0,4095]", v); c->ray_depth = v; return PTB_OK; }
+int ptb_set_spp(ptb_ctx* c, int v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); if (v < 1 || v > 4095) return fail(PTB_E_INVALID, "SPP %d outside [1,4095]", v); c->spp = v; return PTB_OK; }
 int ptb_set_focal_length(ptb_ctx* c, float v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); c->focal_length = v; return PTB_OK; }
 int ptb_set_aperture_diameter(ptb_ctx* c, float v) { if (!c) return fail(PTB_E_INVALID, "ctx is null"); c->aperture_diameter = v; return PTB_OK; }
 int ptb_set_num_spheres(ptb_ctx* c, int n)

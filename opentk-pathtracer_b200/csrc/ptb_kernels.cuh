@@ -29,7 +29,7 @@ constexpr int kCuboidStride = 96;   // Cuboid.cs:8
 #define PTB_THREADS 256
 #endif
 #ifndef PTB_MIN_BLOCKS
-#define PTB_MIN_BLOCKS 2
+#define PTB_MIN_BLOCKS 4       // <= 64 registers: four 256-thread CTAs per SM (measured: 80 registers / 3 CTAs costs 5 %)
 #endif
 #ifndef PTB_REFILL_MIN
 #define PTB_REFILL_MIN 1      // refill as soon as this many lanes of a warp are idle
@@ -37,6 +37,9 @@ constexpr int kCuboidStride = 96;   // Cuboid.cs:8
 // (Round-1 experiment, removed: FADD2/FMUL2/FFMA2 packed fp32x2 in the fold, two spheres per instruction.  Bit-identical,
 //  but on B200 +3 % on the default scene and -15 % on the 1280-primitive scene — the packed ops issue at half rate — and
 //  the pair layout alone cost the scalar loop 20 % on the large scene.  See profiles/r01_experiments.md.)
+#ifndef PTB_COOP_MAX
+#define PTB_COOP_MAX 8        // tail: at most this many live paths in a starved warp -> group-cooperative fold (0 disables)
+#endif
 constexpr int kMegaThreads = PTB_THREADS;
 constexpr int kQueue = 64;          // primary-ray ring entries per warp (two tiles)
 
@@ -249,14 +252,11 @@ __device__ __forceinline__ void primary_ray(const RenderParams& P, Path& p)
     p.depth = 0;
 }
 
-// pt:140-180 — one iteration of the bounce loop for one lane.  Returns true while the sample continues.
+// pt:140-180 — one iteration of the bounce loop for one lane, after the closest-hit fold gave (T, prim, inside).
+// Returns true while the sample continues.
 template <class Scene>
-__device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, Path& p, unsigned long long* stats)
+__device__ __forceinline__ bool shade(const RenderParams& P, const Scene& sc, Path& p, float T, int prim, bool inside, unsigned long long* stats)
 {
-    float T;
-    int prim;
-    bool inside;
-    trace_any(sc, p.o, p.d, T, prim, inside);
     if (stats) atomicAdd(stats + 1, 1ull);
     if (T != kFloatMax) {
         if (stats) atomicAdd(stats + 2, 1ull);
@@ -311,6 +311,107 @@ __device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, P
     }
     p.rad = p.rad + env_lookup(P.env, P.env_size, p.d) * p.thr;          // pt:177
     return false;
+}
+
+template <class Scene>
+__device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, Path& p, unsigned long long* stats)
+{
+    float T;
+    int prim;
+    bool inside;
+    trace_any(sc, p.o, p.d, T, prim, inside);
+    return shade(P, sc, p, T, prim, inside, stats);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Warp-cooperative fold for the tail of a frame.  When a warp has no more pixels to pull and only a few live paths, the
+// per-lane fold (every primitive, serially, for one ray) makes the frame wait ~6 us per bounce of its longest path.
+// Here groups of lanes split the primitives of each remaining ray, and the order-dependent fold
+// (pt:231-255, accept on hit && t2>0 && t1<T) is rebuilt exactly from its closed form:
+//   K  = the largest index whose primitive contains the origin (t1 < 0 < t2): it always overwrites what came before;
+//   the winner is the smallest entry distance t1 among later, non-containing hits if that beats t2_K (strictly),
+//   else K; ties go to the lower index; with no K it is the plain first-wins argmin of t1 (t1 < FLOAT_MAX).
+__device__ __forceinline__ bool coop_test(const PackedScene& sc, int i, V3 o, V3 d, V3 inv, float& t1, float& t2)
+{
+    if (i < sc.nS) {
+        const float4 s = sc.sphere(i);
+        const V3 v = mk(o.x - s.x, o.y - s.y, o.z - s.z);
+        const float b = dot(d, v);
+        const float c = dot(v, v) - s.w;
+        const float disc = b * b - c;
+        if (disc < 0.0f) return false;
+        const float sq = fsqrt(disc);
+        t1 = -b - sq;
+        t2 = -b + sq;
+        return t1 <= t2;
+    }
+    const float4 lo = sc.cmin(i - sc.nS), hi = sc.cmax(i - sc.nS);
+    const float ax = (lo.x - o.x) * inv.x, ay = (lo.y - o.y) * inv.y, az = (lo.z - o.z) * inv.z;
+    const float bx = (hi.x - o.x) * inv.x, by = (hi.y - o.y) * inv.y, bz = (hi.z - o.z) * inv.z;
+    t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
+    t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
+    return t1 <= t2;
+}
+// All 32 lanes call this.  The n_live live rays of the warp (bits of `live`) are served by groups of g = 32 / next_pow2(n_live)
+// lanes: group j works on the j-th live ray, lane `sub` of the group tests primitives sub, sub+g, ...; butterfly
+// reductions inside the group rebuild the fold; the owner lane then picks its result up from its group.
+__device__ __forceinline__ void trace_group(const PackedScene& sc, unsigned lane, unsigned live, unsigned n_live, V3 o_, V3 d_,
+                                            float& T, int& prim, bool& inside)
+{
+    const unsigned log2g = 5u - (n_live <= 1u ? 0u : (32u - (unsigned)__clz(n_live - 1u)));   // g = 32 >> ceil(log2 n_live)
+    const unsigned g = 1u << log2g;
+    const unsigned grp = lane >> log2g, sub = lane & (g - 1u);
+    const unsigned src_bit = __fns(live, 0, (int)grp + 1);                  // position of the grp-th live lane
+    const int src = (grp < n_live) ? (int)src_bit : (int)(__ffs(live) - 1);   // spare groups shadow the first ray (result unused)
+    const V3 o = mk(__shfl_sync(0xffffffffu, o_.x, src), __shfl_sync(0xffffffffu, o_.y, src), __shfl_sync(0xffffffffu, o_.z, src));
+    const V3 d = mk(__shfl_sync(0xffffffffu, d_.x, src), __shfl_sync(0xffffffffu, d_.y, src), __shfl_sync(0xffffffffu, d_.z, src));
+    const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
+    const int n = sc.nS + sc.nC;
+
+    uint32_t key; int idx, k_idx; float t1, t2, k_t2;
+    int after = -1;
+    float limit = kFloatMax;                       // the first accept needs t1 < FLOAT_MAX (pt:228,234)
+    float gT = kFloatMax; int gprim = -1; bool ginside = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        // this lane's share: best non-containing hit (min t1, then min index) and the largest containing index
+        key = 0xffffffffu; idx = 0x7fffffff; t1 = kFloatMax; t2 = 0.0f; k_idx = -1; k_t2 = 0.0f;
+        for (int i = (int)sub; i < n; i += (int)g) {
+            float a1, a2;
+            if (i > after && coop_test(sc, i, o, d, inv, a1, a2) && a2 > 0.0f) {
+                if (a1 < 0.0f) { k_idx = i; k_t2 = a2; }                     // ascending i: the last one is the largest
+                else if (a1 < limit) {
+                    const uint32_t kk = __float_as_uint(a1) & 0x7fffffffu;    // t1 >= 0 orders like its bits (-0 folded onto +0)
+                    if (kk < key) { key = kk; idx = i; t1 = a1; t2 = a2; }
+                }
+            }
+        }
+        // butterfly all-reduce inside the group
+        for (unsigned off = 1u; off < g; off <<= 1) {
+            const uint32_t okey = __shfl_xor_sync(0xffffffffu, key, off);
+            const int oidx = __shfl_xor_sync(0xffffffffu, idx, off);
+            const float ot1 = __shfl_xor_sync(0xffffffffu, t1, off), ot2 = __shfl_xor_sync(0xffffffffu, t2, off);
+            const int ok = __shfl_xor_sync(0xffffffffu, k_idx, off);
+            const float okt2 = __shfl_xor_sync(0xffffffffu, k_t2, off);
+            if (okey < key || (okey == key && oidx < idx)) { key = okey; idx = oidx; t1 = ot1; t2 = ot2; }
+            if (ok > k_idx) { k_idx = ok; k_t2 = okt2; }
+        }
+        const bool found = key != 0xffffffffu;
+        if (pass == 0) {
+            if (k_idx < 0) { gT = found ? t1 : kFloatMax; gprim = found ? idx : -1; ginside = found && (t1 == t2); }
+            // the origin sits inside primitive K: only later primitives can displace it, and only by beating its exit distance
+            else { gT = k_t2; gprim = k_idx; ginside = true; after = k_idx; limit = __uint_as_float(0x7f800000u); }
+            if (!__any_sync(0xffffffffu, k_idx >= 0)) break;
+            if (k_idx < 0) after = n;              // this group is done; it only keeps the second pass convergent
+        } else if (after < n && found && t1 < gT) {
+            gT = t1; gprim = idx; ginside = (t1 == t2);
+        }
+    }
+    // the owner of the j-th live ray reads its result from group j
+    const unsigned rank = (unsigned)__popc(live & ((1u << lane) - 1u));
+    const int from = (int)((rank << log2g) & 31u);
+    T = __shfl_sync(0xffffffffu, gT, from);
+    prim = __shfl_sync(0xffffffffu, gprim, from);
+    inside = __shfl_sync(0xffffffffu, (int)ginside, from) != 0;
 }
 
 // pt:125-129 — mean over SPP, running mean over frames, store.  Frame 0 does not read the image: the reference
@@ -372,13 +473,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // ------------------------------------------------------------------------------------------------------------
 // The megakernel.  Work item = one pixel (all its SPP samples, RNG stream intact).  Work index -> pixel through
 // 8x4 tiles so a freshly filled warp starts on a compact footprint.
-// kRing: stage primary rays through the per-warp shared-memory ring (costs 2 KB per warp; the host turns it off when the
-// scene block is so large that the ring would lower the number of resident CTAs).
+// kRing: stage primary rays through the per-warp shared-memory ring (2 KB per warp; the host turns it off when the scene
+// block is so large that the ring would lower the number of resident CTAs).
 template <bool kStats, bool kRing>
 __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const __grid_constant__ RenderParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_ring[kRing ? (kMegaThreads / 32) * 8 * kQueue : 1];
     float4* sblock = reinterpret_cast<float4*>(smem_raw);
 
     // ---- stage the packed scene: one elected thread arms the barrier and issues the bulk copies
@@ -402,14 +504,11 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long* stats = kStats ? P.stats : nullptr;
 
-    // Per-warp ring of ready-made primary rays.  Ray generation (4 RNG draws, 2 normalisations, sin/cos, 8 matrix rows)
-    // runs with all 32 lanes converged on one 8x4 pixel tile and is amortised over 32 pixels, instead of running for the
-    // ~12 lanes that happen to be idle in every iteration of the bounce loop.
-    constexpr int kQ = kRing ? kQueue : 1;
-    __shared__ float q_f[kRing ? kMegaThreads / 32 : 1][6][kQ];       // origin xyz, direction xyz
-    __shared__ uint32_t q_u[kRing ? kMegaThreads / 32 : 1][2][kQ];    // rng state after the 4 primary draws; px | lrow << 16
-    const unsigned w = threadIdx.x >> 5;
-    unsigned q_head = 0, q_count = 0;                          // warp-uniform
+    // Ring of ready-made primary rays.  Ray generation (4 RNG draws, 2 normalisations, sin/cos, 8 matrix rows) runs with
+    // all 32 lanes converged on one 8x4 pixel tile and is amortised over 32 pixels, instead of running for the ~12 lanes
+    // that happen to be idle in every iteration of the bounce loop.
+    uint32_t* ring = s_ring + (kRing ? (threadIdx.x >> 5) * 8 * kQueue : 0);   // [8][kQueue]: o.xyz d.xyz rng px|lrow<<16
+    unsigned q_head = 0, q_count = 0;                                           // warp-uniform
 
     Path p;
     bool alive = false;         // lane owns an unfinished pixel
@@ -439,9 +538,10 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                         g.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
                         primary_ray(P, g);
                         const unsigned slot = (q_head + q_count + (unsigned)__popc(vmask & lt_mask)) & (kQueue - 1);
-                        q_f[w][0][slot] = g.o.x; q_f[w][1][slot] = g.o.y; q_f[w][2][slot] = g.o.z;
-                        q_f[w][3][slot] = g.d.x; q_f[w][4][slot] = g.d.y; q_f[w][5][slot] = g.d.z;
-                        q_u[w][0][slot] = g.rng; q_u[w][1][slot] = (uint32_t)x | ((uint32_t)lr << 16);
+                        ring[0 * kQueue + slot] = __float_as_uint(g.o.x); ring[1 * kQueue + slot] = __float_as_uint(g.o.y);
+                        ring[2 * kQueue + slot] = __float_as_uint(g.o.z); ring[3 * kQueue + slot] = __float_as_uint(g.d.x);
+                        ring[4 * kQueue + slot] = __float_as_uint(g.d.y); ring[5 * kQueue + slot] = __float_as_uint(g.d.z);
+                        ring[6 * kQueue + slot] = g.rng; ring[7 * kQueue + slot] = (uint32_t)x | ((uint32_t)lr << 16);
                     }
                     q_count += (unsigned)__popc(vmask);
                     __syncwarp();
@@ -453,10 +553,10 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                 const unsigned rank = (unsigned)__popc(dead & lt_mask);
                 if (!alive && rank < take) {
                     const unsigned slot = (q_head + rank) & (kQueue - 1);
-                    p.o = mk(q_f[w][0][slot], q_f[w][1][slot], q_f[w][2][slot]);
-                    p.d = mk(q_f[w][3][slot], q_f[w][4][slot], q_f[w][5][slot]);
-                    p.rng = q_u[w][0][slot];
-                    const uint32_t xy = q_u[w][1][slot];
+                    p.o = mk(__uint_as_float(ring[0 * kQueue + slot]), __uint_as_float(ring[1 * kQueue + slot]), __uint_as_float(ring[2 * kQueue + slot]));
+                    p.d = mk(__uint_as_float(ring[3 * kQueue + slot]), __uint_as_float(ring[4 * kQueue + slot]), __uint_as_float(ring[5 * kQueue + slot]));
+                    p.rng = ring[6 * kQueue + slot];
+                    const uint32_t xy = ring[7 * kQueue + slot];
                     p.px = (int)(xy & 0xffffu); p.lrow = (int)(xy >> 16);
                     p.thr = mk(1.0f, 1.0f, 1.0f); p.rad = mk(0.0f, 0.0f, 0.0f); p.irr = mk(0.0f, 0.0f, 0.0f);
                     p.depth = 0; p.sample = 0;
@@ -493,8 +593,10 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, alive)) {
-            if (exhausted && q_count == 0u) break;
+        const bool starved = exhausted && q_count == 0u;       // this warp can no longer refill its lanes
+        const unsigned live = __ballot_sync(0xffffffffu, alive);
+        if (live == 0u) {
+            if (starved) break;
             continue;   // the tile held only padding pixels; fetch again
         }
         if (alive && fresh) {      // SPP > 1: the next sample continues this pixel's RNG stream, so it is generated in place
@@ -503,9 +605,19 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
             fresh = false;
             if (kStats) atomicAdd(stats, 1ull);
         }
-        // ---- one bounce for every live lane
+        // ---- one bounce for every live lane.  In the tail of the frame (nothing left to pull, at most half the lanes alive)
+        //      the lanes of the warp share the fold of the remaining rays, which shortens the frame's critical path.
+        float T = kFloatMax;
+        int prim = -1;
+        bool inside = false;
+        const unsigned n_live = (unsigned)__popc(live);
+        if (starved && n_live <= (unsigned)PTB_COOP_MAX && P.ray_depth > 0) {
+            trace_group(sc, lane, live, n_live, p.o, p.d, T, prim, inside);
+        } else if (alive && P.ray_depth > 0) {
+            trace_any(sc, p.o, p.d, T, prim, inside);
+        }
         if (alive) {
-            const bool go = P.ray_depth > 0 ? bounce(P, sc, p, stats) : false;
+            const bool go = P.ray_depth > 0 ? shade(P, sc, p, T, prim, inside, stats) : false;
             if (!go) {
                 p.irr = p.irr + p.rad;                // pt:123
                 if (++p.sample < P.spp) fresh = true;
