@@ -88,7 +88,10 @@ int ptb_set_frame(ptb_ctx* ctx, int frame); /* checkpoint/resume of a progressiv
 
 /* PathTracer.Result readback (the reference hands the GL texture to ScreenEffect, MainWindow.cs:51). */
 int ptb_read_result(ptb_ctx* ctx, float* rgba32f);            /* synchronous: W*H*4 floats, row 0 = y 0 */
-int ptb_read_result_async(ptb_ctx* ctx, float* pinned_rgba32f); /* enqueued; pair with ptb_synchronize */
+/* Pipelined read-back: snapshots the image on the render stream and copies the snapshot to (pinned) host memory on a
+ * second stream, so the PCIe transfer of frame f overlaps Render() of frame f+1.  Up to two reads in flight; the data is
+ * valid after ptb_synchronize(). */
+int ptb_read_result_async(ptb_ctx* ctx, float* pinned_rgba32f);
 int ptb_write_result(ptb_ctx* ctx, const float* rgba32f);     /* restore an accumulation image */
 int ptb_synchronize(ptb_ctx* ctx);
 
@@ -118,8 +121,9 @@ int ptb_read_stats(ptb_ctx* ctx, unsigned long long* counters3);
 
 /* Unit-level probes used by the parity tests: evaluate device functions on arrays (host in, host out).
  * op: 0 sincos (in n, out 2n)  1 exp (n -> n)  2 pcg stream (in: 1 seed as uint32 bits, out n floats)
- *     3 texture(samplerCube) (in 3n dirs, out 3n)  4 RayTrace fold over the current scene (in 6n rays, out 12n)
- *     5 min/max/rcp/sqrt probe (in 2n, out 4n) */
+ *     3 texture(samplerCube) (in 3n dirs, out 3n)  4 RayTrace fold over the packed scene (in 6n rays, out 12n)
+ *     5 min/max/rcp/sqrt probe (in 2n, out 4n)  6 RayTrace fold over the raw UBO bytes (proxy view; as 4)
+ *     7 group-cooperative fold of the frame tail: rays are processed k = in[6n] at a time per warp (in 6n+1, out 12n) */
 int ptb_debug_eval(ptb_ctx* ctx, int op, const float* in, int n, float* out);
 
 #ifdef __cplusplus

@@ -66,6 +66,12 @@ struct ptb_ctx {
     bool stats_on = false;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // pipelined read-back: snapshot on the render stream, D2H on the copy stream, two staging buffers in flight
+    cudaStream_t copy_stream = nullptr;
+    float4* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_snap[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    int stage_next = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int launches = 0;
@@ -245,6 +251,8 @@ void ptb_destroy(ptb_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_objects); cudaFree(c->d_block); cudaFree(c->d_env_faces); cudaFree(c->d_env);
     cudaFree(c->d_image); cudaFree(c->d_counters); cudaFree(c->d_stats);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_stage[i]); if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -397,13 +405,37 @@ int ptb_set_frame(ptb_ctx* c, int frame)
 int ptb_read_result_async(ptb_ctx* c, float* dst)
 {
     if (!c || !dst) return fail(PTB_E_INVALID, "null argument");
-    CU(cudaMemcpyAsync(dst, c->d_image, (size_t)c->local_rows * c->width * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->local_rows * c->width * sizeof(float4);
+    if (bytes == 0) return PTB_OK;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->ev_snap[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    if (c->stage_bytes < bytes) {
+        CU(cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; ++i) { if (c->d_stage[i]) CU(cudaFree(c->d_stage[i])); c->d_stage[i] = nullptr; CU(cudaMalloc(&c->d_stage[i], bytes)); }
+        c->stage_bytes = bytes;
+    }
+    // The image is accumulated in place, so the next Render() would race with a slow PCIe copy: snapshot it on the render
+    // stream (HBM -> HBM), then let the copy stream move the snapshot to the host while the next frame renders.
+    const int k = c->stage_next;
+    c->stage_next ^= 1;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[k], 0));       // the D2H that last used this staging buffer is done
+    CU(cudaMemcpyAsync(c->d_stage[k], c->d_image, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_snap[k], c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_snap[k], 0));
+    CU(cudaMemcpyAsync(dst, c->d_stage[k], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[k], c->copy_stream));
     return PTB_OK;
 }
 int ptb_read_result(ptb_ctx* c, float* dst)
 {
-    const int rc = ptb_read_result_async(c, dst);
-    if (rc != PTB_OK) return rc;
+    if (!c || !dst) return fail(PTB_E_INVALID, "null argument");
+    CU(cudaMemcpyAsync(dst, c->d_image, (size_t)c->local_rows * c->width * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return PTB_OK;
 }
@@ -418,6 +450,7 @@ int ptb_synchronize(ptb_ctx* c)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     CU(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
     return PTB_OK;
 }
 
@@ -507,6 +540,7 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
     case 3: in_f = 3 * (size_t)n; out_f = 3 * (size_t)n; break;
     case 4: case 6: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
     case 5: in_f = 2 * (size_t)n; out_f = 4 * (size_t)n; break;
+    case 7: in_f = 6 * (size_t)n + 1; out_f = 12 * (size_t)n; break;
     default: return fail(PTB_E_INVALID, "unknown debug op %d", op);
     }
     float *d_in = nullptr, *d_out = nullptr;
@@ -531,6 +565,16 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
             if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->block_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
             dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : 0);
         } else if (op == 5) dbg_arith_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
+        else if (op == 7) {
+            rc = sync_scene(c);
+            if (rc != PTB_OK) break;
+            const int k = (int)in[6 * (size_t)n];
+            if (k < 1 || k > 32) { rc = fail(PTB_E_INVALID, "group size %d outside [1,32]", k); break; }
+            RenderParams P;
+            fill_params(c, P);
+            if (cudaFuncSetAttribute(dbg_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->block_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
+            dbg_group_kernel<<<(n + k - 1) / k, 32, c->block_bytes, c->stream>>>(P, d_in, n, d_out, k);
+        }
         c->launches++;
         if (cudaGetLastError() != cudaSuccess) { rc = fail(PTB_E_CUDA, "debug kernel launch failed"); break; }
         if (cudaMemcpyAsync(out, d_out, out_f * sizeof(float), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = fail(PTB_E_CUDA, "D2H failed"); break; }

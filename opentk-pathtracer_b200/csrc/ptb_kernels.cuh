@@ -903,6 +903,40 @@ __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const f
         dbg_trace_one(sc, rays, i, out);
     }
 }
+// The group-cooperative fold on its own: each warp serves k rays at a time, parked on scattered lanes (3 + 7j mod 32).
+__global__ void dbg_group_kernel(const __grid_constant__ RenderParams P, const float* rays, int n, float* out, int k)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    {
+        const float4* src = P.scene;
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        for (int q = threadIdx.x; q < P.block_bytes / 16; q += blockDim.x) dst[q] = src[q];
+    }
+    __syncthreads();
+    PackedScene sc; sc.base = reinterpret_cast<const float4*>(smem_raw); sc.nS = P.n_spheres; sc.nC = P.n_cuboids;
+    sc.off_aux = P.off_aux; sc.off_cmin = P.off_cmin; sc.off_cmax = P.off_cmax; sc.off_mat = P.off_mat;
+    const unsigned lane = threadIdx.x & 31u;
+    const int j = (int)(((lane + 29u) * 23u) & 31u);        // inverse of lane = (3 + 7j) mod 32
+    const int i = blockIdx.x * k + j;
+    const bool alive = j < k && i < n;
+    V3 o = mk(0.0f, 0.0f, 0.0f), d = mk(0.0f, 0.0f, 1.0f);
+    if (alive) { o = mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]); d = mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]); }
+    const unsigned live = __ballot_sync(0xffffffffu, alive);
+    if (live == 0u) return;
+    float T; int prim; bool inside;
+    trace_group(sc, lane, live, (unsigned)__popc(live), o, d, T, prim, inside);
+    if (!alive) return;
+    float* q = out + 12 * i;
+    const bool hit = T != kFloatMax;
+    q[0] = hit ? 1.0f : 0.0f; q[1] = T; q[2] = (hit && inside) ? 1.0f : 0.0f; q[3] = 0.0f;
+    for (int m = 4; m < 12; ++m) q[m] = 0.0f;
+    if (hit) {
+        const V3 pos = o + d * T;
+        const V3 nn = surface_normal(sc, prim, pos);
+        q[4] = pos.x; q[5] = pos.y; q[6] = pos.z; q[7] = nn.x; q[8] = nn.y; q[9] = nn.z;
+        q[10] = sc.mat(prim, 0).x; q[11] = sc.mat(prim, 1).x;
+    }
+}
 __global__ void dbg_arith_kernel(const float* in, int n, float* out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -72,7 +72,10 @@ class TiledPathTracer:
     """One rank's share of a frame: a PathTracer restricted to this rank's stripes + the per-frame gather.
 
     Usage (one process per GPU, torch.distributed initialised with nccl):
-        tp = TiledPathTracer(tracer, rank, world); tp.render(); full = tp.gather()   # full image on rank 0
+        tp = TiledPathTracer(tracer, rank, world)
+        tp.render(); full = tp.gather()              # simple: full image on rank 0, in stream order
+        for f in range(n): tp.step()                  # pipelined: the gather of frame f overlaps the render of frame f+1
+        full = tp.flush()
     """
 
     def __init__(self, tracer, rank: int, world: int, stripe_rows: int = DEFAULT_STRIPE_ROWS, device=None):
@@ -89,35 +92,65 @@ class TiledPathTracer:
         assert nbytes >= self.max_rows * self.width * 16
         self._holder = _DeviceBuffer(ptr, (self.max_rows, self.width, 4))
         self.local = torch.as_tensor(self._holder, device=self.device)
-        self.staging = torch.empty_like(self.local)
-        self.full = torch.empty((self.height, self.width, 4), dtype=torch.float32, device=self.device) if rank == 0 else None
-        self._pending = None
+        # two of everything that a gather in flight reads or writes, so frame f+1 never waits for frame f's exchange
+        self.staging = [torch.empty_like(self.local) for _ in range(2)]
+        self.gathered = [torch.empty((world,) + tuple(self.local.shape), dtype=torch.float32, device=self.device) if rank == 0 else None
+                         for _ in range(2)]
+        self.full = [torch.empty((self.height, self.width, 4), dtype=torch.float32, device=self.device) if rank == 0 else None
+                     for _ in range(2)]
+        self._k = 0
+        self._pending = None       # (buffer index, work)
+        self._last_full = None
 
     def render(self, frames: int = 1) -> None:
         self.tracer.Render(frames)
 
-    def gather_async(self):
-        """Snapshot the local stripes (so the next frame may overwrite them) and start the gather."""
-        self.staging.copy_(self.local, non_blocking=True)
-        gathered, work = gather_stripes(self.staging, self.world, dst=0, async_op=True)
-        self._pending = (gathered, work)
+    def _start_gather(self):
+        """Snapshot the local stripes (the next frame overwrites them in place) and start the one collective of the frame."""
+        import torch.distributed as dist
 
-    def finish_gather(self):
-        """Wait for the outstanding gather; on rank 0 de-interleave into the row-major image and return it."""
+        k = self._k
+        self._k ^= 1
+        self.staging[k].copy_(self.local, non_blocking=True)
+        if self.world == 1:
+            work = None
+            if self.rank == 0:
+                self.gathered[k][0].copy_(self.staging[k], non_blocking=True)
+        elif self.rank == 0:
+            work = dist.gather(self.staging[k], list(self.gathered[k].unbind(0)), dst=0, async_op=True)
+        else:
+            work = dist.gather(self.staging[k], None, dst=0, async_op=True)
+        self._pending = (k, work)
+
+    def _finish_gather(self):
+        """Wait (in stream order) for the outstanding gather; rank 0 de-interleaves it into a row-major image."""
         import ctypes as C
 
         from . import _lib
 
         if self._pending is None:
-            return self.full
-        gathered, work = self._pending
+            return self._last_full
+        k, work = self._pending
         self._pending = None
         if work is not None:
             work.wait()
         if self.rank == 0:
-            _lib.check(self.tracer._L.ptb_deinterleave_device(self.tracer._ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(self.full.data_ptr())))
-        return self.full
+            _lib.check(self.tracer._L.ptb_deinterleave_device(self.tracer._ctx, C.c_void_p(self.gathered[k].data_ptr()),
+                                                              C.c_void_p(self.full[k].data_ptr())))
+            self._last_full = self.full[k]
+        return self._last_full
 
     def gather(self):
-        self.gather_async()
-        return self.finish_gather()
+        self._start_gather()
+        return self._finish_gather()
+
+    def step(self):
+        """Render the next frame, complete the PREVIOUS frame's gather (which ran beside this render on NCCL's stream), then
+        start this frame's gather.  Returns the previous frame's full image on rank 0 (None for the first step)."""
+        self.tracer.Render()
+        done = self._finish_gather() if self._pending is not None else None
+        self._start_gather()
+        return done
+
+    def flush(self):
+        return self._finish_gather()

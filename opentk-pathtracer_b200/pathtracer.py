@@ -209,6 +209,10 @@ class PathTracer:
         a = np.ascontiguousarray(image, dtype=np.float32)
         _lib.check(self._L.ptb_write_result(self._ctx, a.ctypes.data_as(C.c_void_p)))
 
+    def ReadResultAsync(self, pinned_host_ptr: int) -> None:
+        """Enqueue a pipelined read-back of the image into pinned host memory (valid after Synchronize())."""
+        _lib.check(self._L.ptb_read_result_async(self._ctx, C.c_void_p(pinned_host_ptr)))
+
     def Synchronize(self) -> None:
         _lib.check(self._L.ptb_synchronize(self._ctx))
 

@@ -116,6 +116,30 @@ def test_closest_hit_fold_bit_exact(tracer256, oracle, default_scene):
         assert_same(got, ref, name)
 
 
+def test_group_cooperative_fold_bit_exact(ptb, oracle, env256, camera):
+    """The tail-of-frame fold (g lanes share one ray, closed-form reduction of the order-dependent closest hit) against the
+    sequential oracle fold, for every group size, with many origins INSIDE primitives (the case that needs the second pass)
+    and a scene with overlapping boxes/spheres."""
+    rng = np.random.default_rng(11)
+    for scene in (ptb.load_default_scene(), ptb.synthetic_scene(96, 40, seed=5)):
+        pt = make_tracer(ptb, env256, 16, 16, scene, camera)
+        n = 6000
+        o = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.array([40, 25, 25], np.float32) + np.array([0, 0, -10], np.float32)
+        centres = np.stack([s.Position for s in scene.spheres])
+        pick = rng.integers(0, len(scene.spheres), n // 2)
+        radii = np.array([s.Radius for s in scene.spheres], np.float32)[pick, None]
+        o[: n // 2] = centres[pick] + (rng.random((n // 2, 3)).astype(np.float32) - np.float32(0.5)) * radii
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        rays = np.concatenate([o, d], 1).astype(np.float32)
+        ref = oracle.ray_trace(rays, scene.ubo_bytes(), scene.max_spheres, len(scene.spheres), len(scene.cuboids))
+        assert ref[:, 2].sum() > 500
+        for k in (1, 2, 3, 4, 5, 8, 9, 16, 17, 32):
+            got = pt.DebugEval(7, np.append(rays.ravel(), np.float32(k)), n, 12 * n).reshape(-1, 12)
+            assert_same(got, ref, f"group fold, {k} live rays per warp, {len(scene.spheres)} spheres")
+        pt.Dispose()
+
+
 # ------------------------------------------------------------------------------- image parity
 CASES = [
     # name, W, H, frames, kwargs
@@ -313,6 +337,22 @@ def test_reset_setsize_and_resume(ptb, oracle, env256, default_scene, camera):
     pt.Render()
     assert_same(pt.Result, oracle_render(oracle, ptb.scene, default_scene, camera, env256, 64, 80, 1), "after SetSize")
     pt.Dispose()
+
+
+def test_pipelined_readback(ptb, env256, default_scene, camera):
+    """ptb_read_result_async: snapshot + copy on a second stream; two reads in flight while the next frames render."""
+    import torch
+    pt = make_tracer(ptb, env256, 320, 200, default_scene, camera)
+    bufs = [torch.empty((200, 320, 4), dtype=torch.float32).pin_memory() for _ in range(3)]
+    for f in range(3):
+        pt.Render()
+        pt.ReadResultAsync(bufs[f].data_ptr())
+    pt.Synchronize()
+    ref = make_tracer(ptb, env256, 320, 200, default_scene, camera)
+    for f in range(3):
+        ref.Render()
+        assert_same(bufs[f].numpy(), ref.Result, f"async read of frame {f}")
+    pt.Dispose(); ref.Dispose()
 
 
 def test_error_codes(ptb, env256):
