@@ -113,6 +113,10 @@ int ptb_max_local_rows(ptb_ctx* ctx);
 
 /* Kernel selection and introspection. */
 int ptb_set_kernel(ptb_ctx* ctx, int kernel);
+/* Frame pipelining.  n >= 2 (default 2): consecutive Render() calls are traced on n alternating streams into per-frame
+ * scratch images and folded into the accumulation image by a stream-ordered blend kernel (same arithmetic as
+ * compute.glsl:126-129), so the tail of frame f overlaps the start of frame f+1.  n <= 1: one stream, in-place blend. */
+int ptb_set_overlap(ptb_ctx* ctx, int n);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
 /* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ptb_max_local_rows": (C.c_int, [_P]),
     "ptb_deinterleave_device": (C.c_int, [_P, C.c_void_p, C.c_void_p]),
     "ptb_set_kernel": (C.c_int, [_P, C.c_int]),
+    "ptb_set_overlap": (C.c_int, [_P, C.c_int]),
     "ptb_kernel_launches": (C.c_int, [_P]),
     "ptb_last_render_ms": (C.c_float, [_P]),
     "ptb_set_stats": (C.c_int, [_P, C.c_int]),

@@ -33,6 +33,7 @@ int fail(int code, const char* fmt, ...)
 
 constexpr int kBasicBytes = 144;   // MainWindow.cs:196
 constexpr int kMaxSmem = 227 * 1024;
+constexpr int kMaxOverlap = 4;
 
 } // namespace
 
@@ -72,6 +73,20 @@ struct ptb_ctx {
     size_t stage_bytes = 0;
     cudaEvent_t ev_snap[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int stage_next = 0;
+    // pipelined frames: `overlap` trace streams, each with its own scratch image and work counters, and one blend stream.
+    // Frame f is traced on stream f % overlap into scratch[f % overlap]; the blend stream folds the estimates into the image
+    // in frame order; the user-visible stream waits for each blend.  overlap <= 1: classic in-place accumulation.
+    int overlap = 2;
+    cudaStream_t trace_stream[kMaxOverlap] = {};
+    cudaStream_t blend_stream = nullptr;
+    float4* d_scratch[kMaxOverlap] = {};
+    unsigned int* d_slot_counters[kMaxOverlap] = {};
+    cudaEvent_t ev_trace_done[kMaxOverlap] = {}, ev_blend_done[kMaxOverlap] = {};
+    bool blend_recorded[kMaxOverlap] = {};
+    cudaEvent_t ev_inputs = nullptr;            // scene / environment / image edits enqueued on `stream`
+    unsigned inputs_version = 1, seen_version[kMaxOverlap + 1] = {};
+    size_t scratch_bytes = 0;
+    unsigned long long launch_seq = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int launches = 0;
@@ -81,6 +96,55 @@ struct ptb_ctx {
 };
 
 namespace {
+
+int sync_all(ptb_ctx* c)
+{
+    CU(cudaSetDevice(c->device));
+    if (c->stream) CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < kMaxOverlap; ++i) if (c->trace_stream[i]) CU(cudaStreamSynchronize(c->trace_stream[i]));
+    if (c->blend_stream) CU(cudaStreamSynchronize(c->blend_stream));
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
+    return PTB_OK;
+}
+
+// Anything enqueued on the user-visible stream that the trace / blend streams must see (scene repack, environment, image writes).
+int mark_inputs(ptb_ctx* c)
+{
+    if (!c->ev_inputs) CU(cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_inputs, c->stream));
+    c->inputs_version++;
+    return PTB_OK;
+}
+
+int ensure_pipeline(ptb_ctx* c)
+{
+    const size_t bytes = c->image_bytes;
+    for (int i = 0; i < c->overlap; ++i) {
+        if (!c->trace_stream[i]) {
+            CU(cudaStreamCreateWithFlags(&c->trace_stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c->ev_trace_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_blend_done[i], cudaEventDisableTiming));
+            CU(cudaMalloc(&c->d_slot_counters[i], 2 * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(c->d_slot_counters[i], 0, 2 * sizeof(unsigned int), c->stream));
+            CU(mark_inputs(c) == PTB_OK ? cudaSuccess : cudaErrorUnknown);
+        }
+    }
+    if (!c->blend_stream) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->blend_stream, cudaStreamNonBlocking, hi));   // small kernel, must not queue behind a persistent grid
+    }
+    if (c->scratch_bytes != bytes) {
+        CU(sync_all(c) == PTB_OK ? cudaSuccess : cudaErrorUnknown);
+        for (int i = 0; i < kMaxOverlap; ++i) { if (c->d_scratch[i]) CU(cudaFree(c->d_scratch[i])); c->d_scratch[i] = nullptr; }
+        for (int i = 0; i < c->overlap; ++i) CU(cudaMalloc(&c->d_scratch[i], bytes));
+        c->scratch_bytes = bytes;
+        for (int i = 0; i < kMaxOverlap; ++i) c->blend_recorded[i] = false;
+    } else {
+        for (int i = 0; i < c->overlap; ++i) if (!c->d_scratch[i]) CU(cudaMalloc(&c->d_scratch[i], bytes));
+    }
+    return PTB_OK;
+}
 
 int compute_local_rows(int height, int rank, int world, int stripe_rows)
 {
@@ -92,7 +156,7 @@ int compute_local_rows(int height, int rank, int world, int stripe_rows)
 
 int alloc_image(ptb_ctx* c)
 {
-    CU(cudaSetDevice(c->device));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     c->local_rows = compute_local_rows(c->height, c->rank, c->world, c->stripe_rows);
     // capacity = the largest local image any rank holds, so gathered buffers are uniform
     const int max_rows = compute_local_rows(c->height, 0, c->world, c->stripe_rows);
@@ -101,7 +165,7 @@ int alloc_image(ptb_ctx* c)
     CU(cudaMalloc(&c->d_image, bytes));
     CU(cudaMemsetAsync(c->d_image, 0, bytes, c->stream));
     c->image_bytes = bytes;
-    return PTB_OK;
+    return mark_inputs(c);
 }
 
 void layout_block(ptb_ctx* c)
@@ -121,6 +185,7 @@ int sync_scene(ptb_ctx* c)
     layout_block(c);
     if (c->block_bytes > kMaxSmem - 1024)
         return fail(PTB_E_INVALID, "scene block of %d bytes does not fit shared memory (%d spheres, %d cuboids)", c->block_bytes, c->n_spheres, c->n_cuboids);
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }     // kernels in flight still read the old block / UBO copy
     if ((size_t)c->block_bytes > c->block_capacity) {
         if (c->d_block) CU(cudaFree(c->d_block));
         c->d_block = nullptr;
@@ -137,7 +202,7 @@ int sync_scene(ptb_ctx* c)
         CU(cudaGetLastError());
     }
     c->scene_dirty = false;
-    return PTB_OK;
+    return mark_inputs(c);
 }
 
 void fill_params(ptb_ctx* c, RenderParams& P)
@@ -163,40 +228,73 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.tiles_magic = (P.tiles_x > 1 && (unsigned long long)P.tiles_total * P.tiles_x < (1ull << 32)) ? (unsigned)(((1ull << 32) + P.tiles_x - 1) / P.tiles_x) : 0u;
 }
 
+template <class F>
+int with_mega(ptb_ctx* c, bool stats, F&& launch)
+{
+    if (c->mega_ring) return stats ? launch(megakernel<true, true>) : launch(megakernel<false, true>);
+    return stats ? launch(megakernel<true, false>) : launch(megakernel<false, false>);
+}
+
 int launch_frame(ptb_ctx* c)
 {
     RenderParams P;
     fill_params(c, P);
+    P.scratch = nullptr;
     if (c->kernel == PTB_KERNEL_NAIVE) {
         dim3 grid((c->width + 7) / 8, (c->local_rows + 7) / 8, 1), block(8, 8, 1);   // PathTracer.cs:121
         if (grid.y > 0) naive_kernel<<<grid, block, 0, c->stream>>>(P);
-    } else {
-        const int smem = c->block_bytes;
-        if (c->mega_smem_set != smem) {
-            CU(cudaFuncSetAttribute(megakernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            int with_ring = 0, without = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true>, kMegaThreads, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false>, kMegaThreads, smem));
-            if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
-            c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
-            c->mega_grid = c->sm_count * (c->mega_ring ? with_ring : without);
-            c->mega_smem_set = smem;
-        }
-        if (c->local_rows > 0) {
-            if (c->mega_ring) {
-                if (c->stats_on) megakernel<true, true><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
-                else megakernel<false, true><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
-            } else {
-                if (c->stats_on) megakernel<true, false><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
-                else megakernel<false, false><<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P);
-            }
+        c->launches++;
+        CU(cudaGetLastError());
+        c->frame++;
+        return mark_inputs(c);      // the image changed on the user-visible stream
+    }
+    const int smem = c->block_bytes;
+    if (c->mega_smem_set != smem) {
+        CU(cudaFuncSetAttribute(megakernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(megakernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(megakernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(megakernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int with_ring = 0, without = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true>, kMegaThreads, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false>, kMegaThreads, smem));
+        if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
+        c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
+        c->mega_grid = c->sm_count * (c->mega_ring ? with_ring : without);
+        c->mega_smem_set = smem;
+    }
+    if (c->local_rows > 0) {
+        if (c->overlap <= 1) {
+            // classic: accumulate in place on the user-visible stream
+            const int rc = with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P); return PTB_OK; });
+            if (rc != PTB_OK) return rc;
+            c->launches++;
+            CU(cudaGetLastError());
+            { const int r2 = mark_inputs(c); if (r2 != PTB_OK) return r2; }
+        } else {
+            { const int rc = ensure_pipeline(c); if (rc != PTB_OK) return rc; }
+            const int s = (int)(c->launch_seq % (unsigned long long)c->overlap);
+            cudaStream_t ts = c->trace_stream[s];
+            if (c->seen_version[s] != c->inputs_version) { CU(cudaStreamWaitEvent(ts, c->ev_inputs, 0)); c->seen_version[s] = c->inputs_version; }
+            if (c->blend_recorded[s]) CU(cudaStreamWaitEvent(ts, c->ev_blend_done[s], 0));      // scratch[s] has been consumed
+            P.scratch = c->d_scratch[s];
+            P.counters = c->d_slot_counters[s];
+            const int rc = with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, ts>>>(P); return PTB_OK; });
+            if (rc != PTB_OK) return rc;
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(c->ev_trace_done[s], ts));
+            cudaStream_t bs = c->blend_stream;
+            if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
+            CU(cudaStreamWaitEvent(bs, c->ev_trace_done[s], 0));
+            const size_t n = (size_t)c->local_rows * c->width;
+            blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_scratch[s], n, c->frame, P.blend);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(c->ev_blend_done[s], bs));
+            c->blend_recorded[s] = true;
+            CU(cudaStreamWaitEvent(c->stream, c->ev_blend_done[s], 0));       // whatever the host enqueues next sees this frame
+            c->launches += 2;
+            c->launch_seq++;
         }
     }
-    c->launches++;
-    CU(cudaGetLastError());
     c->frame++;   // PathTracer.cs:117 thisRenderNumFrame++
     return PTB_OK;
 }
@@ -248,7 +346,15 @@ void ptb_destroy(ptb_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    sync_all(c);
+    for (int i = 0; i < kMaxOverlap; ++i) {
+        cudaFree(c->d_scratch[i]); cudaFree(c->d_slot_counters[i]);
+        if (c->ev_trace_done[i]) cudaEventDestroy(c->ev_trace_done[i]);
+        if (c->ev_blend_done[i]) cudaEventDestroy(c->ev_blend_done[i]);
+        if (c->trace_stream[i]) cudaStreamDestroy(c->trace_stream[i]);
+    }
+    if (c->blend_stream) cudaStreamDestroy(c->blend_stream);
+    if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
     cudaFree(c->d_objects); cudaFree(c->d_block); cudaFree(c->d_env_faces); cudaFree(c->d_env);
     cudaFree(c->d_image); cudaFree(c->d_counters); cudaFree(c->d_stats);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -324,7 +430,7 @@ static int install_environment(ptb_ctx* c, int N)
     c->launches++;
     CU(cudaGetLastError());
     c->env_size = N;
-    return PTB_OK;
+    return mark_inputs(c);
 }
 
 int ptb_set_environment_rgba32f(ptb_ctx* c, int face_size, const float* six_faces)
@@ -464,11 +570,11 @@ int ptb_result_device_ptr(ptb_ctx* c, void** p, size_t* bytes)
 int ptb_set_stream(ptb_ctx* c, void* s)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
-    CU(cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
-    return PTB_OK;
+    return mark_inputs(c);
 }
 int ptb_width(ptb_ctx* c) { return c ? c->width : fail(PTB_E_INVALID, "ctx is null"); }
 int ptb_height(ptb_ctx* c) { return c ? c->height : fail(PTB_E_INVALID, "ctx is null"); }
@@ -500,7 +606,17 @@ int ptb_set_kernel(ptb_ctx* c, int k)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     if (k != PTB_KERNEL_MEGA && k != PTB_KERNEL_NAIVE) return fail(PTB_E_INVALID, "unknown kernel %d", k);
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     c->kernel = k;
+    return PTB_OK;
+}
+int ptb_set_overlap(ptb_ctx* c, int n)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (n < 0 || n > kMaxOverlap) return fail(PTB_E_INVALID, "overlap %d outside [0,%d]", n, kMaxOverlap);
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    c->overlap = n;
+    c->launch_seq = 0;
     return PTB_OK;
 }
 int ptb_kernel_launches(ptb_ctx* c) { return c ? c->launches : fail(PTB_E_INVALID, "ctx is null"); }
@@ -517,7 +633,7 @@ int ptb_set_stats(ptb_ctx* c, int enabled)
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     c->stats_on = enabled != 0;
     CU(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
-    return PTB_OK;
+    return mark_inputs(c);
 }
 int ptb_read_stats(ptb_ctx* c, unsigned long long* out3)
 {

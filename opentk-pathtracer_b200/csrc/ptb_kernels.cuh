@@ -59,6 +59,7 @@ struct RenderParams {
     const float4* scene;      // packed scene block in HBM
     const float4* env;        // padded cubemap
     float4* image;            // local accumulation image: local_rows x width
+    float4* scratch;          // pipelined mode: this frame's own estimate goes here (no read of `image`); blend_kernel folds it in
     unsigned int* counters;   // [0] work counter, [1] finished-CTA counter
     unsigned long long* stats;// optional: samples, traces, hits
     const unsigned char* raw_objects; // raw GameObjectsUBO bytes (naive proxy only)
@@ -419,7 +420,12 @@ __device__ __forceinline__ void trace_group(const PackedScene& sc, unsigned lane
 __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p)
 {
     const V3 irr = p.irr * P.inv_spp;
-    float4* px = P.image + (size_t)p.lrow * P.width + p.px;
+    const size_t at = (size_t)p.lrow * P.width + p.px;
+    if (P.scratch) {              // pipelined frames: the running mean is applied by blend_kernel, in frame order
+        P.scratch[at] = make_float4(irr.x, irr.y, irr.z, 1.0f);
+        return;
+    }
+    float4* px = P.image + at;
     V3 last = mk(0.0f, 0.0f, 0.0f);
     if (P.frame > 0) {
         const float4 l = *px;
@@ -427,6 +433,22 @@ __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& 
     }
     const V3 out = mix(last, irr, P.blend);
     *px = make_float4(out.x, out.y, out.z, 1.0f);
+}
+
+// pt:126-129 for pipelined frames: image = mix(image, this frame's estimate, 1/(frame+1)) — the same operations, in the same
+// order, as finish_pixel's in-place path; one thread per pixel, 128-bit loads and stores.
+__global__ void blend_kernel(float4* __restrict__ image, const float4* __restrict__ estimate, size_t n, int frame, float blend)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 e = estimate[i];
+    V3 last = mk(0.0f, 0.0f, 0.0f);
+    if (frame > 0) {
+        const float4 l = image[i];
+        last = mk(l.x, l.y, l.z);
+    }
+    const V3 out = mix(last, mk(e.x, e.y, e.z), blend);
+    image[i] = make_float4(out.x, out.y, out.z, 1.0f);
 }
 
 // local row -> global y for the stripe partition

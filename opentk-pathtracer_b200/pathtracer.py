@@ -199,6 +199,10 @@ class PathTracer:
     def SetKernel(self, kernel: int) -> None:
         _lib.check(self._L.ptb_set_kernel(self._ctx, kernel))
 
+    def SetOverlap(self, n: int) -> None:
+        """Frames in flight (ptb_set_overlap): >= 2 pipelines consecutive Render() calls, <= 1 renders in place."""
+        _lib.check(self._L.ptb_set_overlap(self._ctx, n))
+
     def SetTile(self, rank: int, world: int, stripe_rows: int = 8) -> None:
         _lib.check(self._L.ptb_set_tile(self._ctx, rank, world, stripe_rows))
 
