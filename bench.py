@@ -177,7 +177,10 @@ def run_ours(args, rank, world, local_rank):
     pt.GenerateAtmosphere(256, 50, 15, 0.5, 15.0)      # the default EnvironmentMap, produced on the GPU (MainWindow.cs:174-175)
     pt.LoadScene(scene)
     pt.SetCamera(cam)
-    tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev) if world > 1 else None
+    # N > 1: the fused exchange (blend kernel stores straight into rank 0's image over NVLink); PTB_EXCHANGE=nccl selects the
+    # NCCL gather + de-interleave path instead
+    fused = os.environ.get("PTB_EXCHANGE", "fused") != "nccl"
+    tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=fused) if world > 1 else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     inv_view = sc.matrix_bytes(sc.inverted(cam.View))
     view_pos = np.append(np.asarray(cam.Position, np.float32), np.float32(0)).tobytes()
@@ -186,6 +189,7 @@ def run_ours(args, rank, world, local_rank):
     host_bufs = [torch.empty((H if rank == 0 else 1, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     side = torch.cuda.Stream(device=dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    snap = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1) else None
     state = {"i": 0}
 
     def step_device():
@@ -209,22 +213,36 @@ def run_ours(args, rank, world, local_rank):
             pt.Render()
             pt.ReadResultAsync(host_bufs[i & 1].data_ptr())
         else:
-            full = tiled.step()
-            if rank == 0 and full is not None:
+            if fused:
+                # rank 0 owns the slot between acquire and release: snapshot it (HBM->HBM) there, copy to the host on a side stream
                 k = i & 1
-                cur = torch.cuda.current_stream(dev)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    host_bufs[k].copy_(full, non_blocking=True)
-                    copy_done[k].record(side)
-                cur.wait_event(copy_done[k])      # (cheap) keeps `full[k]` from being rewritten before its copy was issued
+
+                def consume(full, k=k):
+                    cur = torch.cuda.current_stream(dev)
+                    cur.wait_event(copy_done[k])             # the D2H that last read snap[k] is done
+                    snap[k].copy_(full, non_blocking=True)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        host_bufs[k].copy_(snap[k], non_blocking=True)
+                        copy_done[k].record(side)
+                tiled.step_fused(consumer=consume if rank == 0 else None)
+            else:
+                full = tiled.step()
+                if rank == 0 and full is not None:
+                    k = i & 1
+                    cur = torch.cuda.current_stream(dev)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        host_bufs[k].copy_(full, non_blocking=True)
+                        copy_done[k].record(side)
+                    cur.wait_event(copy_done[k])      # (cheap) keeps `full[k]` from being rewritten before its copy was issued
 
     def finish_e2e():
         if tiled is None:
             pt.Synchronize()
         else:
             full = tiled.flush()
-            if rank == 0:
+            if rank == 0 and not fused:
                 host_bufs[0].copy_(full, non_blocking=True)
             side.synchronize()
             torch.cuda.current_stream(dev).synchronize()
@@ -314,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "flushed every step by a 256 MiB memset on a concurrent stream, inside the timed region",
-                   "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); one gather to rank 0 per frame, overlapped with the next frame's render" if world > 1 else "single GPU, no collective",
+                   "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + ("exchange fused into the blend kernel: peer stores into rank 0's image over NVLink (CUDA IPC), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render") if world > 1 else "single GPU, no collective",
                    "kernel": "persistent megakernel (ptb::megakernel) + blend kernel per frame, 2 frames in flight (ptb_set_overlap)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "ptb::megakernel<false>",
@@ -331,6 +349,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(pt)
+    if tiled is not None and fused:
+        tiled.exchange_ok()
     if rank == 0:
         print(json.dumps(line), flush=True)
     pt.Dispose()

@@ -111,6 +111,19 @@ int ptb_local_rows(ptb_ctx* ctx);
 int ptb_deinterleave_device(ptb_ctx* ctx, const void* gathered_device, void* full_device);
 int ptb_max_local_rows(ptb_ctx* ctx);
 
+/* Fused multi-GPU exchange (the alternative to an NCCL gather + de-interleave): every rank's blend kernel also stores its
+ * blended pixels into rank 0's row-major full image through a CUDA-IPC peer mapping (NVLink stores), with system-scope
+ * arrival / release flags for flow control.  Call order: ptb_set_tile, ptb_exchange_init(slots) on every rank;
+ * ptb_exchange_handle on rank 0 -> ship the 64 bytes to the other ranks -> ptb_exchange_attach there; then per frame
+ * ptb_render on every rank, and on rank 0 ptb_exchange_acquire (stream-ordered wait for all ranks, returns the frame's
+ * device buffer), consumer work on the context stream, ptb_exchange_release.  Waits time out after 4 s (ptb_exchange_status). */
+int ptb_exchange_init(ptb_ctx* ctx, int slots);
+int ptb_exchange_handle(ptb_ctx* ctx, void* handle64);
+int ptb_exchange_attach(ptb_ctx* ctx, const void* handle64);
+int ptb_exchange_acquire(ptb_ctx* ctx, void** full_device);
+int ptb_exchange_release(ptb_ctx* ctx);
+int ptb_exchange_status(ptb_ctx* ctx);
+
 /* Kernel selection and introspection. */
 int ptb_set_kernel(ptb_ctx* ctx, int kernel);
 /* Frame pipelining.  n >= 2 (default 2): consecutive Render() calls are traced on n alternating streams into per-frame

@@ -48,6 +48,12 @@ SIGNATURES = {
     "ptb_local_rows": (C.c_int, [_P]),
     "ptb_max_local_rows": (C.c_int, [_P]),
     "ptb_deinterleave_device": (C.c_int, [_P, C.c_void_p, C.c_void_p]),
+    "ptb_exchange_init": (C.c_int, [_P, C.c_int]),
+    "ptb_exchange_handle": (C.c_int, [_P, C.c_void_p]),
+    "ptb_exchange_attach": (C.c_int, [_P, C.c_void_p]),
+    "ptb_exchange_acquire": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "ptb_exchange_release": (C.c_int, [_P]),
+    "ptb_exchange_status": (C.c_int, [_P]),
     "ptb_set_kernel": (C.c_int, [_P, C.c_int]),
     "ptb_set_overlap": (C.c_int, [_P, C.c_int]),
     "ptb_kernel_launches": (C.c_int, [_P]),

@@ -87,6 +87,13 @@ struct ptb_ctx {
     unsigned inputs_version = 1, seen_version[kMaxOverlap + 1] = {};
     size_t scratch_bytes = 0;
     unsigned long long launch_seq = 0;
+    // fused multi-GPU exchange (ptb_exchange_*): rank 0 owns [flags | slots x full image]; other ranks map it through CUDA IPC
+    bool xch_on = false, xch_mapped = false;
+    int xch_slots = 0;
+    unsigned char* xch_block = nullptr;
+    size_t xch_image_bytes = 0;
+    unsigned long long xch_seq = 0, xch_acquired = 0, xch_released = 0;
+    unsigned int* d_xch_blocks = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int launches = 0;
@@ -286,7 +293,18 @@ int launch_frame(ptb_ctx* c)
             if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
             CU(cudaStreamWaitEvent(bs, c->ev_trace_done[s], 0));
             const size_t n = (size_t)c->local_rows * c->width;
-            blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_scratch[s], n, c->frame, P.blend);
+            if (c->xch_on) {
+                const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
+                const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
+                if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
+                blend_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(
+                    c->d_image, c->d_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->frame, P.blend,
+                    reinterpret_cast<float4*>(c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes), reinterpret_cast<ExchangeFlags*>(c->xch_block),
+                    slot, c->d_xch_blocks);
+                c->xch_seq++;
+            } else {
+                blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_scratch[s], n, c->frame, P.blend);
+            }
             CU(cudaGetLastError());
             CU(cudaEventRecord(c->ev_blend_done[s], bs));
             c->blend_recorded[s] = true;
@@ -302,6 +320,8 @@ int launch_frame(ptb_ctx* c)
 } // namespace
 
 extern "C" {
+
+static int exchange_close(ptb_ctx* c);
 
 const char* ptb_last_error(void) { return g_err; }
 int ptb_version(void) { return 100; }
@@ -353,6 +373,8 @@ void ptb_destroy(ptb_ctx* c)
         if (c->ev_blend_done[i]) cudaEventDestroy(c->ev_blend_done[i]);
         if (c->trace_stream[i]) cudaStreamDestroy(c->trace_stream[i]);
     }
+    exchange_close(c);
+    cudaFree(c->d_xch_blocks);
     if (c->blend_stream) cudaStreamDestroy(c->blend_stream);
     if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
     cudaFree(c->d_objects); cudaFree(c->d_block); cudaFree(c->d_env_faces); cudaFree(c->d_env);
@@ -600,6 +622,98 @@ int ptb_deinterleave_device(ptb_ctx* c, const void* gathered, void* full)
     c->launches++;
     CU(cudaGetLastError());
     return PTB_OK;
+}
+
+static int exchange_close(ptb_ctx* c)
+{
+    if (c->xch_block) {
+        if (c->xch_mapped) cudaIpcCloseMemHandle(c->xch_block);
+        else cudaFree(c->xch_block);
+    }
+    c->xch_block = nullptr;
+    c->xch_on = false;
+    c->xch_mapped = false;
+    return PTB_OK;
+}
+
+int ptb_exchange_init(ptb_ctx* c, int slots)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (slots < 1 || slots > 8) return fail(PTB_E_INVALID, "slots %d outside [1,8]", slots);
+    if (c->overlap < 2) return fail(PTB_E_STATE, "the fused exchange needs the pipelined mode (ptb_set_overlap >= 2)");
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    exchange_close(c);
+    c->xch_slots = slots;
+    c->xch_image_bytes = (((size_t)c->width * c->height * sizeof(float4)) + 255) & ~(size_t)255;
+    c->xch_seq = c->xch_acquired = c->xch_released = 0;
+    if (!c->d_xch_blocks) { CU(cudaMalloc(&c->d_xch_blocks, sizeof(unsigned int))); }
+    CU(cudaMemset(c->d_xch_blocks, 0, sizeof(unsigned int)));
+    CU(cudaDeviceSynchronize());
+    if (c->rank == 0) {
+        const size_t bytes = 4096 + (size_t)slots * c->xch_image_bytes;
+        CU(cudaMalloc(&c->xch_block, bytes));
+        CU(cudaMemset(c->xch_block, 0, bytes));
+        CU(cudaDeviceSynchronize());      // cudaMemset on device memory may return before it ran; peers must never see it land late
+        c->xch_on = true;
+    }
+    return PTB_OK;
+}
+int ptb_exchange_handle(ptb_ctx* c, void* handle64)
+{
+    if (!c || !handle64) return fail(PTB_E_INVALID, "null argument");
+    if (c->rank != 0 || !c->xch_block) return fail(PTB_E_STATE, "only rank 0 exports the exchange block, after ptb_exchange_init");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->xch_block));
+    memcpy(handle64, &h, 64);
+    return PTB_OK;
+}
+int ptb_exchange_attach(ptb_ctx* c, const void* handle64)
+{
+    if (!c || !handle64) return fail(PTB_E_INVALID, "null argument");
+    if (c->rank == 0) return fail(PTB_E_STATE, "rank 0 owns the exchange block");
+    if (c->xch_slots < 1) return fail(PTB_E_STATE, "call ptb_exchange_init first");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->xch_block = (unsigned char*)p;
+    c->xch_mapped = true;
+    c->xch_on = true;
+    return PTB_OK;
+}
+int ptb_exchange_acquire(ptb_ctx* c, void** full_device)
+{
+    if (!c || !full_device) return fail(PTB_E_INVALID, "null argument");
+    if (!c->xch_on || c->rank != 0) return fail(PTB_E_STATE, "acquire is rank 0's side of an initialised exchange");
+    if (c->xch_acquired >= c->xch_seq) return fail(PTB_E_STATE, "no rendered frame left to acquire");
+    const int slot = (int)(c->xch_acquired % (unsigned long long)c->xch_slots);
+    const unsigned target = (unsigned)((c->xch_acquired / (unsigned long long)c->xch_slots + 1) * (unsigned long long)c->world);
+    exchange_acquire_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), slot, target);
+    CU(cudaGetLastError());
+    c->launches++;
+    c->xch_acquired++;
+    *full_device = c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes;
+    return PTB_OK;
+}
+int ptb_exchange_release(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (!c->xch_on || c->rank != 0) return fail(PTB_E_STATE, "release is rank 0's side of an initialised exchange");
+    if (c->xch_released >= c->xch_acquired) return fail(PTB_E_STATE, "nothing acquired");
+    c->xch_released++;
+    exchange_release_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), (unsigned)c->xch_released);
+    CU(cudaGetLastError());
+    c->launches++;
+    return PTB_OK;
+}
+int ptb_exchange_status(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (!c->xch_on) return PTB_OK;
+    unsigned err = 0;
+    CU(cudaMemcpy(&err, c->xch_block + offsetof(ExchangeFlags, error), sizeof err, cudaMemcpyDeviceToHost));
+    return err ? fail(PTB_E_STATE, "a fused-exchange wait timed out (a rank stalled or the consumer never released a slot)") : PTB_OK;
 }
 
 int ptb_set_kernel(ptb_ctx* c, int k)

@@ -856,6 +856,90 @@ __global__ void atmosphere_kernel(const __grid_constant__ AtmosParams A, float4*
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Fused blend + exchange for one-process-per-GPU rendering.  Every rank folds its frame estimate into its local stripes AND
+// stores the blended pixels straight into rank 0's row-major image (a CUDA-IPC peer mapping: the stores travel over NVLink),
+// so the frame needs no staging copy, no NCCL gather and no de-interleave pass.  Flow control lives in a small flag block
+// next to the images on rank 0 (system-scope atomics): `consumed` = frames the consumer has released, `arrived[slot]` = ranks
+// that have finished writing that slot.  Every wait is bounded by a timeout that raises `error` instead of hanging the GPU.
+struct ExchangeFlags {
+    unsigned arrived[8];     // per slot, monotonic: += 1 per rank per use
+    unsigned pad0[8];
+    unsigned consumed;       // frames released by rank 0's consumer
+    unsigned pad1[15];
+    unsigned error;          // != 0: a wait timed out
+};
+constexpr unsigned long long kExchangeTimeoutNs = 4000000000ull;
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void wait_at_least(const unsigned* flag, unsigned target, unsigned* error)
+{
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flag) - target) < 0) {
+        if (ld_acquire_sys(error) != 0u) break;          // sticky: after one timeout nobody waits again
+        __nanosleep(200);
+        if (global_ns() - t0 > kExchangeTimeoutNs) { atomicExch_system(error, 1u); break; }
+    }
+}
+
+__global__ void blend_scatter_kernel(float4* __restrict__ image, const float4* __restrict__ estimate, int width, int local_rows, int height,
+                                     int rank, int world, int stripe_rows, int frame, float blend,
+                                     float4* __restrict__ full, ExchangeFlags* flags, int slot, unsigned* block_count)
+{
+    // (the wait for the slot to be free is a separate one-thread kernel ahead of this one on the same stream: if every block
+    //  of this grid spun on the flag they could fill all SM slots and starve the very kernel that releases the slot)
+    const size_t n = (size_t)local_rows * width;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int lrow = (int)(i / (size_t)width), x = (int)(i - (size_t)lrow * width);
+        const int ls = lrow / stripe_rows;
+        const int y = (ls * world + rank) * stripe_rows + (lrow - ls * stripe_rows);
+        const float4 e = estimate[i];
+        V3 last = mk(0.0f, 0.0f, 0.0f);
+        if (frame > 0) {
+            const float4 l = image[i];
+            last = mk(l.x, l.y, l.z);
+        }
+        const V3 out = mix(last, mk(e.x, e.y, e.z), blend);
+        const float4 o4 = make_float4(out.x, out.y, out.z, 1.0f);
+        image[i] = o4;
+        if (y < height) full[(size_t)y * width + x] = o4;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(block_count, 1u) == gridDim.x - 1) {       // last block of this rank: everything above is visible system-wide
+            *block_count = 0u;
+            __threadfence_system();
+            atomicAdd_system(&flags->arrived[slot], 1u);
+        }
+    }
+}
+__global__ void exchange_wait_free_kernel(ExchangeFlags* flags, unsigned need_consumed)
+{
+    wait_at_least(&flags->consumed, need_consumed, &flags->error);     // the slot's previous frame was released by the consumer
+}
+__global__ void exchange_acquire_kernel(ExchangeFlags* flags, int slot, unsigned target)
+{
+    wait_at_least(&flags->arrived[slot], target, &flags->error);
+}
+__global__ void exchange_release_kernel(ExchangeFlags* flags, unsigned consumed)
+{
+    __threadfence_system();
+    atomicExch_system(&flags->consumed, consumed);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // De-interleave after the per-frame gather: rank-major stripe buffers -> full row-major image.
 __global__ void deinterleave_kernel(const float4* __restrict__ gathered, float4* __restrict__ full, int width, int height,
                                     int world, int stripe_rows, int max_local_rows)

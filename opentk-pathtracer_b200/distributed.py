@@ -78,10 +78,12 @@ class TiledPathTracer:
         full = tp.flush()
     """
 
-    def __init__(self, tracer, rank: int, world: int, stripe_rows: int = DEFAULT_STRIPE_ROWS, device=None):
+    def __init__(self, tracer, rank: int, world: int, stripe_rows: int = DEFAULT_STRIPE_ROWS, device=None, fused: bool = False,
+                 slots: int = 2):
         import torch
 
         self.tracer, self.rank, self.world, self.stripe_rows = tracer, rank, world, stripe_rows
+        self.fused = bool(fused) and world > 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         # kernels and collectives share torch's current stream, so stream order is the only synchronisation needed
         tracer.SetStream(torch.cuda.current_stream(self.device).cuda_stream)
@@ -101,6 +103,59 @@ class TiledPathTracer:
         self._k = 0
         self._pending = None       # (buffer index, work)
         self._last_full = None
+        if self.fused:
+            self._init_fused(slots)
+
+    # ------------------------------------------------------------------ fused exchange (peer stores instead of NCCL)
+    def _init_fused(self, slots: int) -> None:
+        """ptb_exchange_*: rank 0 allocates [flags | slots x full image]; its CUDA-IPC handle (64 bytes) is broadcast with
+        torch.distributed and mapped by every other rank, whose blend kernels then store straight into rank 0's image."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        L, ctx = self.tracer._L, self.tracer._ctx
+        _lib.check(L.ptb_exchange_init(ctx, slots))
+        handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
+        if self.rank == 0:
+            raw = C.create_string_buffer(64)
+            _lib.check(L.ptb_exchange_handle(ctx, raw))
+            handle.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        if self.rank != 0:
+            raw = C.create_string_buffer(bytes(handle.cpu().numpy().tobytes()), 64)
+            _lib.check(L.ptb_exchange_attach(ctx, raw))
+        dist.barrier()
+
+    def step_fused(self, consumer=None):
+        """One frame through the fused path: every rank renders (trace + blend-and-scatter kernels); rank 0 then waits, in
+        stream order, until all ranks' pixels have landed, lets `consumer(full_image_tensor)` enqueue its work on the current
+        stream, and releases the slot.  Returns the full-image tensor on rank 0 (valid until `slots` frames later)."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        self.tracer.Render()
+        if self.rank != 0:
+            return None
+        L, ctx = self.tracer._L, self.tracer._ctx
+        ptr = C.c_void_p()
+        _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
+        full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+        if consumer is not None:
+            consumer(full)
+        _lib.check(L.ptb_exchange_release(ctx))
+        self._last_full = full
+        return full
+
+    def exchange_ok(self) -> None:
+        from . import _lib
+        _lib.check(self.tracer._L.ptb_exchange_status(self.tracer._ctx))
 
     def render(self, frames: int = 1) -> None:
         self.tracer.Render(frames)
@@ -147,10 +202,14 @@ class TiledPathTracer:
     def step(self):
         """Render the next frame, complete the PREVIOUS frame's gather (which ran beside this render on NCCL's stream), then
         start this frame's gather.  Returns the previous frame's full image on rank 0 (None for the first step)."""
+        if self.fused:
+            return self.step_fused()
         self.tracer.Render()
         done = self._finish_gather() if self._pending is not None else None
         self._start_gather()
         return done
 
     def flush(self):
+        if self.fused:
+            return self._last_full
         return self._finish_gather()
