@@ -67,6 +67,10 @@ int ptb_game_objects_subdata(ptb_ctx* ctx, int offset, int size, const void* dat
 /* PathTracer.EnvironmentMap = <RGBA32F cubemap> — PathTracer.cs:85,118.  six_faces = 6*face_size^2*4 floats,
  * faces +X,-X,+Y,-Y,+Z,-Z, row-major with row index = t.  Sampled LINEAR + seamless (compute.glsl:177). */
 int ptb_set_environment_rgba32f(ptb_ctx* ctx, int face_size, const float* six_faces);
+/* PathTracer.EnvironmentMap = SkyBox — the Srgb8Alpha8 cubemap built from six PNG faces (Helper.cs:18-50,
+ * MainWindow.cs:177-187, Gui.cs:84-86).  six_faces = 6*face_size^2 RGBA8 texels, same face / row order; decoded
+ * sRGB -> linear before filtering, as the texture unit does. */
+int ptb_set_environment_srgb8(ptb_ctx* ctx, int face_size, const unsigned char* six_faces);
 /* AtmosphericScatterer(size).Render() into the environment map, on the GPU — AtmosphericScatterer.cs:63-113,
  * AtmosphericScattering/compute.glsl.  ubo = AtmosphericDataUBO bytes (InvProjection + 6 InvView, 448 B used);
  * light_pos / light_intensity / i_steps / j_steps are that shader's uniforms. */
@@ -93,6 +97,10 @@ int ptb_read_result(ptb_ctx* ctx, float* rgba32f);            /* synchronous: W*
  * valid after ptb_synchronize(). */
 int ptb_read_result_async(ptb_ctx* ctx, float* pinned_rgba32f);
 int ptb_write_result(ptb_ctx* ctx, const float* rgba32f);     /* restore an accumulation image */
+/* ScreenEffect.Render(PathTracer.Result) — ScreenEffect.cs:29-37 with PostProcessing/fragment.glsl: ACES fit + linear->sRGB
+ * into an RGBA8 image (W*H*4 bytes, row 0 = y 0), the step right after the path tracer (MainWindow.cs:51). */
+int ptb_tonemap_rgba8(ptb_ctx* ctx, unsigned char* rgba8);
+int ptb_tonemap_device(ptb_ctx* ctx, void* rgba8_device);
 int ptb_synchronize(ptb_ctx* ctx);
 
 /* Device-side access for hosts that own CUDA memory / streams (PyTorch, CUDA-GL interop). */
@@ -140,6 +148,7 @@ int ptb_read_stats(ptb_ctx* ctx, unsigned long long* counters3);
  * op: 0 sincos (in n, out 2n)  1 exp (n -> n)  2 pcg stream (in: 1 seed as uint32 bits, out n floats)
  *     3 texture(samplerCube) (in 3n dirs, out 3n)  4 RayTrace fold over the packed scene (in 6n rays, out 12n)
  *     5 min/max/rcp/sqrt probe (in 2n, out 4n)  6 RayTrace fold over the raw UBO bytes (proxy view; as 4)
+ *     8 log (n -> n)
  *     7 group-cooperative fold of the frame tail: rays are processed k = in[6n] at a time per warp (in 6n+1, out 12n) */
 int ptb_debug_eval(ptb_ctx* ctx, int op, const float* in, int n, float* out);
 

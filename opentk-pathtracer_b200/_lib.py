@@ -28,6 +28,9 @@ SIGNATURES = {
     "ptb_basic_data_subdata": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
     "ptb_game_objects_subdata": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
     "ptb_set_environment_rgba32f": (C.c_int, [_P, C.c_int, _FP]),
+    "ptb_set_environment_srgb8": (C.c_int, [_P, C.c_int, C.c_void_p]),
+    "ptb_tonemap_rgba8": (C.c_int, [_P, C.c_void_p]),
+    "ptb_tonemap_device": (C.c_int, [_P, C.c_void_p]),
     "ptb_generate_atmosphere": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int, _FP, C.c_float, C.c_int, C.c_int]),
     "ptb_read_environment": (C.c_int, [_P, _FP]),
     "ptb_environment_size": (C.c_int, [_P]),

@@ -322,6 +322,7 @@ int launch_frame(ptb_ctx* c)
 extern "C" {
 
 static int exchange_close(ptb_ctx* c);
+static int install_environment(ptb_ctx* c, int N);
 
 const char* ptb_last_error(void) { return g_err; }
 int ptb_version(void) { return 100; }
@@ -468,6 +469,29 @@ int ptb_set_environment_rgba32f(ptb_ctx* c, int face_size, const float* six_face
     return install_environment(c, face_size);
 }
 
+int ptb_set_environment_srgb8(ptb_ctx* c, int face_size, const unsigned char* six_faces)
+{
+    if (!c || !six_faces) return fail(PTB_E_INVALID, "null argument");
+    if (face_size < 1 || face_size > 8192) return fail(PTB_E_INVALID, "face size %d outside [1,8192]", face_size);
+    CU(cudaSetDevice(c->device));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    const size_t n = (size_t)6 * face_size * face_size;
+    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; }
+    CU(cudaMalloc(&c->d_env_faces, n * sizeof(float4)));
+    uchar4* d_raw = nullptr;
+    CU(cudaMalloc(&d_raw, n * sizeof(uchar4)));
+    int rc = PTB_OK;
+    if (cudaMemcpyAsync(d_raw, six_faces, n * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail(PTB_E_CUDA, "H2D failed");
+    if (rc == PTB_OK) {
+        srgb8_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_raw, n, c->d_env_faces);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(PTB_E_CUDA, "sRGB decode failed");
+    }
+    cudaFree(d_raw);
+    if (rc != PTB_OK) return rc;
+    return install_environment(c, face_size);
+}
+
 int ptb_generate_atmosphere(ptb_ctx* c, int face_size, const void* ubo, int ubo_size, const float* light_pos, float light_intensity, int i_steps, int j_steps)
 {
     if (!c || !ubo || !light_pos) return fail(PTB_E_INVALID, "null argument");
@@ -574,6 +598,33 @@ int ptb_write_result(ptb_ctx* c, const float* src)
     CU(cudaStreamSynchronize(c->stream));
     return PTB_OK;
 }
+static int run_tonemap(ptb_ctx* c, uchar4* d_out)
+{
+    const size_t n = (size_t)c->local_rows * c->width;
+    if (n == 0) return PTB_OK;
+    tonemap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_image, n, d_out);
+    c->launches++;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+int ptb_tonemap_device(ptb_ctx* c, void* rgba8_device)
+{
+    if (!c || !rgba8_device) return fail(PTB_E_INVALID, "null argument");
+    return run_tonemap(c, (uchar4*)rgba8_device);
+}
+int ptb_tonemap_rgba8(ptb_ctx* c, unsigned char* rgba8)
+{
+    if (!c || !rgba8) return fail(PTB_E_INVALID, "null argument");
+    const size_t n = (size_t)c->local_rows * c->width;
+    uchar4* d = nullptr;
+    CU(cudaMalloc(&d, (n ? n : 1) * sizeof(uchar4)));
+    int rc = run_tonemap(c, d);
+    if (rc == PTB_OK && cudaMemcpyAsync(rgba8, d, n * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail(PTB_E_CUDA, "D2H failed");
+    if (rc == PTB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(PTB_E_CUDA, "tone-map kernel failed");
+    cudaFree(d);
+    return rc;
+}
+
 int ptb_synchronize(ptb_ctx* c)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
@@ -771,6 +822,7 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
     case 4: case 6: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
     case 5: in_f = 2 * (size_t)n; out_f = 4 * (size_t)n; break;
     case 7: in_f = 6 * (size_t)n + 1; out_f = 12 * (size_t)n; break;
+    case 8: in_f = n; out_f = n; break;
     default: return fail(PTB_E_INVALID, "unknown debug op %d", op);
     }
     float *d_in = nullptr, *d_out = nullptr;
@@ -795,6 +847,7 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
             if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->block_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
             dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : 0);
         } else if (op == 5) dbg_arith_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
+        else if (op == 8) dbg_log_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 7) {
             rc = sync_scene(c);
             if (rc != PTB_OK) break;

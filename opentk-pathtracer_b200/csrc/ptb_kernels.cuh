@@ -952,7 +952,57 @@ __global__ void deinterleave_kernel(const float4* __restrict__ gathered, float4*
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// SURVEY 8f N1 — the pass that follows the path tracer: PostProcessing/fragment.glsl (pp:LINE) into an RGBA8 target
+// (ScreenEffect.cs:20-37): ACES fit, linear -> sRGB, unorm8 store (clamp, *255, round to nearest even).
+__device__ __forceinline__ float aces_film(float x)                       // pp:36-44
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    const float v = fdiv(x * (a * x + b), x * (c * x + d) + e);
+    return fmin_(fmax_(v, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float linear_to_inverse_gamma(float rgb, float gamma)    // pp:28-32
+{
+    const float sel = rgb < 0.0031308f ? 1.0f : 0.0f;
+    return mixf(pow_(rgb, fdiv(1.0f, gamma)) * 1.055f - 0.055f, rgb * 12.92f, sel);
+}
+__device__ __forceinline__ unsigned unorm8(float f)
+{
+    if (f != f) return 0u;
+    f = fmin_(fmax_(f, 0.0f), 1.0f);
+    return (unsigned)__float2int_rn(f * 255.0f);
+}
+__global__ void tonemap_kernel(const float4* __restrict__ image, size_t n, uchar4* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = image[i];
+    const float r = linear_to_inverse_gamma(aces_film(c.x + 0.0f), 2.4f);     // pp:19-24 (Sampler1 is never bound: + 0)
+    const float g = linear_to_inverse_gamma(aces_film(c.y + 0.0f), 2.4f);
+    const float b = linear_to_inverse_gamma(aces_film(c.z + 0.0f), 2.4f);
+    out[i] = make_uchar4((unsigned char)unorm8(r), (unsigned char)unorm8(g), (unsigned char)unorm8(b), 255);
+}
+// SURVEY 8f N2 — Srgb8Alpha8 skybox faces (Helper.cs:18-50): sRGB decode before filtering (GL 4.5 8.24), alpha linear.
+__global__ void srgb8_decode_kernel(const uchar4* __restrict__ in, size_t n, float4* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uchar4 t = in[i];
+    const unsigned char ch[3] = {t.x, t.y, t.z};
+    float lin[3];
+    for (int k = 0; k < 3; ++k) {
+        const float cs = fdiv((float)ch[k], 255.0f);
+        lin[k] = cs <= 0.04045f ? fdiv(cs, 12.92f) : pow_(fdiv(cs + 0.055f, 1.055f), 2.4f);
+    }
+    out[i] = make_float4(lin[0], lin[1], lin[2], fdiv((float)t.w, 255.0f));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Unit probes for the parity tests (ptb_debug_eval).
+__global__ void dbg_log_kernel(const float* in, int n, float* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = log_(in[i]);
+}
 __global__ void dbg_sincos_kernel(const float* in, int n, float* out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -114,6 +114,38 @@ __device__ __forceinline__ float exp_(float x)
     return (e * __uint_as_float((uint32_t)(k1 + 127) << 23)) * __uint_as_float((uint32_t)(k2 + 127) << 23);
 }
 
+// log(x), x > 0 (frexp to [sqrt(1/2), sqrt(2)), degree-8 kernel) and pow(x, y) = exp(y log x) for x >= 0: only the
+// post-process pass and the sRGB decode use them (PostProcessing/fragment.glsl:31, GL sRGB texture decode).
+__device__ __forceinline__ float log_(float x)
+{
+    if (x != x || x < 0.0f) return __uint_as_float(0x7fc00000u);
+    if (x == 0.0f) return __uint_as_float(0xff800000u);
+    if (x == __uint_as_float(0x7f800000u)) return x;
+    int e = 0;
+    if (x < 1.17549435e-38f) { x = x * 8388608.0f; e = -23; }
+    const uint32_t b = __float_as_uint(x);
+    e += (int)(b >> 23) - 126;
+    float m = __uint_as_float((b & 0x007fffffu) | 0x3f000000u);
+    if (m < 0.707106781186547524f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
+    const float z = m * m;
+    float p = 7.0376836292e-2f;
+    p = __fmaf_rn(p, m, -1.1514610310e-1f);
+    p = __fmaf_rn(p, m, 1.1676998740e-1f);
+    p = __fmaf_rn(p, m, -1.2420140846e-1f);
+    p = __fmaf_rn(p, m, 1.4249322787e-1f);
+    p = __fmaf_rn(p, m, -1.6668057665e-1f);
+    p = __fmaf_rn(p, m, 2.0000714765e-1f);
+    p = __fmaf_rn(p, m, -2.4999993993e-1f);
+    p = __fmaf_rn(p, m, 3.3333331174e-1f);
+    float y = (p * z) * m;
+    const float fe = (float)e;
+    y = __fmaf_rn(fe, -2.12194440e-4f, y);
+    y = __fmaf_rn(z, -0.5f, y);
+    const float r = m + y;
+    return __fmaf_rn(fe, 0.693359375f, r);
+}
+__device__ __forceinline__ float pow_(float x, float y) { return exp_(y * log_(x)); }
+
 // compute.glsl:334-344 — PCG-RXS-M-XS hash stream; float(h) / 2^32 (can return exactly 1.0).
 __device__ __forceinline__ uint32_t pcg_hash(uint32_t& seed)
 {

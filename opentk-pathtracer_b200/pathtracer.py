@@ -40,6 +40,22 @@ class BufferObject:
         _lib.check(fn(self._tracer._ctx, offset, size, buf))
 
 
+class ScreenEffect:
+    """Mirror of src/Render/ScreenEffect.cs for the post-process pass: Render(tracer) tone-maps the tracer's Result
+    (ACES fit + linear->sRGB, PostProcessing/fragment.glsl) into an RGBA8 image, `Result` (H, W, 4) uint8."""
+
+    def __init__(self):
+        self.Result = None
+
+    def Render(self, tracer: "PathTracer") -> np.ndarray:
+        rows = _lib.check(tracer._L.ptb_local_rows(tracer._ctx))
+        out = np.empty((rows, tracer.Width, 4), dtype=np.uint8)
+        if rows:
+            _lib.check(tracer._L.ptb_tonemap_rgba8(tracer._ctx, out.ctypes.data_as(C.c_void_p)))
+        self.Result = out
+        return out
+
+
 class PathTracer:
     def __init__(self, environmentMap, width: int, height: int, rayDepth: int, spp: int, focalLength: float,
                  apertureDiamater: float, *, max_spheres: int = _scene.MAX_GAMEOBJECTS_SPHERES,
@@ -126,6 +142,14 @@ class PathTracer:
             raise ValueError("EnvironmentMap must be (6, N, N, 4) float32")
         _lib.check(self._L.ptb_set_environment_rgba32f(self._ctx, a.shape[1], a.ctypes.data_as(C.POINTER(C.c_float))))
         self._env = a
+
+    def SetSkyBox(self, faces_rgba8) -> None:
+        """EnvironmentMap = SkyBox: six sRGB8 faces (6, N, N, 4) uint8, decoded to linear on upload (Helper.cs:18-50, Gui.cs:84-86)."""
+        a = np.ascontiguousarray(faces_rgba8, dtype=np.uint8)
+        if a.ndim != 4 or a.shape[0] != 6 or a.shape[1] != a.shape[2] or a.shape[3] != 4:
+            raise ValueError("SkyBox must be (6, N, N, 4) uint8")
+        _lib.check(self._L.ptb_set_environment_srgb8(self._ctx, a.shape[1], a.ctypes.data_as(C.c_void_p)))
+        self._env = None
 
     def GenerateAtmosphere(self, size: int = 256, iSteps: int = 50, jSteps: int = 15, time: float = 0.5,
                            lightIntensity: float = 15.0) -> None:

@@ -183,4 +183,37 @@ static inline float g_exp(float x)
     return (e * s1) * s2;
 }
 
+/* log(x), x > 0: frexp to [sqrt(1/2), sqrt(2)), degree-8 kernel (the classic single-precision coefficients), explicit fma.
+ * log(0) = -inf, log(x<0) = NaN.  Used only by pow() in the post-process / sRGB paths. */
+static inline float g_log(float x)
+{
+    if (g_isnan(x) || x < 0.0f) return g_float(0x7fc00000u);
+    if (x == 0.0f) return g_float(0xff800000u);
+    if (x == g_float(0x7f800000u)) return x;
+    int e = 0;
+    if (x < 1.17549435e-38f) { x = x * 8388608.0f; e = -23; }
+    uint32_t b = g_bits(x);
+    e += (int)(b >> 23) - 126;
+    float m = g_float((b & 0x007fffffu) | 0x3f000000u);          /* mantissa in [0.5, 1) */
+    if (m < 0.707106781186547524f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
+    float z = m * m;
+    float p = 7.0376836292e-2f;
+    p = g_fma(p, m, -1.1514610310e-1f);
+    p = g_fma(p, m, 1.1676998740e-1f);
+    p = g_fma(p, m, -1.2420140846e-1f);
+    p = g_fma(p, m, 1.4249322787e-1f);
+    p = g_fma(p, m, -1.6668057665e-1f);
+    p = g_fma(p, m, 2.0000714765e-1f);
+    p = g_fma(p, m, -2.4999993993e-1f);
+    p = g_fma(p, m, 3.3333331174e-1f);
+    float y = (p * z) * m;
+    float fe = (float)e;
+    y = g_fma(fe, -2.12194440e-4f, y);
+    y = g_fma(z, -0.5f, y);
+    float r = m + y;
+    return g_fma(fe, 0.693359375f, r);
+}
+/* pow(x, y) for x >= 0 (GLSL: undefined for x < 0): exp(y * log(x)); pow(0, y > 0) = 0. */
+static inline float g_pow(float x, float y) { return g_exp(y * g_log(x)); }
+
 #endif

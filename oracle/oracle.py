@@ -61,6 +61,10 @@ def lib():
         L.pto_texture_cube.argtypes = [fp, C.c_int, fp, C.c_int, fp]
         L.pto_atmosphere.argtypes = [C.c_int, C.c_void_p, fp, C.c_float, C.c_int, C.c_int, fp, C.c_int]
         L.pto_atmosphere.restype = C.c_int
+        u8p = C.POINTER(C.c_uint8)
+        L.pto_tonemap.argtypes = [fp, C.c_int, u8p]
+        L.pto_srgb8_to_linear.argtypes = [u8p, C.c_int, fp]
+        L.pto_log.argtypes = [fp, C.c_int, fp]
         _lib = L
     return _lib
 
@@ -159,3 +163,25 @@ def atmosphere(size: int, ubo: bytes, light_pos, light_intensity: float, i_steps
     if rc != 0:
         raise RuntimeError(f"pto_atmosphere failed: {rc}")
     return out
+
+
+def tonemap(image: np.ndarray) -> np.ndarray:
+    """ScreenEffect.Render(PathTracer.Result): ACES fit + linear->sRGB into RGBA8 (PostProcessing/fragment.glsl)."""
+    a = np.ascontiguousarray(image, dtype=np.float32)
+    out = np.empty(a.shape[:-1] + (4,), dtype=np.uint8)
+    lib().pto_tonemap(_fp(a), int(a.size // 4), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out
+
+
+def srgb8_to_linear(faces: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(faces, dtype=np.uint8)
+    out = np.empty(a.shape, dtype=np.float32)
+    lib().pto_srgb8_to_linear(a.ctypes.data_as(C.POINTER(C.c_uint8)), int(a.size // 4), _fp(out))
+    return out
+
+
+def log(x: np.ndarray):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib().pto_log(_fp(x), x.size, _fp(y))
+    return y

@@ -577,3 +577,54 @@ void pto_texture_cube(const float *env, int env_size, const float *dirs, int n, 
         out[3 * i] = t.x; out[3 * i + 1] = t.y; out[3 * i + 2] = t.z;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY §8f N1 — the post-process pass that follows the path tracer (MainWindow.cs:51):
+ * /root/reference/OpenTK-PathTracer/res/shaders/PostProcessing/fragment.glsl (cited pp:LINE), rendered into an RGBA8 target
+ * (ScreenEffect.cs:20-22).  Sampler1 is never bound by the host (ScreenEffect.Render gets one texture), so it adds 0.
+ * RGBA8 store: clamp to [0,1], scale by 255, round to nearest even.
+ * ------------------------------------------------------------------------------------------ */
+static float ACESFilm1(float x) /* pp:36-44 */
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    float v = g_div(x * (a * x + b), x * (c * x + d) + e);
+    return g_min(g_max(v, 0.0f), 1.0f);
+}
+static float LinearToInverseGamma1(float rgb, float gamma) /* pp:28-32 */
+{
+    float sel = rgb < 0.0031308f ? 1.0f : 0.0f;
+    return g_mix(g_pow(rgb, g_div(1.0f, gamma)) * 1.055f - 0.055f, rgb * 12.92f, sel);
+}
+static uint8_t unorm8(float f)
+{
+    if (g_isnan(f)) return 0;
+    f = g_min(g_max(f, 0.0f), 1.0f);
+    return (uint8_t)__builtin_rintf(f * 255.0f);
+}
+void pto_tonemap(const float *rgba32f, int n_pixels, uint8_t *rgba8)
+{
+    for (int i = 0; i < n_pixels; i++) {
+        for (int c = 0; c < 3; c++) {
+            float color = rgba32f[4 * i + c] + 0.0f;          /* pp:19-20 */
+            color = ACESFilm1(color);                          /* pp:23 */
+            color = LinearToInverseGamma1(color, 2.4f);        /* pp:24 */
+            rgba8[4 * i + c] = unorm8(color);
+        }
+        rgba8[4 * i + 3] = 255;                                /* pp:25 */
+    }
+}
+
+/* SURVEY §8f N2 — the alternate environment: six sRGB8 PNG faces uploaded as Srgb8Alpha8 (Helper.cs:18-50,
+ * MainWindow.cs:177-187).  The texture unit decodes sRGB to linear before filtering (GL 4.5 §8.24): c/12.92 below 0.04045,
+ * ((c+0.055)/1.055)^2.4 above; alpha stays linear. */
+void pto_srgb8_to_linear(const uint8_t *rgba8, int n_texels, float *rgba32f)
+{
+    for (int i = 0; i < n_texels; i++) {
+        for (int c = 0; c < 3; c++) {
+            float cs = g_div((float)rgba8[4 * i + c], 255.0f);
+            rgba32f[4 * i + c] = cs <= 0.04045f ? g_div(cs, 12.92f) : g_pow(g_div(cs + 0.055f, 1.055f), 2.4f);
+        }
+        rgba32f[4 * i + 3] = g_div((float)rgba8[4 * i + 3], 255.0f);
+    }
+}
+void pto_log(const float *x, int n, float *y) { for (int i = 0; i < n; i++) y[i] = g_log(x[i]); }

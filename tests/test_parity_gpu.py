@@ -437,3 +437,45 @@ def test_statistics_counters(ptb, oracle, env256, default_scene, camera):
                         focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7, want_stats=True)
     assert st["samples"] == ref["samples"] and st["bounces"] == ref["bounces"] and st["hits"] == ref["hits"]
     pt.Dispose()
+
+
+# ------------------------------------------------------------------------------- next rows: N1 post-process, N2 sRGB skybox
+def test_log_bit_exact(tracer256, oracle):
+    x = np.concatenate([np.logspace(-44, 38, 400001).astype(np.float32), np.linspace(0.25, 4.0, 400001, dtype=np.float32),
+                        np.array([0.0, -0.0, 1.0, np.inf, -1.0, np.nan, 1e-45], np.float32)])
+    assert_same(tracer256.DebugEval(8, x, x.size, x.size), oracle.log(x), "log")
+
+
+def test_tonemap_bit_exact(ptb, oracle, env256, default_scene, camera):
+    """ScreenEffect.Render(PathTracer.Result) on the GPU == the oracle's pass over the same float image, byte for byte."""
+    pt = make_tracer(ptb, env256, 320, 180, default_scene, camera)
+    pt.Render(4)
+    fx = ptb.ScreenEffect()
+    got = fx.Render(pt)
+    assert got.shape == (180, 320, 4) and got.dtype == np.uint8
+    want = oracle.tonemap(pt.Result)
+    assert (got == want).all(), f"{int((got != want).any(axis=2).sum())} pixels differ"
+    assert 5 < got[..., :3].mean() < 250 and (got[..., 3] == 255).all()
+    # a synthetic HDR ramp incl. the linear toe, values > 1 and garbage
+    ramp = np.zeros((180, 320, 4), np.float32)
+    ramp[..., :3] = np.linspace(0, 12, 180 * 320 * 3, dtype=np.float32).reshape(180, 320, 3) ** 2 / 12
+    ramp[0, :4, 0] = [np.nan, -3.0, np.inf, 1e-8]
+    pt.WriteResult(ramp)
+    assert (fx.Render(pt) == oracle.tonemap(ramp)).all()
+    pt.Dispose()
+
+
+def test_srgb8_skybox_environment(ptb, oracle, default_scene, camera):
+    """EnvironmentMap = SkyBox (Srgb8Alpha8 faces, Helper.cs:18-50): decode on upload == oracle decode, and the render
+    with it == the oracle render with the decoded float cubemap."""
+    rng = np.random.default_rng(21)
+    faces = rng.integers(0, 256, (6, 24, 24, 4), dtype=np.uint8)
+    pt = ptb.PathTracer(None, 96, 64, 13, 1, 20.0, 0.14)
+    pt.SetSkyBox(faces)
+    lin = oracle.srgb8_to_linear(faces)
+    assert_same(pt.ReadEnvironment(), lin, "sRGB8 -> linear decode")
+    pt.LoadScene(default_scene); pt.SetCamera(camera)
+    pt.Render(2)
+    ref = oracle_render(oracle, ptb.scene, default_scene, camera, lin, 96, 64, 2)
+    assert_same(pt.Result, ref, "render with the sRGB skybox")
+    pt.Dispose()
