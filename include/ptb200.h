@@ -148,7 +148,7 @@ int ptb_read_stats(ptb_ctx* ctx, unsigned long long* counters3);
  * op: 0 sincos (in n, out 2n)  1 exp (n -> n)  2 pcg stream (in: 1 seed as uint32 bits, out n floats)
  *     3 texture(samplerCube) (in 3n dirs, out 3n)  4 RayTrace fold over the packed scene (in 6n rays, out 12n)
  *     5 min/max/rcp/sqrt probe (in 2n, out 4n)  6 RayTrace fold over the raw UBO bytes (proxy view; as 4)
- *     8 log (n -> n)
+ *     8 log (n -> n)  9 RayTrace fold through the BVH (scenes of >= 96 primitives; as 4)
  *     7 group-cooperative fold of the frame tail: rays are processed k = in[6n] at a time per warp (in 6n+1, out 12n) */
 int ptb_debug_eval(ptb_ctx* ctx, int op, const float* in, int n, float* out);
 

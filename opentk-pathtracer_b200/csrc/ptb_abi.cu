@@ -4,6 +4,8 @@
 #include "../../include/ptb200.h"
 #include "ptb_kernels.cuh"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -57,6 +59,12 @@ struct ptb_ctx {
     float4* d_block = nullptr;
     size_t block_capacity = 0;
     int off_aux = 0, off_cmin = 0, off_cmax = 0, off_mat = 0, block_bytes = 0;
+    // BVH for large scenes (conservative culling in front of the exact tests)
+    int bvh_threshold = 96;          // primitives; below this the brute-force fold wins
+    int stage_bytes = 0, off_nodes = 0, off_pidx = 0, n_nodes = 0, n_unbounded = 0;
+    float bvh_tau = 0.0f, bvh_D = 0.0f;
+    std::vector<float4> bvh_nodes;
+    std::vector<int> bvh_pidx;
     float4* d_env_faces = nullptr;   // unpadded 6*N*N
     float4* d_env = nullptr;         // padded 6*(N+2)^2
     int env_size = 0;
@@ -70,7 +78,7 @@ struct ptb_ctx {
     // pipelined read-back: snapshot on the render stream, D2H on the copy stream, two staging buffers in flight
     cudaStream_t copy_stream = nullptr;
     float4* d_stage[2] = {nullptr, nullptr};
-    size_t stage_bytes = 0;
+    size_t readback_bytes = 0;
     cudaEvent_t ev_snap[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     int stage_next = 0;
     // pipelined frames: `overlap` trace streams, each with its own scratch image and work counters, and one blend stream.
@@ -100,6 +108,7 @@ struct ptb_ctx {
     int mega_smem_set = -1;
     int mega_grid = 0;
     bool mega_ring = true;
+    bool mega_bvh_set = false;
 };
 
 namespace {
@@ -175,22 +184,149 @@ int alloc_image(ptb_ctx* c)
     return mark_inputs(c);
 }
 
-void layout_block(ptb_ctx* c)
+// ---- conservative BVH over the primitives' inflated boxes (host build; see trace_bvh and DESIGN.md for the error bounds)
+struct Box { double lo[3], hi[3]; };
+#ifndef PTB_BVH_BIG
+#define PTB_BVH_BIG 0.25     // a primitive wider than this fraction of the scene on any axis is tested for every ray instead
+#endif
+#ifndef PTB_BVH_LEAF
+#define PTB_BVH_LEAF 4
+#endif
+
+float required_extent(ptb_ctx* c, const std::vector<Box>& boxes)
+{
+    // D bounds every coordinate that enters a test and every origin-to-primitive distance: scene boxes + camera + lens
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, maxabs = 0.0;
+    auto grow = [&](const double* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); maxabs = std::max(maxabs, std::fabs(p[k])); } };
+    for (const Box& b : boxes) { grow(b.lo); grow(b.hi); }
+    float cam[3];
+    memcpy(cam, c->basic + 128, 12);
+    const double lens = std::fabs((double)c->aperture_diameter) * 0.5 + 1.0;
+    for (int sgn = -1; sgn <= 1; sgn += 2) { double p[3] = {cam[0] + sgn * lens, cam[1] + sgn * lens, cam[2] + sgn * lens}; if (std::isfinite(p[0] + p[1] + p[2])) grow(p); }
+    double diag2 = 0.0;
+    for (int k = 0; k < 3; ++k) diag2 += (hi[k] - lo[k]) * (hi[k] - lo[k]);
+    const double D = 1.01 * std::max(std::sqrt(diag2), maxabs) + 1.0;
+    float Dq = 1.0f;
+    while (Dq < D && Dq < 1e30f) Dq *= 2.0f;
+    return Dq;
+}
+
+void raw_boxes(ptb_ctx* c, double E, double m, std::vector<Box>& boxes, std::vector<char>& bounded)
 {
     const int nS = c->n_spheres, nC = c->n_cuboids;
-    c->off_aux = nS;                              // float4 units
+    boxes.assign((size_t)nS + nC, Box());
+    bounded.assign((size_t)nS + nC, 1);
+    for (int i = 0; i < nS + nC; ++i) {
+        Box& b = boxes[i];
+        if (i < nS) {
+            float g[4];
+            memcpy(g, c->objects.data() + (size_t)i * kSphereStride, 16);
+            const double r = std::sqrt((double)g[3] * g[3] + E) + m;
+            for (int k = 0; k < 3; ++k) { b.lo[k] = g[k] - r; b.hi[k] = g[k] + r; }
+        } else {
+            float lo[4], hi[4];
+            const unsigned char* p = c->objects.data() + (size_t)c->max_spheres * kSphereStride + (size_t)(i - nS) * kCuboidStride;
+            memcpy(lo, p, 16); memcpy(hi, p + 16, 16);
+            for (int k = 0; k < 3; ++k) { b.lo[k] = std::min(lo[k], hi[k]) - m; b.hi[k] = std::max(lo[k], hi[k]) + m; }
+        }
+        double sum = 0.0;
+        for (int k = 0; k < 3; ++k) sum += b.lo[k] + b.hi[k];
+        if (!std::isfinite(sum)) bounded[i] = 0;      // NaN / Inf geometry: always tested, never culled
+    }
+}
+
+void build_bvh(ptb_ctx* c)
+{
+    c->bvh_nodes.clear(); c->bvh_pidx.clear(); c->n_nodes = 0; c->n_unbounded = 0; c->bvh_tau = 0.0f; c->bvh_D = 0.0f;
+    const int n = c->n_spheres + c->n_cuboids;
+    if (n < c->bvh_threshold) return;
+    std::vector<Box> boxes; std::vector<char> bounded;
+    raw_boxes(c, 0.0, 0.0, boxes, bounded);
+    std::vector<Box> finite;
+    for (int i = 0; i < n; ++i) if (bounded[i]) finite.push_back(boxes[i]);
+    const float D = required_extent(c, finite);
+    const double E = 4e-6 * (double)D * D, m = 1e-5 * (double)D + 1e-6;
+    raw_boxes(c, E, m, boxes, bounded);
+    // primitives that span a large part of the scene (the room's walls and floor) would drag every ancestor box up to scene
+    // size: they go to the always-tested list together with the non-finite ones
+    double slo[3] = {1e300, 1e300, 1e300}, shi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; ++i) if (bounded[i]) for (int k = 0; k < 3; ++k) { slo[k] = std::min(slo[k], boxes[i].lo[k]); shi[k] = std::max(shi[k], boxes[i].hi[k]); }
+    std::vector<int> order;
+    for (int i = 0; i < n; ++i) {
+        bool big = !bounded[i];
+        if (!big) for (int k = 0; k < 3; ++k) if (boxes[i].hi[k] - boxes[i].lo[k] > PTB_BVH_BIG * (shi[k] - slo[k])) big = true;
+        if (big && (int)c->bvh_pidx.size() < 64) c->bvh_pidx.push_back(i); else if (bounded[i]) order.push_back(i); else c->bvh_pidx.push_back(i);
+    }
+    c->n_unbounded = (int)c->bvh_pidx.size();
+    c->bvh_D = D;
+    c->bvh_tau = 1e-4f * D;
+    if (order.empty()) return;
+    struct Task { int node, begin, end; };
+    std::vector<Task> todo;
+    auto set_box = [&](int node, int begin, int end) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int q = begin; q < end; ++q) for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], boxes[order[q]].lo[k]); hi[k] = std::max(hi[k], boxes[order[q]].hi[k]); }
+        float4 A, B;   // round outwards
+        A.x = std::nextafter((float)lo[0], -INFINITY); A.y = std::nextafter((float)lo[1], -INFINITY); A.z = std::nextafter((float)lo[2], -INFINITY);
+        B.x = std::nextafter((float)hi[0], INFINITY); B.y = std::nextafter((float)hi[1], INFINITY); B.z = std::nextafter((float)hi[2], INFINITY);
+        A.w = 0.0f; B.w = 0.0f;
+        c->bvh_nodes[2 * node] = A; c->bvh_nodes[2 * node + 1] = B;
+    };
+    c->bvh_nodes.resize(2);
+    todo.push_back({0, 0, (int)order.size()});
+    while (!todo.empty()) {
+        const Task t = todo.back(); todo.pop_back();
+        set_box(t.node, t.begin, t.end);
+        const int cnt = t.end - t.begin;
+        if (cnt <= PTB_BVH_LEAF) {
+            std::sort(order.begin() + t.begin, order.begin() + t.end);
+            const int first = (int)c->bvh_pidx.size();
+            for (int q = t.begin; q < t.end; ++q) c->bvh_pidx.push_back(order[q]);
+            memcpy(&c->bvh_nodes[2 * t.node].w, &first, 4);
+            memcpy(&c->bvh_nodes[2 * t.node + 1].w, &cnt, 4);
+            continue;
+        }
+        double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+        for (int q = t.begin; q < t.end; ++q) for (int k = 0; k < 3; ++k) { const double ce = boxes[order[q]].lo[k] + boxes[order[q]].hi[k]; clo[k] = std::min(clo[k], ce); chi[k] = std::max(chi[k], ce); }
+        int axis = 0;
+        if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+        if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+        const int mid = t.begin + cnt / 2;
+        std::nth_element(order.begin() + t.begin, order.begin() + mid, order.begin() + t.end,
+                         [&](int a, int b) { return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis]; });
+        const int left = (int)(c->bvh_nodes.size() / 2);
+        c->bvh_nodes.resize(c->bvh_nodes.size() + 4);
+        const int zero = 0;
+        memcpy(&c->bvh_nodes[2 * t.node].w, &left, 4);
+        memcpy(&c->bvh_nodes[2 * t.node + 1].w, &zero, 4);
+        todo.push_back({left, t.begin, mid});
+        todo.push_back({left + 1, mid, t.end});
+    }
+    c->n_nodes = (int)(c->bvh_nodes.size() / 2);
+}
+
+void layout_block(ptb_ctx* c)
+{
+    // float4 units: [spheres][1/r][cuboid lo][cuboid hi][BVH nodes][BVH index list] | [materials]
+    const int nS = c->n_spheres, nC = c->n_cuboids;
+    c->off_aux = nS;
     c->off_cmin = c->off_aux + (nS + 3) / 4;
     c->off_cmax = c->off_cmin + nC;
-    c->off_mat = c->off_cmax + nC;
+    c->off_nodes = c->off_cmax + nC;
+    c->off_pidx = c->off_nodes + 2 * c->n_nodes;
+    c->off_mat = c->off_pidx + ((int)c->bvh_pidx.size() + 3) / 4;
     c->block_bytes = (c->off_mat + (nS + nC) * 4) * 16;
     if (c->block_bytes < 16) c->block_bytes = 16;
+    // with a BVH the materials stay in HBM / L2 (only the winner's 64 B are read per bounce) so more CTAs fit an SM
+    c->stage_bytes = c->n_nodes > 0 || c->n_unbounded > 0 ? std::max(16, c->off_mat * 16) : c->block_bytes;
 }
 
 int sync_scene(ptb_ctx* c)
 {
     if (!c->scene_dirty) return PTB_OK;
+    build_bvh(c);
     layout_block(c);
-    if (c->block_bytes > kMaxSmem - 1024)
+    if (c->stage_bytes > kMaxSmem - 1024)
         return fail(PTB_E_INVALID, "scene block of %d bytes does not fit shared memory (%d spheres, %d cuboids)", c->block_bytes, c->n_spheres, c->n_cuboids);
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }     // kernels in flight still read the old block / UBO copy
     if ((size_t)c->block_bytes > c->block_capacity) {
@@ -208,6 +344,9 @@ int sync_scene(ptb_ctx* c)
         c->launches++;
         CU(cudaGetLastError());
     }
+    if (c->n_nodes > 0) CU(cudaMemcpyAsync(c->d_block + c->off_nodes, c->bvh_nodes.data(), c->bvh_nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    if (!c->bvh_pidx.empty()) CU(cudaMemcpyAsync(c->d_block + c->off_pidx, c->bvh_pidx.data(), c->bvh_pidx.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (c->n_nodes > 0 || !c->bvh_pidx.empty()) CU(cudaStreamSynchronize(c->stream));     // the host vectors may be rebuilt before the copy ran
     c->scene_dirty = false;
     return mark_inputs(c);
 }
@@ -222,6 +361,8 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.env_size = c->env_size;
     P.rank = c->rank; P.world = c->world; P.stripe_rows = c->stripe_rows; P.local_rows = c->local_rows;
     P.off_aux = c->off_aux; P.off_cmin = c->off_cmin; P.off_cmax = c->off_cmax; P.off_mat = c->off_mat; P.block_bytes = c->block_bytes;
+    P.stage_bytes = c->stage_bytes; P.off_nodes = c->off_nodes; P.off_pidx = c->off_pidx; P.n_nodes = c->n_nodes; P.n_unbounded = c->n_unbounded;
+    P.bvh_tau = c->bvh_tau;
     P.scene = c->d_block; P.env = c->d_env; P.image = c->d_image;
     P.counters = c->d_counters; P.stats = c->d_stats;
     P.raw_objects = c->d_objects; P.max_spheres = c->max_spheres;
@@ -238,8 +379,13 @@ void fill_params(ptb_ctx* c, RenderParams& P)
 template <class F>
 int with_mega(ptb_ctx* c, bool stats, F&& launch)
 {
-    if (c->mega_ring) return stats ? launch(megakernel<true, true>) : launch(megakernel<false, true>);
-    return stats ? launch(megakernel<true, false>) : launch(megakernel<false, false>);
+    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
+    if (bvh) {
+        if (c->mega_ring) return stats ? launch(megakernel<true, true, true>) : launch(megakernel<false, true, true>);
+        return stats ? launch(megakernel<true, false, true>) : launch(megakernel<false, false, true>);
+    }
+    if (c->mega_ring) return stats ? launch(megakernel<true, true, false>) : launch(megakernel<false, true, false>);
+    return stats ? launch(megakernel<true, false, false>) : launch(megakernel<false, false, false>);
 }
 
 int launch_frame(ptb_ctx* c)
@@ -255,19 +401,30 @@ int launch_frame(ptb_ctx* c)
         c->frame++;
         return mark_inputs(c);      // the image changed on the user-visible stream
     }
-    const int smem = c->block_bytes;
-    if (c->mega_smem_set != smem) {
-        CU(cudaFuncSetAttribute(megakernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(megakernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(megakernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(megakernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = c->stage_bytes;
+    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
+    if (c->mega_smem_set != smem || c->mega_bvh_set != bvh) {
         int with_ring = 0, without = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true>, kMegaThreads, smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false>, kMegaThreads, smem));
+        if (bvh) {
+            CU(cudaFuncSetAttribute(megakernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true, true>, kMegaThreads, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false, true>, kMegaThreads, smem));
+        } else {
+            CU(cudaFuncSetAttribute(megakernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(megakernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true, false>, kMegaThreads, smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false, false>, kMegaThreads, smem));
+        }
         if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
         c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
         c->mega_grid = c->sm_count * (c->mega_ring ? with_ring : without);
         c->mega_smem_set = smem;
+        c->mega_bvh_set = bvh;
     }
     if (c->local_rows > 0) {
         if (c->overlap <= 1) {
@@ -531,6 +688,14 @@ int ptb_render_frames(ptb_ctx* c, int n)
     if (n < 0) return fail(PTB_E_INVALID, "n < 0");
     if (!c->d_env) return fail(PTB_E_STATE, "Render() before an EnvironmentMap was set");
     CU(cudaSetDevice(c->device));
+    if (!c->scene_dirty && (c->n_nodes > 0 || c->n_unbounded > 0)) {
+        // the BVH margins were sized for an extent D that includes the camera: a camera that left it forces a rebuild
+        std::vector<Box> boxes; std::vector<char> bounded;
+        raw_boxes(c, 0.0, 0.0, boxes, bounded);
+        std::vector<Box> finite;
+        for (size_t i = 0; i < boxes.size(); ++i) if (bounded[i]) finite.push_back(boxes[i]);
+        if (required_extent(c, finite) > c->bvh_D) c->scene_dirty = true;
+    }
     int rc = sync_scene(c);
     if (rc != PTB_OK) return rc;
     CU(cudaEventRecord(c->ev0, c->stream));
@@ -567,10 +732,10 @@ int ptb_read_result_async(ptb_ctx* c, float* dst)
             CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         }
     }
-    if (c->stage_bytes < bytes) {
+    if (c->readback_bytes < bytes) {
         CU(cudaStreamSynchronize(c->copy_stream));
         for (int i = 0; i < 2; ++i) { if (c->d_stage[i]) CU(cudaFree(c->d_stage[i])); c->d_stage[i] = nullptr; CU(cudaMalloc(&c->d_stage[i], bytes)); }
-        c->stage_bytes = bytes;
+        c->readback_bytes = bytes;
     }
     // The image is accumulated in place, so the next Render() would race with a slow PCIe copy: snapshot it on the render
     // stream (HBM -> HBM), then let the copy stream move the snapshot to the host while the next frame renders.
@@ -819,7 +984,7 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
     case 1: in_f = n; out_f = n; break;
     case 2: in_f = 1; out_f = n; break;
     case 3: in_f = 3 * (size_t)n; out_f = 3 * (size_t)n; break;
-    case 4: case 6: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
+    case 4: case 6: case 9: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
     case 5: in_f = 2 * (size_t)n; out_f = 4 * (size_t)n; break;
     case 7: in_f = 6 * (size_t)n + 1; out_f = 12 * (size_t)n; break;
     case 8: in_f = n; out_f = n; break;
@@ -838,14 +1003,15 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
         else if (op == 3) {
             if (!c->d_env) { rc = fail(PTB_E_STATE, "no environment map set"); break; }
             dbg_env_kernel<<<gb, tb, 0, c->stream>>>(c->d_env, c->env_size, d_in, n, d_out);
-        } else if (op == 4 || op == 6) {
+        } else if (op == 4 || op == 6 || op == 9) {
             rc = sync_scene(c);
             if (rc != PTB_OK) break;
             RenderParams P;
             fill_params(c, P);
-            const int smem = op == 4 ? c->block_bytes : 0;
-            if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->block_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
-            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : 0);
+            const int smem = op == 6 ? 0 : c->stage_bytes;
+            if (op == 9 && c->n_nodes == 0 && c->n_unbounded == 0) { rc = fail(PTB_E_STATE, "the current scene has no BVH (fewer than %d primitives)", c->bvh_threshold); break; }
+            if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->stage_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
+            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : (op == 9 ? 2 : 0));
         } else if (op == 5) dbg_arith_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 8) dbg_log_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 7) {
@@ -855,8 +1021,8 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
             if (k < 1 || k > 32) { rc = fail(PTB_E_INVALID, "group size %d outside [1,32]", k); break; }
             RenderParams P;
             fill_params(c, P);
-            if (cudaFuncSetAttribute(dbg_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->block_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
-            dbg_group_kernel<<<(n + k - 1) / k, 32, c->block_bytes, c->stream>>>(P, d_in, n, d_out, k);
+            if (cudaFuncSetAttribute(dbg_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->stage_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
+            dbg_group_kernel<<<(n + k - 1) / k, 32, c->stage_bytes, c->stream>>>(P, d_in, n, d_out, k);
         }
         c->launches++;
         if (cudaGetLastError() != cudaSuccess) { rc = fail(PTB_E_CUDA, "debug kernel launch failed"); break; }

@@ -56,6 +56,9 @@ struct RenderParams {
     int rank, world, stripe_rows, local_rows;  // pixel-tile partition (rows y with (y/stripe_rows)%world==rank)
     // packed scene block (float4 units from the block base)
     int off_aux, off_cmin, off_cmax, off_mat, block_bytes;
+    int stage_bytes;          // bytes of the block staged into shared memory (== block_bytes unless materials stay in HBM)
+    int off_nodes, off_pidx, n_nodes, n_unbounded;   // BVH (float4 units from the block base); n_nodes == 0: brute force
+    float bvh_tau;
     const float4* scene;      // packed scene block in HBM
     const float4* env;        // padded cubemap
     float4* image;            // local accumulation image: local_rows x width
@@ -74,12 +77,17 @@ struct RenderParams {
 // Scene views.  Both expose the same accessors; the fold and the shader are written once against them.
 struct PackedScene {           // SoA block in shared memory
     const float4* base;
+    const float4* mats;        // materials: in the shared block, or (large scenes with a BVH) left in HBM / L2
+    const float4* nodes;       // BVH nodes, 2 x float4 each (large scenes only)
+    const int* pidx;           // BVH primitive index list: [unbounded primitives][leaf contents]
+    int n_nodes, n_unbounded;
+    float tau;                 // slack on ray parameters in the conservative box tests
     int nS, nC, off_aux, off_cmin, off_cmax, off_mat;
     __device__ __forceinline__ float4 sphere(int i) const { return base[i]; }                 // (c, r*r)
     __device__ __forceinline__ float sphere_rcp_r(int i) const { return reinterpret_cast<const float*>(base + off_aux)[i]; }
     __device__ __forceinline__ float4 cmin(int i) const { return base[off_cmin + i]; }
     __device__ __forceinline__ float4 cmax(int i) const { return base[off_cmax + i]; }
-    __device__ __forceinline__ float4 mat(int prim, int k) const { return base[off_mat + prim * 4 + k]; }
+    __device__ __forceinline__ float4 mat(int prim, int k) const { return mats[off_mat + prim * 4 + k]; }
 };
 struct RawScene {              // the std140 bytes exactly as the host uploaded them (naive proxy)
     const unsigned char* ubo;
@@ -103,6 +111,22 @@ struct RawScene {              // the std140 bytes exactly as the host uploaded 
         return __ldg(reinterpret_cast<const float4*>(p) + k);
     }
 };
+
+__device__ __forceinline__ PackedScene make_packed_scene(const float4* smem_block, const float4* global_block, int nS, int nC,
+                                                        int off_aux, int off_cmin, int off_cmax, int off_mat, int stage_bytes, int block_bytes,
+                                                        int off_nodes, int off_pidx, int n_nodes, int n_unbounded, float tau)
+{
+    PackedScene sc;
+    sc.base = smem_block;
+    sc.mats = stage_bytes >= block_bytes ? smem_block : global_block;
+    sc.nodes = smem_block + off_nodes;
+    sc.pidx = reinterpret_cast<const int*>(smem_block + off_pidx);
+    sc.n_nodes = n_nodes; sc.n_unbounded = n_unbounded; sc.tau = tau;
+    sc.nS = nS; sc.nC = nC; sc.off_aux = off_aux; sc.off_cmin = off_cmin; sc.off_cmax = off_cmax; sc.off_mat = off_mat;
+    return sc;
+}
+#define PTB_PACKED_SCENE(P, smem) make_packed_scene(smem, (P).scene, (P).n_spheres, (P).n_cuboids, (P).off_aux, (P).off_cmin, (P).off_cmax, \
+                                                    (P).off_mat, (P).stage_bytes, (P).block_bytes, (P).off_nodes, (P).off_pidx, (P).n_nodes, (P).n_unbounded, (P).bvh_tau)
 
 // ------------------------------------------------------------------------------------------------------------
 // pt:226-294 — the order-dependent closest-hit fold (spheres, then cuboids; accept on hit && t2>0 && t1<T).
@@ -415,6 +439,84 @@ __device__ __forceinline__ void trace_group(const PackedScene& sc, unsigned lane
     inside = __shfl_sync(0xffffffffu, (int)ginside, from) != 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Large scenes: the same fold through a bounding-volume hierarchy in shared memory.  The hierarchy only ever REMOVES
+// primitives that provably fail the exact test: every primitive's box is inflated by more than the worst-case rounding error
+// of its own fp32 test (spheres: radius^2 + 4e-6 D^2; slabs: 1e-5 D; D bounds every coordinate and origin-centre distance —
+// the derivation is in DESIGN.md), node tests carry a slack tau on the ray parameter, and whatever survives is tested with the
+// exact formulas.  Because candidates arrive out of index order, the order-dependent fold is rebuilt from its closed form
+// (see trace_group): pass 0 finds K, the largest index containing the origin, and the first-index argmin of the entry distance;
+// if K exists a second pass looks only at later primitives that beat t2_K.
+__device__ __forceinline__ void bvh_consider(const PackedScene& sc, int i, V3 o, V3 d, V3 inv, int after, float limit,
+                                             uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2, float& best)
+{
+    float a1, a2;
+    if (i > after && coop_test(sc, i, o, d, inv, a1, a2) && a2 > 0.0f) {
+        if (a1 < 0.0f) { if (i > k_idx) { k_idx = i; k_t2 = a2; } }
+        else if (a1 < limit) {
+            const uint32_t kk = __float_as_uint(a1) & 0x7fffffffu;
+            if (kk < key || (kk == key && i < idx)) { key = kk; idx = i; t1b = a1; t2b = a2; best = fmin_(best, a1); }
+        }
+    }
+}
+__device__ __forceinline__ bool bvh_box(const float4 lo, const float4 hi, V3 o, V3 inv, float tau, float best, float& tn)
+{
+    const float ax = (lo.x - o.x) * inv.x, ay = (lo.y - o.y) * inv.y, az = (lo.z - o.z) * inv.z;
+    const float bx = (hi.x - o.x) * inv.x, by = (hi.y - o.y) * inv.y, bz = (hi.z - o.z) * inv.z;
+    tn = fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz)));
+    const float tf = fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz)));
+    return tn <= tf && tf >= -tau && tn <= best + tau;
+}
+__device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, V3 inv, int after, float limit, float best,
+                                         uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2)
+{
+    key = 0xffffffffu; idx = 0x7fffffff; t1b = kFloatMax; t2b = 0.0f; k_idx = -1; k_t2 = 0.0f;
+    for (int u = 0; u < sc.n_unbounded; ++u) bvh_consider(sc, sc.pidx[u], o, d, inv, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
+    if (sc.n_nodes == 0) return;
+    int stack[32];
+    int sp = 0, node = 0;
+    while (true) {
+        const float4 A = sc.nodes[2 * node], B = sc.nodes[2 * node + 1];
+        const int count = __float_as_int(B.w), first = __float_as_int(A.w);
+        if (count > 0) {
+            for (int j = 0; j < count; ++j) bvh_consider(sc, sc.pidx[first + j], o, d, inv, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
+        } else {
+            float tl, tr;
+            const bool hl = bvh_box(sc.nodes[2 * first], sc.nodes[2 * first + 1], o, inv, sc.tau, best, tl);
+            const bool hr = bvh_box(sc.nodes[2 * first + 2], sc.nodes[2 * first + 3], o, inv, sc.tau, best, tr);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                if (sp < 32) stack[sp++] = left_first ? first + 1 : first;
+                node = left_first ? first : first + 1;
+                continue;
+            }
+            if (hl || hr) { node = hl ? first : first + 1; continue; }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+__device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
+{
+    // non-finite rays (normalize(0) after total internal reflection, ...) take the plain fold: nothing to cull by
+    const float fin = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+    if (!(fin <= kFloatMax)) { trace(sc, o, d, T, prim, inside); return; }
+    const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
+    uint32_t key; int idx, k_idx; float t1, t2, k_t2;
+    bvh_pass(sc, o, d, inv, -1, kFloatMax, kFloatMax, key, idx, t1, t2, k_idx, k_t2);
+    if (k_idx < 0) {
+        const bool found = key != 0xffffffffu;
+        T = found ? t1 : kFloatMax; prim = found ? idx : -1; inside = found && (t1 == t2);
+        return;
+    }
+    const int K = k_idx;
+    const float t2K = k_t2;
+    int k2; float k2t;
+    bvh_pass(sc, o, d, inv, K, __uint_as_float(0x7f800000u), t2K, key, idx, t1, t2, k2, k2t);
+    if (key != 0xffffffffu && t1 < t2K) { T = t1; prim = idx; inside = (t1 == t2); }
+    else { T = t2K; prim = K; inside = true; }
+}
+
 // pt:125-129 — mean over SPP, running mean over frames, store.  Frame 0 does not read the image: the reference
 // multiplies the stale value by exactly 0 there (mix(x, y, 1.0)), so a zero stands in for it.
 __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p)
@@ -497,7 +599,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // 8x4 tiles so a freshly filled warp starts on a compact footprint.
 // kRing: stage primary rays through the per-warp shared-memory ring (2 KB per warp; the host turns it off when the scene
 // block is so large that the ring would lower the number of resident CTAs).
-template <bool kStats, bool kRing>
+template <bool kStats, bool kRing, bool kBvh>
 __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const __grid_constant__ RenderParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -509,18 +611,16 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (uint32_t)P.block_bytes);
+        mbar_expect_tx(&bar, (uint32_t)P.stage_bytes);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(P.scene);
-        for (int off = 0; off < P.block_bytes; off += 32768) {
-            const int n = min(32768, P.block_bytes - off);
+        for (int off = 0; off < P.stage_bytes; off += 32768) {
+            const int n = min(32768, P.stage_bytes - off);
             tma_bulk_g2s(smem_raw + off, src + off, (uint32_t)n, &bar);
         }
     }
     mbar_wait(&bar, 0);
 
-    PackedScene sc;
-    sc.base = sblock; sc.nS = P.n_spheres; sc.nC = P.n_cuboids;
-    sc.off_aux = P.off_aux; sc.off_cmin = P.off_cmin; sc.off_cmax = P.off_cmax; sc.off_mat = P.off_mat;
+    const PackedScene sc = PTB_PACKED_SCENE(P, sblock);
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -636,7 +736,8 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
         if (starved && n_live <= (unsigned)PTB_COOP_MAX && P.ray_depth > 0) {
             trace_group(sc, lane, live, n_live, p.o, p.d, T, prim, inside);
         } else if (alive && P.ray_depth > 0) {
-            trace_any(sc, p.o, p.d, T, prim, inside);
+            if constexpr (kBvh) trace_bvh(sc, p.o, p.d, T, prim, inside);
+            else trace_any(sc, p.o, p.d, T, prim, inside);
         }
         if (alive) {
             const bool go = P.ray_depth > 0 ? shade(P, sc, p, T, prim, inside, stats) : false;
@@ -1045,7 +1146,7 @@ __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const f
     if (!use_raw) {
         const float4* src = P.scene;
         float4* dst = reinterpret_cast<float4*>(smem_raw);
-        for (int k = threadIdx.x; k < P.block_bytes / 16; k += blockDim.x) dst[k] = src[k];
+        for (int k = threadIdx.x; k < P.stage_bytes / 16; k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1053,9 +1154,23 @@ __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const f
     if (use_raw) {
         RawScene sc; sc.ubo = P.raw_objects; sc.nS = P.n_spheres; sc.nC = P.n_cuboids; sc.max_spheres = P.max_spheres;
         dbg_trace_one(sc, rays, i, out);
+    } else if (use_raw == 2) {
+        const PackedScene sc = PTB_PACKED_SCENE(P, reinterpret_cast<const float4*>(smem_raw));
+        const V3 o = mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        float T; int prim; bool inside;
+        trace_bvh(sc, o, d, T, prim, inside);
+        float* q = out + 12 * i;
+        const bool hit = T != kFloatMax;
+        q[0] = hit ? 1.0f : 0.0f; q[1] = T; q[2] = (hit && inside) ? 1.0f : 0.0f; q[3] = 0.0f;
+        for (int k = 4; k < 12; ++k) q[k] = 0.0f;
+        if (hit) {
+            const V3 pos = o + d * T;
+            const V3 n = surface_normal(sc, prim, pos);
+            q[4] = pos.x; q[5] = pos.y; q[6] = pos.z; q[7] = n.x; q[8] = n.y; q[9] = n.z;
+            q[10] = sc.mat(prim, 0).x; q[11] = sc.mat(prim, 1).x;
+        }
     } else {
-        PackedScene sc; sc.base = reinterpret_cast<const float4*>(smem_raw); sc.nS = P.n_spheres; sc.nC = P.n_cuboids;
-        sc.off_aux = P.off_aux; sc.off_cmin = P.off_cmin; sc.off_cmax = P.off_cmax; sc.off_mat = P.off_mat;
+        const PackedScene sc = PTB_PACKED_SCENE(P, reinterpret_cast<const float4*>(smem_raw));
         dbg_trace_one(sc, rays, i, out);
     }
 }
@@ -1066,11 +1181,10 @@ __global__ void dbg_group_kernel(const __grid_constant__ RenderParams P, const f
     {
         const float4* src = P.scene;
         float4* dst = reinterpret_cast<float4*>(smem_raw);
-        for (int q = threadIdx.x; q < P.block_bytes / 16; q += blockDim.x) dst[q] = src[q];
+        for (int q = threadIdx.x; q < P.stage_bytes / 16; q += blockDim.x) dst[q] = src[q];
     }
     __syncthreads();
-    PackedScene sc; sc.base = reinterpret_cast<const float4*>(smem_raw); sc.nS = P.n_spheres; sc.nC = P.n_cuboids;
-    sc.off_aux = P.off_aux; sc.off_cmin = P.off_cmin; sc.off_cmax = P.off_cmax; sc.off_mat = P.off_mat;
+    const PackedScene sc = PTB_PACKED_SCENE(P, reinterpret_cast<const float4*>(smem_raw));
     const unsigned lane = threadIdx.x & 31u;
     const int j = (int)(((lane + 29u) * 23u) & 31u);        // inverse of lane = (3 + 7j) mod 32
     const int i = blockIdx.x * k + j;

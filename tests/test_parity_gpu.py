@@ -140,6 +140,62 @@ def test_group_cooperative_fold_bit_exact(ptb, oracle, env256, camera):
         pt.Dispose()
 
 
+def test_bvh_fold_bit_exact(ptb, oracle, env256, camera):
+    """Scenes of >= 96 primitives go through the shared-memory BVH.  It may only remove primitives that fail the exact test,
+    so the fold must equal the oracle's brute-force fold bit for bit — including rays that start inside (overlapping)
+    primitives, axis-parallel rays, rays grazing box faces, far-away origins and degenerate / non-finite geometry."""
+    rng = np.random.default_rng(17)
+    for scene in (ptb.synthetic_scene(1024, 256), ptb.synthetic_scene(200, 60, seed=3)):
+        if len(scene.spheres) == 200:      # poison a few primitives: NaN centre, infinite box, inverted box, zero radius
+            scene.spheres[5].Position = np.array([np.nan, 0, 0], np.float32)
+            scene.spheres[6].Radius = np.float32(0.0)
+            scene.cuboids[20].Dimensions = np.array([np.inf, 1, 1], np.float32)
+            scene.cuboids[21].Dimensions = np.array([-1.0, 2.0, -0.5], np.float32)
+        pt = make_tracer(ptb, env256, 16, 16, scene, camera)
+        n = 60000
+        o = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.array([44, 28, 28], np.float32) + np.array([0, 0, -10], np.float32)
+        centres = np.stack([s.Position for s in scene.spheres])
+        pick = rng.integers(0, len(scene.spheres), n // 3)
+        radii = np.array([s.Radius for s in scene.spheres], np.float32)[pick, None]
+        o[: n // 3] = np.nan_to_num(centres[pick]) + (rng.random((n // 3, 3)).astype(np.float32) - np.float32(0.5)) * radii * np.float32(1.8)
+        cpick = rng.integers(0, len(scene.cuboids), n // 6)
+        cmin = np.stack([c.Min for c in scene.cuboids])[cpick]; cmax = np.stack([c.Max for c in scene.cuboids])[cpick]
+        with np.errstate(all="ignore"):
+            inside_box = cmin + rng.random((n // 6, 3)).astype(np.float32) * (cmax - cmin)
+        o[n // 3: n // 3 + n // 6] = np.nan_to_num(inside_box, posinf=5.0, neginf=-5.0)
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        d[-300:-200, 0] = 0; d[-200:-100, 1] = 0; d[-100:, :2] = 0; d[-100:, 2] = 1       # axis-parallel: infinite reciprocals
+        o[-50:] *= np.float32(40.0)                                                          # far outside the scene
+        rays = np.concatenate([o, d], 1).astype(np.float32)
+        ref = oracle.ray_trace(rays, scene.ubo_bytes(), scene.max_spheres, len(scene.spheres), len(scene.cuboids))
+        assert ref[:, 2].sum() > 3000 and ref[:, 0].sum() > 30000
+        got = pt.DebugEval(9, rays, n, 12 * n).reshape(-1, 12)
+        assert_same(got, ref, f"BVH fold, {len(scene.spheres)} spheres + {len(scene.cuboids)} cuboids")
+        pt.Dispose()
+    small = make_tracer(ptb, env256, 16, 16, ptb.load_default_scene(), camera)
+    with pytest.raises(ptb.PtbError):          # 55 primitives: brute force, no BVH to probe
+        small.DebugEval(9, np.zeros(6, np.float32), 1, 12)
+    small.Dispose()
+
+
+def test_bvh_survives_camera_leaving_the_scene(ptb, oracle, env256):
+    """The BVH's safety margins scale with an extent that includes the camera; moving the camera far away must rebuild them."""
+    scene = ptb.synthetic_scene(160, 40, seed=8)
+    sc = ptb.scene
+    pt = ptb.PathTracer(env256, 96, 54, 8, 1, 20.0, 0.14, max_spheres=scene.max_spheres, max_cuboids=scene.max_cuboids)
+    pt.LoadScene(scene)
+    for pos in ([-17.14, 3.53, -8.62], [-900.0, 40.0, 700.0], [3.0e4, 10.0, -2.0e4], [-17.14, 3.53, -8.62]):
+        cam = sc.Camera(np.array(pos, np.float32), np.array([0, 1, 0], np.float32), -32.2, 0.8)
+        cam_target = sc.Camera(np.array(pos, np.float32), np.array([0, 1, 0], np.float32),
+                               float(np.degrees(np.arctan2(-10 - pos[2], -pos[0]))), float(np.degrees(np.arctan2(-pos[1], np.hypot(pos[0], pos[2] + 10)))))
+        for c in (cam, cam_target):
+            pt.SetCamera(c); pt.ResetRenderer(); pt.Render()
+            ref = oracle_render(oracle, sc, scene, c, env256, 96, 54, 1, depth=8)
+            assert_same(pt.Result, ref, f"camera at {pos}")
+    pt.Dispose()
+
+
 # ------------------------------------------------------------------------------- image parity
 CASES = [
     # name, W, H, frames, kwargs
@@ -402,12 +458,23 @@ def test_error_codes(ptb, env256):
     assert L.ptb_game_objects_subdata(ctx, 256 * 80 + 64 * 96 - 16, 16, buf) == 0
     assert L.ptb_set_tile(ctx, 2, 2, 8) == -1 and L.ptb_set_kernel(ctx, 7) == -1
     L.ptb_destroy(ctx)
-    # a scene too large for shared memory is refused, not silently truncated
-    big = ptb.PathTracer(env256, 16, 16, 4, 1, 20.0, 0.14, max_spheres=4096, max_cuboids=64)
-    big.NumSpheres = 4096
+    # a scene whose geometry cannot be staged in shared memory is refused, not silently truncated
+    huge = ptb.PathTracer(env256, 16, 16, 4, 1, 20.0, 0.14, max_spheres=16384, max_cuboids=64)
+    huge.NumSpheres = 16384
     with pytest.raises(ptb.PtbError):
-        big.Render()
-    big.Dispose()
+        huge.Render()
+    huge.Dispose()
+
+
+def test_four_thousand_spheres(ptb, oracle, env256, camera):
+    """4096 spheres + 64 cuboids: 327 KB as a packed block, but with the BVH only geometry + hierarchy (~190 KB) are staged and
+    the materials stay in HBM."""
+    scene = ptb.synthetic_scene(4096, 64, seed=77)
+    pt = make_tracer(ptb, env256, 48, 32, scene, camera, depth=6)
+    pt.Render(2)
+    ref = oracle_render(oracle, ptb.scene, scene, camera, env256, 48, 32, 2, depth=6)
+    assert_same(pt.Result, ref, "4096-sphere scene")
+    pt.Dispose()
 
 
 # ------------------------------------------------------------------------------- atmosphere producer on the GPU

@@ -1,0 +1,17 @@
+import os, sys, zlib
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ptb200
+sc = ptb200.scene
+cam = sc.default_camera()
+syn = sc.synthetic_scene(1024, 256)
+p = ptb200.PathTracer(None, 1920, 1080, 8, 1, 20.0, 0.14, max_spheres=1024, max_cuboids=256)
+p.GenerateAtmosphere(256, 50, 15, 0.5, 15.0); p.LoadScene(syn); p.SetCamera(cam)
+p.Render(2); p.Synchronize()
+best = 1e9
+for _ in range(3):
+    p.ResetRenderer(); p.Render(6); best = min(best, p.LastRenderMs() / 6)
+p.ResetRenderer(); p.Render(2); a = p.Result
+p.SetStats(True); p.ResetRenderer(); p.Render(1); st = p.ReadStats(); p.SetStats(False)
+print(f"C3: {best:.3f} ms/frame -> {1920*1080/best/1e3:.0f} Msamples/s crc={zlib.crc32(a.tobytes()):08x} bounces/sample={st['bounces']/st['samples']:.2f}", flush=True)
