@@ -31,7 +31,7 @@ W, H = 1920, 1080
 RAY_DEPTH, SPP, FOCAL, APERTURE = 13, 1, 20.0, 0.14
 WORKLOAD = "default demo scene (48 spheres + 7 cuboids), 1920x1080, SPP 1 per frame, rayDepth 13, 256^2 atmosphere env (BASELINE configs[1])"
 STRIPE_ROWS = 8
-L2_FLUSH_BYTES = 256 << 20
+L2_FLUSH_BYTES = 160 << 20      # larger than the 126 MB L2
 
 
 def measured_peaks():
@@ -42,6 +42,18 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def issue_roofline(ncu, kern_ms, world):
+    """The bound that actually binds: warp-instructions issued per second against 148 SMs x 4 schedulers x SM clock.
+    Instruction count per launch comes from the committed ncu capture (full frame); duration is measured live."""
+    inst = ncu.get("inst_executed_per_launch")
+    if not inst:
+        return None
+    achieved = inst / world / (kern_ms * 1e-3) / 1e12
+    peak = 148 * 4 * 1.965e9 / 1e12
+    return {"achieved": achieved, "peak": peak, "unit": "T warp-inst/s", "frac": achieved / peak,
+            "note": "peak = 148 SMs x 4 issue slots x 1.965 GHz; instructions per launch from profiles/ncu_summary.json"}
 
 
 def ncu_summary():
@@ -179,8 +191,22 @@ def run_ours(args, rank, world, local_rank):
     pt.SetCamera(cam)
     # N > 1: the fused exchange (blend kernel stores straight into rank 0's image over NVLink); PTB_EXCHANGE=nccl selects the
     # NCCL gather + de-interleave path instead
-    fused = os.environ.get("PTB_EXCHANGE", "fused") != "nccl"
-    tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=fused) if world > 1 else None
+    fused = os.environ.get("PTB_EXCHANGE", "fused") != "nccl" and world > 1
+    tiled = None
+    if world > 1:
+        if fused:
+            # CUDA IPC needs peer access between the ranks' devices; if any rank cannot set it up, everybody uses NCCL
+            try:
+                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True)
+                ok = torch.ones(1, device=dev)
+            except Exception as exc:      # noqa: BLE001
+                print(f"rank {rank}: fused exchange unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr, flush=True)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1:
+                fused, tiled = False, None
+        if tiled is None:
+            tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=False)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     inv_view = sc.matrix_bytes(sc.inverted(cam.View))
     view_pos = np.append(np.asarray(cam.Position, np.float32), np.float32(0)).tobytes()
@@ -256,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
 
     def timed(fn, steps, flush_l2, finisher=None):
         """K steps enqueued back to back on the launching stream (the library pipelines consecutive frames), one CUDA-event
-        bracket around the whole region.  L2 flush: a 256 MiB memset per step on a concurrent stream, INSIDE the timed region
+        bracket around the whole region.  L2 flush: a 160 MiB memset (> the 126 MB L2) per step on a concurrent stream, INSIDE the timed region
         (a serialised flush would have to drain the frame pipeline and time something the library never does)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -331,14 +357,15 @@ def run_ours(args, rank, world, local_rank):
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "flushed every step by a 256 MiB memset on a concurrent stream, inside the timed region",
+        "config": {"workload": WORKLOAD, "l2": "flushed every step by a 160 MiB memset (> 126 MB L2) on a concurrent stream, inside the timed region",
                    "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + ("exchange fused into the blend kernel: peer stores into rank 0's image over NVLink (CUDA IPC), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render") if world > 1 else "single GPU, no collective",
                    "kernel": "persistent megakernel (ptb::megakernel) + blend kernel per frame, 2 frames in flight (ptb_set_overlap)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "ptb::megakernel<false>",
                      "kernel_ms": kern_ms, "kernel_timing": "megakernel alone, in-place mode (ptb_set_overlap(1)), 20 launches back to back, CUDA events", "algorithmic_bytes_per_launch": algo_bytes,
                      "note": "the pass is FP32-issue-bound, not HBM-bound: ~3.4k lane-instructions per 32 B of image traffic (DESIGN.md); see issue_*",
-                     "issue_active_pct": ncu.get("smsp_issue_active_pct"), "inst_executed_per_launch": ncu.get("inst_executed_per_launch")},
+                     "issue_active_pct": ncu.get("smsp_issue_active_pct"), "inst_executed_per_launch": ncu.get("inst_executed_per_launch"),
+                     "issue": issue_roofline(ncu, kern_ms, world)},
         "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 80 + 144,
                 "d2h_bytes_per_step": W * H * 16, "steps": e2e_steps,
                 "note": "per step: InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), full RGBA32F image read back to pinned host memory through ptb_read_result_async (snapshot + copy stream, overlapping the next Render()); one sync after the last step, inside the timed region"},
