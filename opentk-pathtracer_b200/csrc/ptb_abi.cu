@@ -309,7 +309,7 @@ void layout_block(ptb_ctx* c)
 {
     // float4 units: [spheres][1/r][cuboid lo][cuboid hi][BVH nodes][BVH index list] | [materials]
     const int nS = c->n_spheres, nC = c->n_cuboids;
-    c->off_aux = nS;
+    c->off_aux = (nS + 3) & ~3;                 // the sphere array is padded to a multiple of four (never-hit dummies)
     c->off_cmin = c->off_aux + (nS + 3) / 4;
     c->off_cmax = c->off_cmin + nC;
     c->off_nodes = c->off_cmax + nC;

@@ -170,7 +170,63 @@ __device__ __forceinline__ void trace(const Scene& sc, V3 o, V3 d, float& T, int
     }
 }
 
-__device__ __forceinline__ void trace_any(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside) { trace(sc, o, d, T, prim, inside); }
+// The fold over the shared-memory block: spheres four at a time (the array is padded to a multiple of four with spheres of
+// r^2 = -inf that nothing can hit), one max + branch for the four discriminants — a NaN or negative discriminant never hits,
+// so dropping those through the NaN-ignoring max is exact — then the cuboids as in trace().
+__device__ __forceinline__ void accept_sphere(float b, float disc, int i, float& T, int& prim, bool& inside)
+{
+    if (!(disc < 0.0f)) {
+        const float sq = fsqrt(disc);
+        const float t1 = -b - sq;
+        const float t2 = -b + sq;
+        if (t1 <= t2 && t2 > 0.0f && t1 < T) {
+            T = t1 < 0.0f ? t2 : t1;
+            inside = (T == t2);
+            prim = i;
+        }
+    }
+}
+__device__ __forceinline__ void sphere_terms(const float4 s, V3 o, V3 d, float& b, float& disc)
+{
+    const V3 v = mk(o.x - s.x, o.y - s.y, o.z - s.z);
+    b = dot(d, v);
+    const float c = dot(v, v) - s.w;
+    disc = b * b - c;
+}
+__device__ __forceinline__ void trace_any(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
+{
+    T = kFloatMax;
+    prim = -1;
+    inside = false;
+    const int n4 = (sc.nS + 3) & ~3;
+    for (int i = 0; i < n4; i += 4) {
+        float b0, b1, b2, b3, d0, d1, d2, d3;
+        sphere_terms(sc.base[i], o, d, b0, d0);
+        sphere_terms(sc.base[i + 1], o, d, b1, d1);
+        sphere_terms(sc.base[i + 2], o, d, b2, d2);
+        sphere_terms(sc.base[i + 3], o, d, b3, d3);
+        if (fmax_(fmax_(d0, d1), fmax_(d2, d3)) >= 0.0f) {
+            accept_sphere(b0, d0, i, T, prim, inside);
+            accept_sphere(b1, d1, i + 1, T, prim, inside);
+            accept_sphere(b2, d2, i + 2, T, prim, inside);
+            accept_sphere(b3, d3, i + 3, T, prim, inside);
+        }
+    }
+    const float ix = rcp(d.x), iy = rcp(d.y), iz = rcp(d.z);
+#pragma unroll 2
+    for (int i = 0; i < sc.nC; ++i) {
+        const float4 lo = sc.cmin(i), hi = sc.cmax(i);
+        const float ax = (lo.x - o.x) * ix, ay = (lo.y - o.y) * iy, az = (lo.z - o.z) * iz;
+        const float bx = (hi.x - o.x) * ix, by = (hi.y - o.y) * iy, bz = (hi.z - o.z) * iz;
+        const float t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
+        const float t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
+        if (t1 <= t2 && t2 > 0.0f && t1 < T) {
+            T = t1 < 0.0f ? t2 : t1;
+            inside = (T == t2);
+            prim = sc.nS + i;
+        }
+    }
+}
 __device__ __forceinline__ void trace_any(const RawScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside) { trace(sc, o, d, T, prim, inside); }
 
 // pt:316-332 — surface normal of the winning primitive.
@@ -304,23 +360,32 @@ __device__ __forceinline__ bool shade(const RenderParams& P, const Scene& sc, Pa
             const float diffuse_chance = 1.0f - spec - refr;
             refr = 1.0f - spec - diffuse_chance;
         }
-        const V3 diffuse = cosine_hemisphere(n, p.rng);
+        // RNG draws in the shader's order: hemisphere z, hemisphere angle, lobe roll, and for the refraction lobe a
+        // second (z, angle) pair.  The refraction lobe never uses the first hemisphere DIRECTION (pt:210-211), only its draws, so
+        // one hemisphere evaluation serves every lane: around -n from the second pair for refraction, around n from the first
+        // pair otherwise.  Same operations on the same values as pt:297-307, once instead of twice per iteration.
+        float uz = rand01(p.rng);
+        float ua = rand01(p.rng);
         const float roll = rand01(p.rng);
-        bool refractive = false;
-        float prob;
-        V3 nd;
-        if (spec > roll) {
-            nd = normalize(mix(reflect(p.d, n), diffuse, m1.w * m1.w));
-            prob = spec;
-        } else if (spec + refr > roll) {
-            const V3 rdir = refract(p.d, n, inside ? fdiv(ior, 1.0f) : fdiv(1.0f, ior));
-            const V3 hemi = cosine_hemisphere(-n, p.rng);
-            nd = normalize(mix(rdir, hemi, m3.x * m3.x));
-            prob = refr;
-            refractive = true;
-        } else {
-            nd = diffuse;
-            prob = 1.0f - spec - refr;
+        const bool lobe_spec = spec > roll;
+        const bool lobe_refr = !lobe_spec && (spec + refr > roll);
+        V3 hn = n;
+        if (lobe_refr) { uz = rand01(p.rng); ua = rand01(p.rng); hn = -n; }
+        const float hz = uz * 2.0f - 1.0f;
+        const float ha = ua * 2.0f * kPi;
+        const float hr = fsqrt(1.0f - hz * hz);
+        float hs, hc;
+        sincos_(ha, hs, hc);
+        const V3 hemi = normalize(hn + mk(hr * hc, hr * hs, hz));
+        const bool refractive = lobe_refr;
+        float prob = 1.0f - spec - refr;
+        V3 nd = hemi;
+        if (lobe_spec || lobe_refr) {
+            V3 x;
+            float rough;
+            if (lobe_spec) { x = reflect(p.d, n); rough = m1.w * m1.w; prob = spec; }
+            else { x = refract(p.d, n, inside ? fdiv(ior, 1.0f) : fdiv(1.0f, ior)); rough = m3.x * m3.x; prob = refr; }
+            nd = normalize(mix(x, hemi, rough));
         }
         p.d = nd;
         p.o = pos + nd * kEps;
@@ -792,6 +857,8 @@ __global__ void pack_scene_kernel(const unsigned char* __restrict__ ubo, int max
         block[i] = make_float4(g.x, g.y, g.z, g.w * g.w);
         reinterpret_cast<float*>(block + off_aux)[i] = rcp(g.w);
         for (int k = 0; k < 4; ++k) block[off_mat + i * 4 + k] = s[1 + k];
+        if (i == nS - 1)                                         // pad to a multiple of four with spheres nothing can hit
+            for (int q = nS; q < ((nS + 3) & ~3); ++q) block[q] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xff800000u));
     } else if (i < nS + nC) {
         const int c = i - nS;
         const float4* s = reinterpret_cast<const float4*>(ubo + (size_t)max_spheres * kSphereStride + (size_t)c * kCuboidStride);
