@@ -31,6 +31,7 @@ W, H = 1920, 1080
 RAY_DEPTH, SPP, FOCAL, APERTURE = 13, 1, 20.0, 0.14
 WORKLOAD = "default demo scene (48 spheres + 7 cuboids), 1920x1080, SPP 1 per frame, rayDepth 13, 256^2 atmosphere env (BASELINE configs[1])"
 STRIPE_ROWS = 8
+EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "4"))      # full-image buffers on rank 0: how far the ranks may drift apart
 L2_FLUSH_BYTES = 160 << 20      # larger than the 126 MB L2
 
 
@@ -197,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
         if fused:
             # CUDA IPC needs peer access between the ranks' devices; if any rank cannot set it up, everybody uses NCCL
             try:
-                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True)
+                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True, slots=EXCHANGE_SLOTS)
                 ok = torch.ones(1, device=dev)
             except Exception as exc:      # noqa: BLE001
                 print(f"rank {rank}: fused exchange unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr, flush=True)

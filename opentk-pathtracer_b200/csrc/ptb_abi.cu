@@ -39,6 +39,8 @@ constexpr int kMaxOverlap = 4;
 
 } // namespace
 
+struct SceneExtent { double lo[3], hi[3], maxabs; };     // bounds of the finite primitive boxes (BVH error-margin sizing)
+
 struct ptb_ctx {
     int device = 0;
     int sm_count = 148;
@@ -65,6 +67,7 @@ struct ptb_ctx {
     float bvh_tau = 0.0f, bvh_D = 0.0f;
     std::vector<float4> bvh_nodes;
     std::vector<int> bvh_pidx;
+    SceneExtent bvh_extent = {};
     float4* d_env_faces = nullptr;   // unpadded 6*N*N
     float4* d_env = nullptr;         // padded 6*(N+2)^2
     int env_size = 0;
@@ -142,7 +145,7 @@ int ensure_pipeline(ptb_ctx* c)
             CU(cudaEventCreateWithFlags(&c->ev_blend_done[i], cudaEventDisableTiming));
             CU(cudaMalloc(&c->d_slot_counters[i], 2 * sizeof(unsigned int)));
             CU(cudaMemsetAsync(c->d_slot_counters[i], 0, 2 * sizeof(unsigned int), c->stream));
-            CU(mark_inputs(c) == PTB_OK ? cudaSuccess : cudaErrorUnknown);
+            { const int rc = mark_inputs(c); if (rc != PTB_OK) return rc; }
         }
     }
     if (!c->blend_stream) {
@@ -151,7 +154,7 @@ int ensure_pipeline(ptb_ctx* c)
         CU(cudaStreamCreateWithPriority(&c->blend_stream, cudaStreamNonBlocking, hi));   // small kernel, must not queue behind a persistent grid
     }
     if (c->scratch_bytes != bytes) {
-        CU(sync_all(c) == PTB_OK ? cudaSuccess : cudaErrorUnknown);
+        { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
         for (int i = 0; i < kMaxOverlap; ++i) { if (c->d_scratch[i]) CU(cudaFree(c->d_scratch[i])); c->d_scratch[i] = nullptr; }
         for (int i = 0; i < c->overlap; ++i) CU(cudaMalloc(&c->d_scratch[i], bytes));
         c->scratch_bytes = bytes;
@@ -193,19 +196,32 @@ struct Box { double lo[3], hi[3]; };
 #define PTB_BVH_LEAF 4
 #endif
 
-float required_extent(ptb_ctx* c, const std::vector<Box>& boxes)
+SceneExtent scene_extent(const std::vector<Box>& boxes)
 {
-    // D bounds every coordinate that enters a test and every origin-to-primitive distance: scene boxes + camera + lens
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, maxabs = 0.0;
-    auto grow = [&](const double* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); maxabs = std::max(maxabs, std::fabs(p[k])); } };
-    for (const Box& b : boxes) { grow(b.lo); grow(b.hi); }
+    SceneExtent e = {{1e300, 1e300, 1e300}, {-1e300, -1e300, -1e300}, 0.0};
+    for (const Box& b : boxes)
+        for (int k = 0; k < 3; ++k) {
+            e.lo[k] = std::min(e.lo[k], b.lo[k]); e.hi[k] = std::max(e.hi[k], b.hi[k]);
+            e.maxabs = std::max(e.maxabs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+        }
+    return e;
+}
+
+// D bounds every coordinate that enters a test and every origin-to-primitive distance: scene boxes + camera + lens,
+// rounded up to a power of two so that small camera moves do not change it.
+float required_extent(ptb_ctx* c, SceneExtent e)
+{
     float cam[3];
     memcpy(cam, c->basic + 128, 12);
     const double lens = std::fabs((double)c->aperture_diameter) * 0.5 + 1.0;
-    for (int sgn = -1; sgn <= 1; sgn += 2) { double p[3] = {cam[0] + sgn * lens, cam[1] + sgn * lens, cam[2] + sgn * lens}; if (std::isfinite(p[0] + p[1] + p[2])) grow(p); }
+    for (int k = 0; k < 3; ++k) {
+        if (!std::isfinite(cam[k])) continue;
+        e.lo[k] = std::min(e.lo[k], cam[k] - lens); e.hi[k] = std::max(e.hi[k], cam[k] + lens);
+        e.maxabs = std::max(e.maxabs, std::fabs((double)cam[k]) + lens);
+    }
     double diag2 = 0.0;
-    for (int k = 0; k < 3; ++k) diag2 += (hi[k] - lo[k]) * (hi[k] - lo[k]);
-    const double D = 1.01 * std::max(std::sqrt(diag2), maxabs) + 1.0;
+    for (int k = 0; k < 3; ++k) diag2 += (e.hi[k] - e.lo[k]) * (e.hi[k] - e.lo[k]);
+    const double D = 1.01 * std::max(std::sqrt(diag2), e.maxabs) + 1.0;
     float Dq = 1.0f;
     while (Dq < D && Dq < 1e30f) Dq *= 2.0f;
     return Dq;
@@ -244,7 +260,8 @@ void build_bvh(ptb_ctx* c)
     raw_boxes(c, 0.0, 0.0, boxes, bounded);
     std::vector<Box> finite;
     for (int i = 0; i < n; ++i) if (bounded[i]) finite.push_back(boxes[i]);
-    const float D = required_extent(c, finite);
+    c->bvh_extent = scene_extent(finite);
+    const float D = required_extent(c, c->bvh_extent);
     const double E = 4e-6 * (double)D * D, m = 1e-5 * (double)D + 1e-6;
     raw_boxes(c, E, m, boxes, bounded);
     // primitives that span a large part of the scene (the room's walls and floor) would drag every ancestor box up to scene
@@ -690,11 +707,7 @@ int ptb_render_frames(ptb_ctx* c, int n)
     CU(cudaSetDevice(c->device));
     if (!c->scene_dirty && (c->n_nodes > 0 || c->n_unbounded > 0)) {
         // the BVH margins were sized for an extent D that includes the camera: a camera that left it forces a rebuild
-        std::vector<Box> boxes; std::vector<char> bounded;
-        raw_boxes(c, 0.0, 0.0, boxes, bounded);
-        std::vector<Box> finite;
-        for (size_t i = 0; i < boxes.size(); ++i) if (bounded[i]) finite.push_back(boxes[i]);
-        if (required_extent(c, finite) > c->bvh_D) c->scene_dirty = true;
+        if (required_extent(c, c->bvh_extent) > c->bvh_D) c->scene_dirty = true;
     }
     int rc = sync_scene(c);
     if (rc != PTB_OK) return rc;

@@ -347,7 +347,9 @@ __device__ __forceinline__ bool shade(const RenderParams& P, const Scene& sc, Pa
         const float ior = m3.y;
         if (inside) {                                        // pt:145-149 Beer's law
             n = -n;
-            p.thr = p.thr * mk(exp_(-m2.x * T), exp_(-m2.y * T), exp_(-m2.z * T));
+            // exp(-0 * T) is exactly 1 for finite T, so a medium without absorbance (clear glass) skips the three exponentials
+            if (!(m2.x == 0.0f && m2.y == 0.0f && m2.z == 0.0f && T <= kFloatMax))
+                p.thr = p.thr * mk(exp_(-m2.x * T), exp_(-m2.y * T), exp_(-m2.z * T));
         }
         // ---- BSDF, pt:184-224
         float spec = m0.w, refr = m2.w;

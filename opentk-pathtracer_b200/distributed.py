@@ -103,6 +103,7 @@ class TiledPathTracer:
         self._k = 0
         self._pending = None       # (buffer index, work)
         self._last_full = None
+        self._slot_tensors = {}
         if self.fused:
             self._init_fused(slots)
 
@@ -146,7 +147,10 @@ class TiledPathTracer:
         L, ctx = self.tracer._L, self.tracer._ctx
         ptr = C.c_void_p()
         _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
-        full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+        full = self._slot_tensors.get(ptr.value)
+        if full is None:           # wrapping a raw pointer costs tens of microseconds: once per slot, not once per frame
+            full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+            self._slot_tensors[ptr.value] = full
         if consumer is not None:
             consumer(full)
         _lib.check(L.ptb_exchange_release(ctx))

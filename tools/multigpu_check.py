@@ -22,7 +22,7 @@ dist.init_process_group("nccl", device_id=dev)
 sc = ptb200.scene
 scene, cam = sc.load_default_scene(), sc.default_camera()
 W, H = (int(v) for v in os.environ.get("SIZE", "1920x1080").split("x"))
-FRAMES = 6
+FRAMES = int(os.environ.get('FRAMES', '6'))
 
 
 def make():
@@ -46,7 +46,7 @@ if True:
 ok = True
 for fused in (False, True):
     pt = make()
-    tp = D.TiledPathTracer(pt, rank, world, 8, device=dev, fused=fused)
+    tp = D.TiledPathTracer(pt, rank, world, 8, device=dev, fused=fused, slots=int(os.environ.get('SLOTS', '2')))
     snap = torch.empty((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None
     full = None
     for f in range(FRAMES):
