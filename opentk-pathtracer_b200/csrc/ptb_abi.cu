@@ -278,7 +278,7 @@ void build_bvh(ptb_ctx* c)
     c->bvh_D = D;
     c->bvh_tau = 1e-4f * D;
     if (order.empty()) return;
-    struct Task { int node, begin, end; };
+    struct Task { int node, begin, end, depth; };      // the device-side traversal stack holds 32 entries: depth is bounded below
     std::vector<Task> todo;
     auto set_box = [&](int node, int begin, int end) {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -290,7 +290,7 @@ void build_bvh(ptb_ctx* c)
         c->bvh_nodes[2 * node] = A; c->bvh_nodes[2 * node + 1] = B;
     };
     c->bvh_nodes.resize(2);
-    todo.push_back({0, 0, (int)order.size()});
+    todo.push_back({0, 0, (int)order.size(), 0});
     while (!todo.empty()) {
         const Task t = todo.back(); todo.pop_back();
         set_box(t.node, t.begin, t.end);
@@ -303,21 +303,72 @@ void build_bvh(ptb_ctx* c)
             memcpy(&c->bvh_nodes[2 * t.node + 1].w, &cnt, 4);
             continue;
         }
+        // binned surface-area heuristic: 16 bins per axis over the centroid range, cost = area(L) * n(L) + area(R) * n(R)
         double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
         for (int q = t.begin; q < t.end; ++q) for (int k = 0; k < 3; ++k) { const double ce = boxes[order[q]].lo[k] + boxes[order[q]].hi[k]; clo[k] = std::min(clo[k], ce); chi[k] = std::max(chi[k], ce); }
-        int axis = 0;
-        if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-        if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-        const int mid = t.begin + cnt / 2;
-        std::nth_element(order.begin() + t.begin, order.begin() + mid, order.begin() + t.end,
-                         [&](int a, int b) { return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis]; });
+        auto half_area = [](const double* lo, const double* hi) { const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return dx * dy + dy * dz + dz * dx; };
+        constexpr int kBins = 16;
+        int best_axis = -1, best_bin = -1;
+        double best_cost = 1e300;
+        // beyond depth 14 only balanced median splits are used, so the total depth stays under 14 + log2(n) < 32
+        for (int axis = 0; axis < 3 && t.depth < 14; ++axis) {
+            const double ext = chi[axis] - clo[axis];
+            if (!(ext > 0.0)) continue;
+            int cntb[kBins] = {};
+            double blo[kBins][3], bhi[kBins][3];
+            for (int b = 0; b < kBins; ++b) for (int k = 0; k < 3; ++k) { blo[b][k] = 1e300; bhi[b][k] = -1e300; }
+            for (int q = t.begin; q < t.end; ++q) {
+                const Box& bx = boxes[order[q]];
+                int b = (int)(((bx.lo[axis] + bx.hi[axis]) - clo[axis]) / ext * kBins);
+                b = std::min(std::max(b, 0), kBins - 1);
+                cntb[b]++;
+                for (int k = 0; k < 3; ++k) { blo[b][k] = std::min(blo[b][k], bx.lo[k]); bhi[b][k] = std::max(bhi[b][k], bx.hi[k]); }
+            }
+            double rlo[kBins][3], rhi[kBins][3]; int rcnt[kBins];
+            double alo[3] = {1e300, 1e300, 1e300}, ahi[3] = {-1e300, -1e300, -1e300}; int acc = 0;
+            for (int b = kBins - 1; b >= 0; --b) {
+                for (int k = 0; k < 3; ++k) { alo[k] = std::min(alo[k], blo[b][k]); ahi[k] = std::max(ahi[k], bhi[b][k]); }
+                acc += cntb[b];
+                for (int k = 0; k < 3; ++k) { rlo[b][k] = alo[k]; rhi[b][k] = ahi[k]; }
+                rcnt[b] = acc;
+            }
+            double llo[3] = {1e300, 1e300, 1e300}, lhi[3] = {-1e300, -1e300, -1e300}; int lc = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                for (int k = 0; k < 3; ++k) { llo[k] = std::min(llo[k], blo[b][k]); lhi[k] = std::max(lhi[k], bhi[b][k]); }
+                lc += cntb[b];
+                if (lc == 0 || rcnt[b + 1] == 0) continue;
+                const double cost = half_area(llo, lhi) * lc + half_area(rlo[b + 1], rhi[b + 1]) * rcnt[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+        int mid;
+        if (best_axis >= 0) {
+            const int axis = best_axis;
+            const double ext = chi[axis] - clo[axis];
+            auto it = std::partition(order.begin() + t.begin, order.begin() + t.end, [&](int a) {
+                int b = (int)(((boxes[a].lo[axis] + boxes[a].hi[axis]) - clo[axis]) / ext * kBins);
+                b = std::min(std::max(b, 0), kBins - 1);
+                return b <= best_bin;
+            });
+            mid = (int)(it - order.begin());
+        } else {
+            mid = t.begin;      // all centroids coincide
+        }
+        if (mid == t.begin || mid == t.end) {      // degenerate: fall back to an object-median split on the widest axis
+            int axis = 0;
+            if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+            if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+            mid = t.begin + cnt / 2;
+            std::nth_element(order.begin() + t.begin, order.begin() + mid, order.begin() + t.end,
+                             [&](int a, int b) { return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis]; });
+        }
         const int left = (int)(c->bvh_nodes.size() / 2);
         c->bvh_nodes.resize(c->bvh_nodes.size() + 4);
         const int zero = 0;
         memcpy(&c->bvh_nodes[2 * t.node].w, &left, 4);
         memcpy(&c->bvh_nodes[2 * t.node + 1].w, &zero, 4);
-        todo.push_back({left, t.begin, mid});
-        todo.push_back({left + 1, mid, t.end});
+        todo.push_back({left, t.begin, mid, t.depth + 1});
+        todo.push_back({left + 1, mid, t.end, t.depth + 1});
     }
     c->n_nodes = (int)(c->bvh_nodes.size() / 2);
 }
