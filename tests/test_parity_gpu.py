@@ -254,6 +254,21 @@ def test_frame_pipelining_modes(ptb, oracle, env256, camera, overlap):
     pt.Dispose()
 
 
+def test_progressive_accumulation_to_1024_spp(ptb, oracle, env256, default_scene, camera):
+    """BASELINE config 2's protocol (frames 0..1023 at SPP 1, running mean) at reduced size: after 1024 pipelined frames the
+    accumulation image still equals the oracle's bit for bit — per-channel MSE exactly 0 (the north star asks for < 1e-6)."""
+    W, H = 96, 54
+    pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+    pt.Render(1024)
+    got = pt.Result
+    ref = oracle_render(oracle, ptb.scene, default_scene, camera, env256, W, H, 1024)
+    assert pt.Samples == 1024
+    assert_same(got, ref, "1024-spp accumulation")
+    assert float(((got[..., :3].astype(np.float64) - ref[..., :3]) ** 2).mean()) == 0.0
+    assert np.isfinite(got).all()
+    pt.Dispose()
+
+
 def test_golden_image(ptb, default_scene, camera):
     env16 = np.load(os.path.join(GOLD, "env16.npy"))
     pt = make_tracer(ptb, env16, 64, 64, default_scene, camera)
