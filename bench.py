@@ -187,6 +187,10 @@ def run_ours(args, rank, world, local_rank):
     scene, cam = sc.load_default_scene(), sc.default_camera()
     pt = ptb200.PathTracer(None, W, H, RAY_DEPTH, SPP, FOCAL, APERTURE, device=local_rank)
     pt.SetStream(torch.cuda.current_stream(dev).cuda_stream)
+    # frames in flight: 2 on one GPU (a third starves the read-back snapshot of SM slots and costs e2e), 3 when the frame is
+    # split over several GPUs (small per-GPU tiles are dominated by the per-frame tail; measured at N = 8: 22.1 -> 25.7 Gsamples/s)
+    frames_in_flight = int(os.environ.get("PTB_OVERLAP", "3" if world > 1 else "2"))
+    pt.SetOverlap(frames_in_flight)
     pt.GenerateAtmosphere(256, 50, 15, 0.5, 15.0)      # the default EnvironmentMap, produced on the GPU (MainWindow.cs:174-175)
     pt.LoadScene(scene)
     pt.SetCamera(cam)
@@ -342,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
     pt.Render(3); pt.Synchronize()
     pt.Render(20)
     kern_ms = pt.LastRenderMs() / 20
-    pt.SetOverlap(2)
+    pt.SetOverlap(frames_in_flight)
     if world > 1:
         t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -360,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "flushed every step by a 160 MiB memset (> 126 MB L2) on a concurrent stream, inside the timed region",
                    "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + ("exchange fused into the blend kernel: peer stores into rank 0's image over NVLink (CUDA IPC), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render") if world > 1 else "single GPU, no collective",
-                   "kernel": "persistent megakernel (ptb::megakernel) + blend kernel per frame, 2 frames in flight (ptb_set_overlap)"},
+                   "kernel": f"persistent megakernel (ptb::megakernel) + blend kernel per frame, {frames_in_flight} frames in flight (ptb_set_overlap)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "ptb::megakernel<false>",
                      "kernel_ms": kern_ms, "kernel_timing": "megakernel alone, in-place mode (ptb_set_overlap(1)), 20 launches back to back, CUDA events", "algorithmic_bytes_per_launch": algo_bytes,
