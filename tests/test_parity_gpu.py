@@ -561,3 +561,59 @@ def test_srgb8_skybox_environment(ptb, oracle, default_scene, camera):
     ref = oracle_render(oracle, ptb.scene, default_scene, camera, lin, 96, 64, 2)
     assert_same(pt.Result, ref, "render with the sRGB skybox")
     pt.Dispose()
+
+
+# ------------------------------------------------------------------------------- outputs of the reference's own shaders
+# tests/golden/ref_*.npz come from the reference's GLSL compiled for the CPU (oracle/build_ref.py; generator
+# tests/golden/make_ref_golden.py).  The CUDA path is driven with the stored input BYTES through the two SubData entry
+# points, exactly as the C# host would, and must reproduce the stored images bit for bit.
+def _tracer_from_bytes(ptb, env, W, H, basic, ubo, ns, nc, **kw):
+    pt = ptb.PathTracer(env, W, H, kw["depth"], kw["spp"], kw["focal"], kw["aperture"])
+    pt.BasicDataUBO.SubData(0, len(basic), basic)
+    pt.GameObjectsUBO.SubData(0, len(ubo), ubo)
+    pt.NumSpheres, pt.NumCuboids = ns, nc
+    return pt
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["megakernel", "gl-proxy"])
+def test_reference_golden_default_scene(ptb, kernel):
+    g = np.load(os.path.join(GOLD, "ref_pt_default.npz"))
+    n, H, W, _ = g["after_frame"].shape
+    pt = _tracer_from_bytes(ptb, g["env"], W, H, g["basic_ubo"].tobytes(), g["objects_ubo"].tobytes(), 48, 7,
+                            depth=13, spp=2, focal=20.0, aperture=0.14)
+    pt.SetKernel(kernel)
+    for f in range(n):
+        pt.Render()
+        assert_same(pt.Result, g["after_frame"][f], f"reference golden, default scene, frame {f}")
+    pt.Dispose()
+
+
+def test_reference_golden_synthetic_scene(ptb):
+    g = np.load(os.path.join(GOLD, "ref_pt_synthetic.npz"))
+    env = np.load(os.path.join(GOLD, "ref_pt_default.npz"))["env"]
+    n, H, W, _ = g["after_frame"].shape
+    pt = _tracer_from_bytes(ptb, env, W, H, g["basic_ubo"].tobytes(), g["objects_ubo"].tobytes(), 256, 64,
+                            depth=8, spp=1, focal=8.0, aperture=0.4)            # 320 primitives: the BVH fold
+    pt.WriteResult(np.zeros((H, W, 4), np.float32))
+    pt.SetFrame(5)
+    for k in range(n):
+        pt.Render()
+        assert_same(pt.Result, g["after_frame"][k], f"reference golden, synthetic scene, frame {5 + k}")
+    pt.Dispose()
+
+
+def test_reference_golden_atmosphere_and_post(ptb):
+    g = np.load(os.path.join(GOLD, "ref_atmosphere.npz"))
+    pt = ptb.PathTracer(None, 32, 24, 13, 1, 20.0, 0.14)
+    pt.GenerateAtmosphere(16, 8, 4, 0.5, 15.0)
+    assert_same(pt.ReadEnvironment(), g["faces_a"], "reference golden, atmosphere 16")
+    pt.GenerateAtmosphere(12, 6, 3, 0.2, 22.0)
+    assert_same(pt.ReadEnvironment(), g["faces_b"], "reference golden, atmosphere 12")
+    p = np.load(os.path.join(GOLD, "ref_post.npz"))
+    pt.WriteResult(p["ramp"])
+    assert (ptb.ScreenEffect().Render(pt) == p["ramp_rgba8"]).all()
+    final = np.load(os.path.join(GOLD, "ref_pt_default.npz"))["after_frame"][-1]
+    pt.SetSize(final.shape[1], final.shape[0])
+    pt.WriteResult(final)
+    assert (ptb.ScreenEffect().Render(pt) == p["rendered"]).all()
+    pt.Dispose()

@@ -1,0 +1,294 @@
+"""Pins the hand-written oracle (oracle/pt_oracle.c, atmosphere_oracle.c) against THE REFERENCE ITSELF: the reference's
+three GLSL shaders compiled for the CPU from where they lie under /root/reference (oracle/build_ref.py +
+oracle/glsl_shim.hpp -> oracle/_ref/libglsl_ref.so).  Bar: bit-exact float32 / uint8, 0 ulp (any NaN == any NaN).
+
+What this proves: every structural decision of the restatement — draw order of the RNG, which operand goes where, the
+order-dependent closest-hit fold, Beer / emission / albedo / Russian-roulette order, std140 field offsets, the atmosphere
+integrator, the ACES + sRGB pass — is what the reference's source text says, under the one evaluation model of
+oracle/glsl_model.h.  (What it cannot prove: that a particular GL driver rounds a division or a sin() like the model does —
+GLSL leaves that open)
+
+Runs wherever oracle/_ref/libglsl_ref.so exists: here (built on demand while /root/reference is mounted) and on the GPU
+box (the binary travels with the snapshot).  Nothing reads /root/reference at test time except the optional staleness
+check, which is skipped when the directory is absent.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import f32_same
+
+REFERENCE = "/root/reference"
+
+
+@pytest.fixture(scope="session")
+def ref():
+    from oracle import ref as R
+    if not R.available() and os.path.isdir(REFERENCE):
+        from oracle import build_ref
+        build_ref.build(REFERENCE)
+    if not R.available():
+        pytest.skip("oracle/_ref/libglsl_ref.so not built (needs /root/reference once: python oracle/build_ref.py)")
+    return R
+
+
+def _same_images(a, b, what):
+    bad = ~f32_same(a, b)
+    assert not bad.any(), f"{what}: {int(bad.any(axis=-1).sum())} differing pixels; first at {np.argwhere(bad)[0].tolist()}"
+
+
+def _render_both(O, R, image_o, image_r, basic, ubo, env, **kw):
+    O.render(image_o, basic, ubo, env, **kw)
+    R.render(image_r, basic, ubo, env, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ the build recipe itself
+def test_translation_rules():
+    """The lexical rewrites, on snippets written here (no reference text needed)."""
+    from oracle.build_ref import translate
+    t = translate("#version 450 core\nuniform float k;\nfloat f(inout vec3 v, out float o) { o = 2.0 * v.xyz.x / 3e2; return vec3(1, 2.5, 0).x; }\n", "t")
+    assert "#version" not in t
+    assert "GLSL_UNIFORM Float k;" in t
+    assert "vec3& v" in t and "Float& o" in t
+    assert "Float(2.0f)" in t and "Float(3e2f)" in t
+    assert ".xyz().x" in t
+    assert "vec3{1, Float(2.5f), 0}" in t
+    t = translate("layout(std140, binding = 1) uniform Blk\n{\n mat4[6] M;\n} blk;\nuint seed;\nvoid main() { }\n", "t")
+    assert "struct Blk" in t and "mat4 M[6];" in t and "thread_local uint seed;" in t and "void glsl_main()" in t
+    # R11's safety net: an argument list whose evaluation order C++ would not fix must be refused, not guessed
+    with pytest.raises(RuntimeError):
+        translate("float g(float a, float b);\nvoid main() { float x = g(GetRandomFloat01(), GetRandomFloat01()); }\n", "t")
+    with pytest.raises(RuntimeError):
+        translate("void main() { float x = GetRandomFloat01() - GetRandomFloat01(); }\n", "t")
+    # ... while the constructor form the reference uses is accepted (braces order it)
+    assert "vec2{GetRandomFloat01(), GetRandomFloat01()}" in translate("void main() { vec2 o = vec2(GetRandomFloat01(), GetRandomFloat01()); }\n", "t")
+
+
+def test_manifest_matches_the_mounted_reference(ref):
+    m = ref.manifest()
+    assert set(m["built_from"]) == {"pt", "atmosphere", "post"}
+    assert m["built_from"]["pt"]["path"].endswith("res/shaders/PathTracing/compute.glsl")
+    if os.path.isdir(REFERENCE):
+        import hashlib
+        for k, v in m["built_from"].items():
+            with open(os.path.join(REFERENCE, v["path"]), "rb") as f:
+                assert hashlib.sha256(f.read()).hexdigest() == v["sha256"], f"oracle/_ref is stale for {k}: rebuild"
+    assert ref.capacity() == (256, 64)          # compute.glsl:69-70
+
+
+# ------------------------------------------------------------------------------------------------ unit level
+def test_pcg_stream(ref, oracle):
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pcg_kats.json")))
+    for k in gold:                                   # Python-integer KATs -> the compiled shader's GetPCGHash / GetRandomFloat01
+        h, f = ref.pcg_stream(k["seed"], 8)
+        assert [f"{int(v):08x}" for v in h] == k["hashes"]
+        assert [int(v) for v in f.view(np.uint32)] == k["floats_hex"]
+    for s in (1, 0xFFFFFFFF, 12345 | 1, 0x80000001):
+        ho, fo = oracle.pcg_stream(s, 4096)
+        hr, fr = ref.pcg_stream(s, 4096)
+        assert (ho == hr).all() and (fo.view(np.uint32) == fr.view(np.uint32)).all()
+
+
+def test_closest_hit_fold(ref, oracle, default_scene):
+    """RayTrace() of the compiled shader vs the restatement: hit flag, T, FromInside, position, normal, material."""
+    rng = np.random.default_rng(11)
+    n = 120000
+    o = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.array([40, 25, 25], np.float32) + np.array([0, 0, -10], np.float32)
+    o[:20000] = default_scene.spheres[40].Position + (rng.random((20000, 3)).astype(np.float32) - np.float32(0.5)) * np.float32(1.5)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[:200, 0] = 0                                   # axis-parallel: infinite slabs, 0 * inf
+    d[200:300] = 0                                   # zero direction
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    ubo = default_scene.ubo_bytes()
+    for ns, nc in ((48, 7), (48, 0), (0, 7), (13.5, 2.25), (0, 0)):     # the counts are FLOATS in the shader (compute.glsl:88)
+        a = oracle.ray_trace(rays, ubo, 256, ns, nc)
+        b = ref.ray_trace(rays, ubo, 256, ns, nc)
+        hit = a[:, 0] == 1
+        assert (a[:, 0] == b[:, 0]).all()
+        _same_images(a[hit], b[hit], f"RayTrace counts=({ns},{nc})")
+    assert oracle.ray_trace(rays, ubo, 256, 48, 7)[:, 2].sum() > 3000      # plenty of rays start inside a primitive
+
+
+def test_closest_hit_fold_adversarial_geometry(ref, oracle):
+    """Overlapping, nested, degenerate, inverted and non-finite primitives: the fold is order dependent."""
+    rng = np.random.default_rng(12)
+    ubo = np.zeros((80 * 256 + 96 * 64) // 4, np.float32)
+    sph = ubo[:256 * 20].reshape(256, 20)
+    cub = ubo[256 * 20:].reshape(64, 24)
+    sph[:, :3] = rng.standard_normal((256, 3)) * 2
+    sph[:, 3] = rng.random(256) * 3                  # heavily overlapping
+    sph[5, 3] = 0; sph[6, 3] = -1.5; sph[7, 3] = np.nan; sph[8, 0] = np.inf; sph[9, 3] = np.inf; sph[10, 3] = 1e-30
+    sph[:, 4] = np.arange(256)                       # Albedo.x identifies the winner
+    lo = rng.standard_normal((64, 3)) * 2
+    cub[:, 0:3] = lo
+    cub[:, 4:7] = lo + rng.random((64, 3)) * 3
+    cub[3, 4:7] = cub[3, 0:3]                        # zero volume
+    cub[4, 0:3], cub[4, 4:7] = cub[4, 4:7].copy(), cub[4, 0:3].copy()   # inverted
+    cub[5, 0] = np.nan; cub[6, 4] = np.inf; cub[7, 0] = -np.inf
+    cub[:, 8] = 1000 + np.arange(64)
+    n = 60000
+    o = (rng.standard_normal((n, 3)) * 2.5).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[:300, rng.integers(0, 3)] = 0
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    a = oracle.ray_trace(rays, ubo.tobytes(), 256, 256, 64)
+    b = ref.ray_trace(rays, ubo.tobytes(), 256, 256, 64)
+    assert (a[:, 0] == b[:, 0]).all()
+    hit = a[:, 0] == 1
+    assert hit.sum() > n // 2
+    _same_images(a[hit], b[hit], "RayTrace, adversarial geometry")
+
+
+def test_texture_unit_independent_implementations_agree(ref, oracle):
+    """The cubemap lookup is GL, not shader code, so both sides had to write one: pt_oracle.c walks an integer lattice per
+    tap, glsl_shim.hpp pre-pads each face through its Table 8.19 frame.  Written independently; must agree bitwise."""
+    rng = np.random.default_rng(13)
+    dirs = rng.standard_normal((200000, 3)).astype(np.float32)
+    dirs[:6] = np.eye(3, dtype=np.float32).repeat(2, 0) * np.array([1, -1] * 3, np.float32)[:, None]
+    dirs[6:14] = np.array([[sx, sy, sz] for sx in (1, -1) for sy in (1, -1) for sz in (1, -1)], np.float32)
+    e = rng.standard_normal((6000, 3)).astype(np.float32)
+    e[:, 0] = np.sign(e[:, 0]); e[:, 1] = np.sign(e[:, 1])
+    dirs[14:6014] = np.concatenate([e[:2000], e[2000:4000, [1, 2, 0]], e[4000:, [2, 0, 1]]])       # on every kind of edge
+    dirs[6014] = np.nan; dirs[6015] = 0; dirs[6016] = (np.inf, 1, 1); dirs[6017] = (1e-30, -1e-30, 1e-30)
+    for n in (1, 2, 3, 5, 16, 64):
+        env = rng.random((6, n, n, 4)).astype(np.float32)
+        _same_images(oracle.texture_cube(env, dirs), ref.texture_cube(env, dirs), f"texture(samplerCube), N={n}")
+
+
+# ------------------------------------------------------------------------------------------------ whole dispatches
+@pytest.mark.parametrize("W,H,spp,depth,focal,aperture,frames", [
+    (96, 54, 1, 13, 20.0, 0.14, 3),        # the demo's defaults (MainWindow.cs:190)
+    (61, 35, 3, 13, 20.0, 0.14, 2),        # not a multiple of the 8x8 work group
+    (64, 64, 2, 13, 5.0, 0.5, 2),          # wide aperture, near focus (BASELINE config 5's corner)
+    (64, 64, 2, 13, 50.0, 0.0, 2),         # pinhole
+    (64, 36, 2, 1, 20.0, 0.14, 1),         # a single bounce
+    (64, 36, 1, 0, 20.0, 0.14, 1),         # rayDepth 0: nothing traced, radiance 0
+    (48, 27, 1, 40, 20.0, 0.14, 1),        # deep paths
+])
+def test_default_scene_dispatches(ref, oracle, ptb, default_scene, camera, env16, W, H, spp, depth, focal, aperture, frames):
+    sc = ptb.scene
+    basic, ubo = sc.basic_data_bytes(camera, W, H), default_scene.ubo_bytes()
+    io, ir = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    for f in range(frames):
+        _render_both(oracle, ref, io, ir, basic, ubo, env16, frame=f, spp=spp, ray_depth=depth, focal_length=focal,
+                     aperture_diameter=aperture, n_spheres=48, n_cuboids=7)
+        _same_images(io, ir, f"frame {f}")
+    if depth > 0:
+        assert float(io[..., :3].mean()) > 0.01 and (io[..., 3] == 1).all()
+
+
+def test_default_environment_and_late_frames(ref, oracle, ptb, default_scene, camera, env256):
+    """The 256^2 atmosphere cubemap, frame numbers far from 0 (seed term frame * 2699, blend weight 1/(frame+1))."""
+    sc = ptb.scene
+    W, H = 80, 45
+    basic, ubo = sc.basic_data_bytes(camera, W, H), default_scene.ubo_bytes()
+    rng = np.random.default_rng(5)
+    start = rng.random((H, W, 4)).astype(np.float32)
+    for frame in (1, 7, 1023, 100000):
+        io, ir = start.copy(), start.copy()
+        _render_both(oracle, ref, io, ir, basic, ubo, env256, frame=frame, spp=2, ray_depth=13, focal_length=20.0,
+                     aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+        _same_images(io, ir, f"frame {frame}")
+
+
+def test_crops_equal_the_full_dispatch(ref, oracle, ptb, default_scene, camera, env16):
+    """A crop of a 1920x1080 dispatch (BASELINE's resolution) — pixels depend on global coordinates only."""
+    sc = ptb.scene
+    W, H = 1920, 1080
+    basic, ubo = sc.basic_data_bytes(camera, W, H), default_scene.ubo_bytes()
+    io, ir = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    kw = dict(frame=0, spp=1, ray_depth=13, focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7,
+              rows=(500, 560), cols=(900, 1100))
+    _render_both(oracle, ref, io, ir, basic, ubo, env16, **kw)
+    _same_images(io, ir, "1080p crop")
+    assert io[500:560, 900:1100, 3].min() == 1 and io[:500].max() == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_scenes_at_the_shaders_capacity(ref, oracle, ptb, env16, seed):
+    """256 spheres + 64 cuboids with random materials (every BSDF lobe, absorbing media, emitters), random cameras —
+    including cameras inside glass — and partial / fractional object counts."""
+    sc = ptb.scene
+    scene = sc.synthetic_scene(256, 64, seed=seed)
+    rng = np.random.default_rng(100 + seed)
+    W, H = 56, 32
+    for trial in range(3):
+        cam = sc.default_camera()
+        if trial == 1:
+            cam.Position = np.asarray(scene.spheres[int(rng.integers(0, 256))].Position, np.float32).copy()   # inside a sphere
+        elif trial == 2:
+            cam.Position = (np.asarray(cam.Position, np.float32) + rng.standard_normal(3).astype(np.float32) * 3).astype(np.float32)
+        basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+        ns, nc = [(256, 64), (200.5, 10), (17, 64)][trial]
+        io, ir = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+        for f in range(2):
+            _render_both(oracle, ref, io, ir, basic, ubo, env16, frame=f, spp=2, ray_depth=8, focal_length=float(rng.uniform(1, 50)),
+                         aperture_diameter=float(rng.uniform(0, 0.5)), n_spheres=ns, n_cuboids=nc, max_spheres=256)
+            _same_images(io, ir, f"seed {seed} trial {trial} frame {f}")
+
+
+def test_unclamped_materials(ref, oracle, ptb, env16, camera):
+    """Material fields written past the constructor's clamps (Material.cs:26-29 clamps only in `new Material`): chances
+    above 1 and below 0, IOR below 1, negative roughness and albedo, zero-roughness glass (total internal reflection ->
+    refract() returns 0 -> normalize(0) = NaN -> texture(NaN)), huge emitters."""
+    sc = ptb.scene
+    scene = sc.load_default_scene()
+    rng = np.random.default_rng(21)
+    raw = np.frombuffer(scene.ubo_bytes(), np.float32).copy()
+    sph = raw[:256 * 20].reshape(256, 20)
+    for i in range(48):
+        sph[i, 4:7] = rng.uniform(-0.2, 1.5, 3)          # Albedo
+        sph[i, 7] = rng.uniform(-0.5, 1.5)               # SpecularChance
+        sph[i, 8:11] = rng.uniform(0, 3, 3) * (rng.random() < 0.2)
+        sph[i, 11] = rng.uniform(-0.3, 1.2)              # SpecularRoughness
+        sph[i, 12:15] = rng.uniform(-1, 4, 3)            # Absorbance
+        sph[i, 15] = rng.uniform(-0.5, 1.5)              # RefractionChance
+        sph[i, 16] = rng.choice([0.0, 0.0, rng.uniform(-0.2, 1.0)])   # RefractionRoughness
+        sph[i, 17] = rng.uniform(0.3, 2.5)               # IOR
+    W, H = 64, 36
+    basic, ubo = sc.basic_data_bytes(camera, W, H), raw.tobytes()
+    io, ir = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    for f in range(3):
+        _render_both(oracle, ref, io, ir, basic, ubo, env16, frame=f, spp=4, ray_depth=13, focal_length=20.0,
+                     aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+        _same_images(io, ir, f"unclamped materials, frame {f}")
+
+
+# ------------------------------------------------------------------------------------------------ the other two shaders
+@pytest.mark.parametrize("size,isteps,jsteps,time,intensity", [(16, 8, 4, 0.5, 15.0), (20, 5, 3, 0.1, 15.0), (33, 6, 2, 0.3, 40.0), (8, 50, 15, 0.5, 15.0)])
+def test_atmosphere_shader(ref, oracle, ptb, size, isteps, jsteps, time, intensity):
+    sc = ptb.scene
+    ubo, lp = sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(time)
+    a = oracle.atmosphere(size, ubo, lp, intensity, isteps, jsteps)
+    b = ref.atmosphere(size, ubo, lp, intensity, isteps, jsteps)
+    _same_images(a, b, f"atmosphere {size}")
+    assert float(a[..., :3].max()) > 0
+
+
+def test_post_process_shader(ref, oracle):
+    rng = np.random.default_rng(31)
+    img = (rng.random((40, 64, 4)).astype(np.float32) * 10.0 ** rng.integers(-6, 3, (40, 64, 1))).astype(np.float32)
+    img[0, :8, 0] = [0.0, -0.0, -1.0, np.nan, np.inf, -np.inf, 1e-30, 0.0031308]
+    img[1, :4, 1] = [0.0031307, 0.0031309, 1.0, 1e30]
+    a, b = oracle.tonemap(img), ref.post(img)
+    assert a.dtype == np.uint8 and (a == b).all(), f"{int((a != b).sum())} differing bytes"
+    assert (a[..., 3] == 255).all() and a[..., :3].max() == 255 and a[..., :3].min() == 0
+
+
+# ------------------------------------------------------------------------------------------------ committed reference outputs
+def test_committed_reference_goldens_are_reproduced(ref):
+    """tests/golden/ref_*.npz were written by tests/golden/make_ref_golden.py from the compiled reference shaders; the
+    binary at hand must still reproduce them (guards against a silently different rebuild)."""
+    from golden import make_ref_golden as G
+    for name, arrays in G.generate(ref).items():
+        stored = np.load(os.path.join(G.HERE, name))
+        for k, v in arrays.items():
+            assert stored[k].dtype == v.dtype and stored[k].shape == v.shape
+            if v.dtype == np.float32:
+                assert f32_same(stored[k], v).all(), f"{name}:{k}"
+            else:
+                assert (stored[k] == v).all(), f"{name}:{k}"
