@@ -12,8 +12,10 @@ exchange the path has: a gather of the stripe buffers to rank 0 + de-interleave.
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launching stream, inputs resident in HBM, L2
 flushed before every timed step; `e2e` goes through the same public API with host buffers: the per-frame camera UBO
 upload the C# host does (MainWindow.cs:131-132) and a read-back of the accumulation image into pinned host memory.
-`--impl reference` times the CPU oracle (the reference has no CPU path and cannot run without .NET + OpenGL 4.5; the
-oracle is the restatement of its shader) on all host threads.
+`--impl reference` times the reference's own compute shader on the host CPUs: compute.glsl compiled by g++ from
+/root/reference through oracle/build_ref.py (oracle/_ref/libglsl_ref.so, kind "reference"), all host threads; where that
+binary is absent it falls back to the oracle's C restatement (kind "port").  The reference's C# + OpenGL host cannot run
+here (no .NET, no GL).
 """
 import argparse
 import json
@@ -130,14 +132,24 @@ def physical_gpu_index(local_rank):
 
 
 # ================================================================================================ reference arm
+def cpu_reference():
+    """(module, kind, description): the compiled reference shaders when oracle/_ref was built, else the oracle port."""
+    from oracle import oracle as O, ref as R
+    if R.available():
+        return R, "reference", "the reference's compute.glsl compiled for the CPU (g++, oracle/build_ref.py -> oracle/_ref/libglsl_ref.so); its C# + OpenGL host needs .NET + GL 4.5, absent here"
+    return O, "port", "CPU oracle (C restatement of compute.glsl); oracle/_ref not built on this machine"
+
+
 def run_reference(args, rank, world):
-    """The reference's algorithm on the host CPUs: the oracle (kind "port"), all threads, a bounded sample per step."""
+    """The reference's shader on the host CPUs (oracle/_ref, kind "reference"; else the oracle, kind "port"), all threads,
+    a bounded sample per step."""
     if rank != 0:
         return
     import ptb200
-    from oracle import oracle as O
+    from oracle import oracle as O_
+    O, kind, kind_text = cpu_reference()
     sc = ptb200.scene
-    threads = O.max_threads()
+    threads = O_.max_threads()
     env = O.atmosphere(256, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 50, 15)
     scene, cam = sc.load_default_scene(), sc.default_camera()
     basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
@@ -166,8 +178,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference_kind": "CPU oracle (C restatement of compute.glsl); the reference itself needs .NET + OpenGL 4.5, absent here"},
-            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "reference_kind": kind_text},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -389,9 +401,11 @@ def run_ours(args, rank, world, local_rank):
 
 
 def cpu_baseline(pt):
-    """The oracle on this box's host cores, a bounded sample of the same workload (rank 0, N = 1 only)."""
+    """The compiled reference shader (else the oracle port) on this box's host cores, a bounded sample of the same
+    workload (rank 0, N = 1 only)."""
     import ptb200
-    from oracle import oracle as O
+    from oracle import oracle as O_
+    O, kind, _ = cpu_reference()
     sc = ptb200.scene
     env = pt.ReadEnvironment()
     scene, cam = sc.load_default_scene(), sc.default_camera()
@@ -404,7 +418,7 @@ def cpu_baseline(pt):
         frames += 1
         O.render(img, basic, ubo, env, frame=frames, **kw)
     dt = time.perf_counter() - t0
-    return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": O.max_threads(), "kind": "port",
+    return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": O_.max_threads(), "kind": kind,
             "sample": f"{frames} full 1920x1080 frames at SPP 1 ({dt:.1f} s), OpenMP over rows"}
 
 
