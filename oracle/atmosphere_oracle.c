@@ -2,7 +2,8 @@
  * oracle/atmosphere_oracle.c — TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's
  * atmosphere cubemap producer, /root/reference/OpenTK-PathTracer/res/shaders/AtmosphericScattering/compute.glsl
  * (cited as atmos:LINE) driven as AtmosphericScatterer.cs:63-113 drives it.  Arithmetic per glsl_model.h.
- * PARITY UNPINNED (no reference tests / vectors exist).
+ * PARITY PIN: bit-exact against the same shader compiled for the CPU from /root/reference (oracle/build_ref.py,
+ * tests/test_reference_pin.py::test_atmosphere_shader, tests/golden/ref_atmosphere.npz).
  */
 #include "glsl_model.h"
 #ifdef _OPENMP

@@ -45,6 +45,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "libglsl_ref.so")
+LIB_ALT = os.path.join(OUT_DIR, "libglsl_ref_alt.so")
 MANIFEST = os.path.join(OUT_DIR, "manifest.json")
 
 SHADERS = {
@@ -173,8 +174,13 @@ def shader_paths(reference: str) -> dict[str, str]:
     return {k: os.path.join(base, v[0]) for k, v in SHADERS.items()}
 
 
-def build(reference: str = "/root/reference", keep: bool = False, verbose: bool = False) -> str:
+def build(reference: str = "/root/reference", keep: bool = False, verbose: bool = False, alt_model: bool = False) -> str:
+    """alt_model=True builds oracle/_ref/libglsl_ref_alt.so instead: the same shaders under a second admissible evaluation
+    model (IEEE division, libm transcendentals, nothing fused) — a measuring instrument for tools/model_sensitivity.py,
+    never a parity reference."""
     paths = shader_paths(reference)
+    lib_out = LIB_ALT if alt_model else LIB
+    flags = CXXFLAGS + (["-DGLSL_SHIM_ALT_MODEL"] if alt_model else [])
     for p in paths.values():
         if not os.path.exists(p):
             raise FileNotFoundError(p)
@@ -196,12 +202,14 @@ def build(reference: str = "/root/reference", keep: bool = False, verbose: bool 
                         "}}\n"
                         f'#include "{harness}"\n')
             obj = os.path.join(tmp, f"{key}.o")
-            cmd = [CXX, *CXXFLAGS, "-I", HERE, "-c", tu, "-o", obj]
+            cmd = [CXX, *flags, "-I", HERE, "-c", tu, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
             objs.append(obj)
-        subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB, *objs], check=True)
+        subprocess.run([CXX, "-shared", "-fopenmp", "-o", lib_out, *objs, "-lm"], check=True)
+        if alt_model:
+            return lib_out
         manifest = {
             "built_from": {k: {"path": os.path.relpath(p, reference), "sha256": _sha256(p)} for k, p in paths.items()},
             "shim": {n: _sha256(os.path.join(HERE, n)) for n in
@@ -216,7 +224,7 @@ def build(reference: str = "/root/reference", keep: bool = False, verbose: bool 
             print(f"translated text kept in {tmp}", file=sys.stderr)
         else:
             shutil.rmtree(tmp, ignore_errors=True)
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":
@@ -224,5 +232,6 @@ if __name__ == "__main__":
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--keep", action="store_true", help="leave the translated text in its /tmp directory")
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--alt-model", action="store_true", help="build libglsl_ref_alt.so (second evaluation model, for tools/model_sensitivity.py)")
     a = ap.parse_args()
-    print(build(a.reference, a.keep, a.verbose))
+    print(build(a.reference, a.keep, a.verbose, a.alt_model))

@@ -26,9 +26,16 @@
  *   step, sign, abs    GLSL definitions
  *   sin, cos, exp      the fixed polynomial algorithms below
  *   float(uint)        RNE;  f2i = truncation, NaN -> 0, saturating
- * PARITY UNPINNED: the reference has no tests, fixtures or golden vectors for
- * this path and cannot run here; the pins are the integer
- * KATs in tests/golden/ derived from compute.glsl:106,334-344.
+ * PARITY PIN: the reference has no tests, fixtures or golden vectors for this
+ * path and its C# + OpenGL host cannot run here, but its
+ * SHADERS can: oracle/build_ref.py compiles the three GLSL files from
+ * /root/reference with g++ against oracle/glsl_shim.hpp (which evaluates GLSL
+ * operators and built-ins with the scalar primitives of THIS header) into
+ * oracle/_ref/libglsl_ref.so.  tests/test_reference_pin.py holds the hand-written
+ * restatement (pt_oracle.c, atmosphere_oracle.c) to that library bit for bit, and
+ * tests/golden/ref_*.npz are its outputs.  So the algorithm is pinned to the
+ * reference's source text; what remains a choice is this header — how a GL
+ * driver would round `/`, sin, cos, exp, pow and filter a cubemap.
  */
 #ifndef PTO_GLSL_MODEL_H
 #define PTO_GLSL_MODEL_H

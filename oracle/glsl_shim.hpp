@@ -54,7 +54,14 @@ struct Float {
 inline Float operator+(Float a, Float b) { return Float(a.v + b.v); }
 inline Float operator-(Float a, Float b) { return Float(a.v - b.v); }
 inline Float operator*(Float a, Float b) { return Float(a.v * b.v); }
+#ifdef GLSL_SHIM_ALT_MODEL
+/* A second, equally admissible evaluation model, used ONLY by tools/model_sensitivity.py to measure how much of the image
+ * depends on the choice: IEEE-correct division, libm sinf / cosf / expf / powf, unfused dot / mix / mat*vec. */
+extern "C" { float sinf(float); float cosf(float); float expf(float); float powf(float, float); }
+inline Float operator/(Float a, Float b) { return Float(a.v / b.v); }
+#else
 inline Float operator/(Float a, Float b) { return Float(gm::g_div(a.v, b.v)); }
+#endif
 inline Float operator-(Float a) { return Float(-a.v); }
 inline Float &operator+=(Float &a, Float b) { a = a + b; return a; }
 inline Float &operator-=(Float &a, Float b) { a = a - b; return a; }
@@ -154,22 +161,36 @@ GLSL_SHIM_COMPOUND(vec2) GLSL_SHIM_COMPOUND(vec3) GLSL_SHIM_COMPOUND(vec4)
 inline Float abs(Float a) { return gm::g_abs(a.v); }
 inline Float sign(Float a) { return gm::g_sign(a.v); }
 inline Float sqrt(Float a) { return gm::g_sqrt(a.v); }
+#ifdef GLSL_SHIM_ALT_MODEL
+inline Float sin(Float a) { return ::glsl::sinf(a.v); }
+inline Float cos(Float a) { return ::glsl::cosf(a.v); }
+inline Float exp(Float a) { return ::glsl::expf(a.v); }
+#else
 inline Float sin(Float a) { return gm::g_sin(a.v); }
 inline Float cos(Float a) { return gm::g_cos(a.v); }
 inline Float exp(Float a) { return gm::g_exp(a.v); }
+#endif
 inline Float min(Float a, Float b) { return gm::g_min(a.v, b.v); }
 inline Float max(Float a, Float b) { return gm::g_max(a.v, b.v); }
 inline Float step(Float edge, Float x) { return gm::g_step(edge.v, x.v); }
+#ifdef GLSL_SHIM_ALT_MODEL
+inline Float fma_(Float a, Float b, Float c) { return a * b + c; }
+#else
 inline Float fma_(Float a, Float b, Float c) { return gm::g_fma(a.v, b.v, c.v); }
+#endif
 /* mix(x, y, a) = x*(1-a) + y*a, the y*a product fused into the sum */
 inline Float mix(Float x, Float y, Float a) { return fma_(y, a, x * (Float(1.0f) - a)); }
 inline Float clamp(Float x, Float lo, Float hi) { return min(max(x, lo), hi); }
 /* pow with the constant exponents the shaders use is strength-reduced as the model states; otherwise exp(y*log(x)). */
 inline Float pow(Float x, Float y)
 {
+#ifdef GLSL_SHIM_ALT_MODEL
+    return ::glsl::powf(x.v, y.v);
+#else
     if (y.v == 5.0f) { Float x2 = x * x; Float x4 = x2 * x2; return x4 * x; }
     if (y.v == 1.5f) return x * sqrt(x);
     return gm::g_exp((y * Float(gm::g_log(x.v))).v);
+#endif
 }
 
 inline vec3 exp(const vec3 &a) { return vec3(exp(a.x), exp(a.y), exp(a.z)); }

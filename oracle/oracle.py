@@ -1,6 +1,6 @@
 """ctypes loader for the CPU oracle (oracle/libpt_oracle.so).  TEST INFRASTRUCTURE ONLY:
 imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never by the product.
-PARITY UNPINNED: see oracle/glsl_model.h.
+Parity pin: oracle/ref.py (the reference's shaders compiled for the CPU) and tests/test_reference_pin.py; see oracle/glsl_model.h.
 """
 from __future__ import annotations
 

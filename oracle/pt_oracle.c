@@ -4,8 +4,11 @@
  * All citations are /root/reference/OpenTK-PathTracer/res/shaders/PathTracing/compute.glsl:LINE
  * unless another file is named.  Arithmetic follows oracle/glsl_model.h.
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this path and cannot
- * be executed in this environment (no .NET, no OpenGL); see SURVEY.md §8c and DESIGN.md.
+ * PARITY PIN: the reference ships no tests / golden vectors for this path, so this file is pinned
+ * against the reference's own shader instead: compute.glsl compiled for the CPU from /root/reference
+ * (oracle/build_ref.py -> oracle/_ref/libglsl_ref.so) must agree with it bit for bit on whole
+ * dispatches, RayTrace() probes, the RNG stream and the post-process pass
+ * (tests/test_reference_pin.py; committed outputs tests/golden/ref_*.npz).  See DESIGN.md §2.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product never does.

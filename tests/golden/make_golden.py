@@ -6,8 +6,9 @@ pcg_kats.json     integer-exact known answers for the seed (compute.glsl:106) an
 layout_pins.json  byte sizes / offsets the host relies on (Material.cs:9, Sphere.cs:8,20, Cuboid.cs:8,21, MainWindow.cs:196,200).
 env16.npy, c1_64x64_f0.npy, c1_64x64_f0_3.npy
                   regression pins of the oracle itself (a 16^2 atmosphere cubemap, and the default scene at 64x64:
-                  frame 0, and the running mean after frames 0..3).  The reference cannot run here (no .NET / GL), so these
-                  are NOT reference outputs: parity with the reference stays "unpinned" (DESIGN.md).
+                  frame 0, and the running mean after frames 0..3).  Written by the oracle; tests/test_reference_pin.py checks
+                  that the compiled reference shaders (oracle/_ref) produce the same files, and the reference's own outputs
+                  are the ref_*.npz files written by make_ref_golden.py.
 Run: python tests/golden/make_golden.py
 """
 import json

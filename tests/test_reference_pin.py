@@ -292,3 +292,18 @@ def test_committed_reference_goldens_are_reproduced(ref):
                 assert f32_same(stored[k], v).all(), f"{name}:{k}"
             else:
                 assert (stored[k] == v).all(), f"{name}:{k}"
+
+
+def test_older_oracle_written_goldens_are_reference_outputs_too(ref, ptb, default_scene, camera):
+    """env16.npy and c1_64x64_*.npy were written by the oracle (make_golden.py) before oracle/_ref existed."""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sc = ptb.scene
+    env = ref.atmosphere(16, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 8, 4)
+    assert f32_same(env, np.load(os.path.join(gold, "env16.npy"))).all()
+    basic, ubo = sc.basic_data_bytes(camera, 64, 64), default_scene.ubo_bytes()
+    img = np.zeros((64, 64, 4), np.float32)
+    for f in range(4):
+        ref.render(img, basic, ubo, env, frame=f, spp=1, ray_depth=13, focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+        if f == 0:
+            assert f32_same(img, np.load(os.path.join(gold, "c1_64x64_f0.npy"))).all()
+    assert f32_same(img, np.load(os.path.join(gold, "c1_64x64_f0_3.npy"))).all()

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""How much of the image depends on the GLSL evaluation model?  (CPU only; needs oracle/_ref, i.e. /root/reference once.)
+
+GLSL leaves the rounding of `/`, sin, cos, exp, pow and whether a*b+c fuses to the implementation, so "the reference's
+output at a matched seed" is only defined per driver.  This tool runs the reference's own compute shader (compiled for the
+CPU, oracle/build_ref.py) under TWO admissible models — the repo's (oracle/glsl_model.h: a/b = a*rcp(b), fma dot, fixed
+polynomials) and an alternative (IEEE division, libm sinf/cosf/expf/powf, nothing fused; `build_ref.py --alt-model`) — on
+the same seeds and reports
+  * after ONE frame: the fraction of pixels that differ at all, and by more than 1e-3 relative (a different path was taken),
+  * after N accumulated frames: per-channel MSE between the models, next to the MSE between two seed offsets under ONE
+    model (pure Monte-Carlo noise at the same sample count).
+Result (profiles/r01_model_sensitivity.md): ~40 % of pixels differ in some low bit after one frame, ~0.1 % by more than
+1e-3 relative, and the per-channel MSE between the two models at matched seeds is 1e-7..2e-6 — three to five orders of
+magnitude below the seed-to-seed Monte-Carlo noise at the same sample count.  So (a) bit parity exists only under one
+fixed arithmetic, which is why the oracle, the compiled reference and the CUDA kernels share one and are compared at
+0 ulp; (b) the north star's "MSE < 1e-6 vs the GL reference at matched seed" is the right order of magnitude for what a
+real driver's arithmetic would leave, and a matched-seed comparison is far more sensitive than a statistical one.
+"""
+import argparse
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def load_alt():
+    from oracle import build_ref
+    if not os.path.exists(build_ref.LIB_ALT):
+        build_ref.build(alt_model=True)
+    spec = importlib.util.spec_from_file_location("oracle.ref_alt", os.path.join(ROOT, "oracle", "ref.py"))
+    m = importlib.util.module_from_spec(spec)
+    m.__package__ = "oracle"
+    spec.loader.exec_module(m)
+    m.LIB_PATH = build_ref.LIB_ALT
+    return m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=480)
+    ap.add_argument("--height", type=int, default=270)
+    ap.add_argument("--frames", type=int, default=256)
+    a = ap.parse_args()
+    import ptb200
+    from oracle import ref as R
+    A = load_alt()
+    sc = ptb200.scene
+    W, H = a.width, a.height
+    scene, cam = sc.load_default_scene(), sc.default_camera()
+    basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+    env = R.atmosphere(64, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 20, 6)
+    env_alt = A.atmosphere(64, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 20, 6)
+    rel = np.abs(env - env_alt)[..., :3] / np.maximum(np.abs(env[..., :3]), 1e-20)
+    print(f"atmosphere 64^2: {100 * (env.view(np.uint32) != env_alt.view(np.uint32)).any(-1).mean():.1f} % of texels differ, max relative difference {rel.max():.2e}")
+    kw = dict(spp=1, ray_depth=13, focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+
+    def accumulate(M, e, first, n, snaps=()):
+        img = np.zeros((H, W, 4), np.float32)
+        out = {}
+        for k in range(n):
+            # running mean restarted at `first`: frame index drives the seed, the blend weight uses k
+            est = np.zeros((H, W, 4), np.float32)
+            M.render(est, basic, ubo, e, frame=first + k, **{**kw})
+            # frame>0 blends with 1/(frame+1); undo by rendering onto zeros: est = estimate/(frame+1)
+            est[..., :3] *= np.float32(first + k + 1)
+            img[..., :3] += (est[..., :3] - img[..., :3]) / np.float32(k + 1)
+            if k + 1 in snaps:
+                out[k + 1] = img.copy()
+        return out
+
+    snaps = sorted({1, 16, a.frames})
+    m0 = accumulate(R, env, 0, a.frames, snaps)
+    m1 = accumulate(A, env, 0, a.frames, snaps)          # same environment: isolate the integrator
+    n0 = accumulate(R, env, 100000, a.frames, snaps)     # other seeds, same model: the noise floor
+    one, alt = m0[1][..., :3], m1[1][..., :3]
+    differ = (one.view(np.uint32) != alt.view(np.uint32)).any(-1)
+    far = (np.abs(one - alt) > 1e-3 * np.maximum(np.abs(one), 1e-3)).any(-1)
+    print(f"frame 0, {W}x{H}, SPP 1: {100 * differ.mean():.2f} % of pixels differ in some bit, {100 * far.mean():.2f} % by more than 1e-3 relative (another path)")
+    print("| accumulated frames | MSE model A vs model B (same seeds) | MSE seeds vs other seeds (same model) |")
+    print("|---|---|---|")
+    for n in snaps:
+        mse_model = float(((m0[n][..., :3].astype(np.float64) - m1[n][..., :3]) ** 2).mean())
+        mse_noise = float(((m0[n][..., :3].astype(np.float64) - n0[n][..., :3]) ** 2).mean())
+        print(f"| {n} | {mse_model:.3e} | {mse_noise:.3e} |")
+
+
+if __name__ == "__main__":
+    main()
