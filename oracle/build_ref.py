@@ -60,7 +60,7 @@ IMPURE = ("GetPCGHash", "GetRandomFloat01", "CosineSampleHemisphere", "UniformSa
 CXX = "/usr/bin/g++"   # like oracle/Makefile: the system compiler (an env-provided g++ may lack libgomp)
 # same value-preserving flags as oracle/Makefile; -fwrapv: GLSL integer arithmetic wraps
 CXXFLAGS = ["-std=c++17", "-O3", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-fno-math-errno",
-            "-fno-trapping-math", "-mfma", "-fwrapv", "-ftls-model=initial-exec", "-Wall", "-Wno-unused-function", "-Wno-unused-variable",
+            "-fno-trapping-math", "-mfma", "-fwrapv", "-Wall", "-Wno-unused-function", "-Wno-unused-variable",
             "-Wno-misleading-indentation", "-Wno-parentheses"]
 
 _FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
