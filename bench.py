@@ -229,7 +229,20 @@ def run_ours(args, rank, world, local_rank):
     view_pos = np.append(np.asarray(cam.Position, np.float32), np.float32(0)).tobytes()
     rows_local = pt.Result.shape[0]
 
-    host_bufs = [torch.empty((H if rank == 0 else 1, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    # e2e read-back format: RGB32F — the colour floats bit for bit; the alpha the shader stores is the constant 1.0
+    # (compute.glsl:129) and stays on the device.  N = 1: compact pipelined read into pinned memory.  N > 1: every rank writes
+    # its stripes straight into ONE full-frame image in pinned host memory shared by all ranks (each over its own PCIe link);
+    # if that mapping cannot be set up on every rank, the legacy path copies rank 0's assembled RGBA32F image instead.
+    shared = None
+    if world > 1 and os.environ.get("PTB_E2E", "scatter") == "scatter":
+        try:
+            shared = D.SharedHostFrame(W * H * 12, 2, rank, world)
+        except Exception as exc:      # noqa: BLE001  (collective: raised on every rank or on none)
+            if rank == 0:
+                print(f"shared host frame unavailable ({exc}); e2e falls back to rank 0's copy of the assembled image", file=sys.stderr, flush=True)
+            shared = None
+    rgb_e2e = world == 1 or shared is not None
+    host_bufs = [torch.empty((H if rank == 0 else 1, W, 3 if world == 1 else 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     side = torch.cuda.Stream(device=dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
     snap = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1) else None
@@ -254,7 +267,10 @@ def run_ours(args, rank, world, local_rank):
         pt.BasicDataUBO.SubData(128, 16, view_pos)
         if tiled is None:
             pt.Render()
-            pt.ReadResultAsync(host_bufs[i & 1].data_ptr())
+            pt.ReadResultAsync(host_bufs[i & 1].data_ptr(), ptb200.FORMAT_RGB32F)
+        elif shared is not None:
+            tiled.step()           # the device-side exchange keeps running exactly as in the device-timed loop
+            pt.ReadResultScatterAsync(shared.ptr(i), ptb200.FORMAT_RGB32F)
         else:
             if fused:
                 # rank 0 owns the slot between acquire and release: snapshot it (HBM->HBM) there, copy to the host on a side stream
@@ -283,12 +299,18 @@ def run_ours(args, rank, world, local_rank):
     def finish_e2e():
         if tiled is None:
             pt.Synchronize()
+        elif shared is not None:
+            tiled.flush()
+            pt.Synchronize()       # render stream + this rank's copy stream; the closing barrier covers the other ranks
         else:
             full = tiled.flush()
             if rank == 0 and not fused:
                 host_bufs[0].copy_(full, non_blocking=True)
             side.synchronize()
             torch.cuda.current_stream(dev).synchronize()
+
+    def samples_per_step_():
+        return W * H * SPP
 
     def barrier():
         if world > 1:
@@ -352,6 +374,43 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    # outside the timed region: the frame that reached host memory last is the image on the device, bit for bit
+    e2e_verified = None
+    try:
+        if tiled is None:
+            got = host_bufs[state["i"] & 1].numpy()
+            want = pt.Result[..., :3]
+            e2e_verified = bool((got.view(np.uint32) == want.view(np.uint32)).all())
+        elif shared is not None:
+            barrier()
+            if rank == 0:
+                got = shared.view(state["i"], (H, W, 3), torch.float32).numpy()
+                want = tiled.flush()[..., :3].contiguous().cpu().numpy()
+                e2e_verified = bool((got.view(np.uint32) == want.view(np.uint32)).all())
+    except Exception as exc:      # noqa: BLE001
+        e2e_verified = f"check failed to run: {exc}"
+
+    # N = 1: the same end-to-end loop in the other two read-back formats (PCIe is the bound: 16 / 12 / 4 bytes per pixel)
+    e2e_formats = None
+    if tiled is None:
+        e2e_formats = {}
+        alt_buf = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        for name, fmt in (("RGBA32F", ptb200.FORMAT_RGBA32F), ("RGBA8_display", ptb200.FORMAT_RGBA8)):
+            def step_alt(fmt=fmt):
+                pt.BasicDataUBO.SubData(64, 64, inv_view)
+                pt.BasicDataUBO.SubData(128, 16, view_pos)
+                pt.Render()
+                pt.ReadResultAsync(alt_buf.data_ptr(), fmt)
+            for _ in range(3):
+                step_alt()
+            pt.Synchronize()
+            n_alt = max(5, min(args.steps, 100))
+            t0 = time.perf_counter()
+            for _ in range(n_alt):
+                step_alt()
+            pt.Synchronize()
+            e2e_formats[name] = {"value": samples_per_step_() * n_alt / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s",
+                                 "d2h_bytes_per_step": W * H * (16 if fmt == ptb200.FORMAT_RGBA32F else 4)}
 
     # kernel-only duration for the roofline (device time of the megakernel launches alone, max over ranks)
     pt.SetOverlap(1)                 # isolate the megakernel: one stream, no blend kernel, launches back to back
@@ -383,9 +442,15 @@ def run_ours(args, rank, world, local_rank):
                      "note": "the pass is FP32-issue-bound, not HBM-bound: ~3.4k lane-instructions per 32 B of image traffic (DESIGN.md); see issue_*",
                      "issue_active_pct": ncu.get("smsp_issue_active_pct"), "inst_executed_per_launch": ncu.get("inst_executed_per_launch"),
                      "issue": issue_roofline(ncu, kern_ms, world)},
-        "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 80 + 144,
-                "d2h_bytes_per_step": W * H * 16, "steps": e2e_steps,
-                "note": "per step: InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), full RGBA32F image read back to pinned host memory through ptb_read_result_async (snapshot + copy stream, overlapping the next Render()); one sync after the last step, inside the timed region"},
+        "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": (80 + 144) * world,
+                "d2h_bytes_per_step": W * H * (12 if rgb_e2e else 16), "steps": e2e_steps, "format": "RGB32F" if rgb_e2e else "RGBA32F",
+                "last_frame_on_host_equals_device_image": e2e_verified,
+                "note": ("per step: InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), the frame read back to pinned host memory as RGB32F "
+                         "(colour floats bit for bit; the constant alpha 1.0 of compute.glsl:129 is not shipped) through the pipelined read-back (snapshot/pack kernel on the render stream + copy stream, "
+                         "overlapping the next Render()); one sync after the last step, inside the timed region. "
+                         + ("" if world == 1 else ("N > 1: ptb_read_result_scatter_async — every rank writes its stripes into their rows of one full-frame image in pinned host memory shared by all ranks, each over its own PCIe link; the device-side exchange runs as in the device-timed loop"
+                                                   if shared is not None else "N > 1 fallback: rank 0 copies the assembled RGBA32F image")))},
+        "e2e_other_formats": e2e_formats,
         "back_to_back": {"value": samples_per_step * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_b2b / args.steps,
                          "note": "same steps without the concurrent L2 flush"},
         "gpu_launches": launches,
@@ -395,6 +460,9 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baseline(pt)
     if tiled is not None and fused:
         tiled.exchange_ok()
+    if shared is not None:
+        pt.Synchronize()
+        shared.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     pt.Dispose()

@@ -96,6 +96,21 @@ int ptb_read_result(ptb_ctx* ctx, float* rgba32f);            /* synchronous: W*
  * second stream, so the PCIe transfer of frame f overlaps Render() of frame f+1.  Up to two reads in flight; the data is
  * valid after ptb_synchronize(). */
 int ptb_read_result_async(ptb_ctx* ctx, float* pinned_rgba32f);
+/* The same pipelined read-back with the pixel format a host would ask glGetTexImage for (Texture.cs wraps Rgba32f; the
+ * alpha the shader stores is the constant 1.0, compute.glsl:129, so shipping it over PCIe buys nothing):
+ *   PTB_FORMAT_RGBA32F  16 B/pixel, identical to ptb_read_result_async;
+ *   PTB_FORMAT_RGB32F   12 B/pixel, the three colour floats bit for bit, packed (W*H*3 floats);
+ *   PTB_FORMAT_RGBA8     4 B/pixel, the display frame: ScreenEffect's tone-map pass (as ptb_tonemap_rgba8) fused into the snapshot.
+ * The snapshot is a kernel on the render stream; the copy runs on the copy stream.  Valid after ptb_synchronize(). */
+#define PTB_FORMAT_RGBA32F 0
+#define PTB_FORMAT_RGB32F 1
+#define PTB_FORMAT_RGBA8 2
+int ptb_read_result_format_async(ptb_ctx* ctx, int format, void* pinned_dst);
+/* Multi-GPU read-back (after ptb_set_tile): this rank's stripes go straight into THEIR ROWS of one full-frame host image
+ * (`pinned_full_frame` = row 0 of the W x H frame in `format`; typically one shared mapping that every rank registered
+ * with cudaHostRegister), one strided D2H per rank over that GPU's own PCIe link — the host-side frame is assembled
+ * without any device-side exchange.  With world == 1 it equals ptb_read_result_format_async. */
+int ptb_read_result_scatter_async(ptb_ctx* ctx, int format, void* pinned_full_frame);
 int ptb_write_result(ptb_ctx* ctx, const float* rgba32f);     /* restore an accumulation image */
 /* ScreenEffect.Render(PathTracer.Result) — ScreenEffect.cs:29-37 with PostProcessing/fragment.glsl: ACES fit + linear->sRGB
  * into an RGBA8 image (W*H*4 bytes, row 0 = y 0), the step right after the path tracer (MainWindow.cs:51). */

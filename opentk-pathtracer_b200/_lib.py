@@ -41,6 +41,8 @@ SIGNATURES = {
     "ptb_set_frame": (C.c_int, [_P, C.c_int]),
     "ptb_read_result": (C.c_int, [_P, C.c_void_p]),
     "ptb_read_result_async": (C.c_int, [_P, C.c_void_p]),
+    "ptb_read_result_format_async": (C.c_int, [_P, C.c_int, C.c_void_p]),
+    "ptb_read_result_scatter_async": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ptb_write_result": (C.c_int, [_P, C.c_void_p]),
     "ptb_synchronize": (C.c_int, [_P]),
     "ptb_result_device_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

@@ -783,11 +783,19 @@ int ptb_set_frame(ptb_ctx* c, int frame)
     return PTB_OK;
 }
 
-int ptb_read_result_async(ptb_ctx* c, float* dst)
+int ptb_read_result_async(ptb_ctx* c, float* dst) { return ptb_read_result_format_async(c, PTB_FORMAT_RGBA32F, dst); }
+
+// Pipelined read-back, shared by the compact and the scattered form.  The image is accumulated in place, so the next
+// Render() would race with a slow PCIe copy: snapshot it on the render stream (HBM -> HBM; for RGB32F / RGBA8 the snapshot
+// is the packing / tone-map kernel), then let the copy stream move the snapshot to the host while the next frame renders.
+static int read_result_impl(ptb_ctx* c, int format, void* dst, bool scatter)
 {
     if (!c || !dst) return fail(PTB_E_INVALID, "null argument");
+    if (format != PTB_FORMAT_RGBA32F && format != PTB_FORMAT_RGB32F && format != PTB_FORMAT_RGBA8) return fail(PTB_E_INVALID, "unknown read-back format %d", format);
     CU(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)c->local_rows * c->width * sizeof(float4);
+    const size_t n_pixels = (size_t)c->local_rows * c->width;
+    const size_t bpp = format == PTB_FORMAT_RGBA32F ? 16 : (format == PTB_FORMAT_RGB32F ? 12 : 4);
+    const size_t bytes = n_pixels * sizeof(float4);                  // staging buffers hold the largest format
     if (bytes == 0) return PTB_OK;
     if (!c->copy_stream) {
         CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -801,18 +809,44 @@ int ptb_read_result_async(ptb_ctx* c, float* dst)
         for (int i = 0; i < 2; ++i) { if (c->d_stage[i]) CU(cudaFree(c->d_stage[i])); c->d_stage[i] = nullptr; CU(cudaMalloc(&c->d_stage[i], bytes)); }
         c->readback_bytes = bytes;
     }
-    // The image is accumulated in place, so the next Render() would race with a slow PCIe copy: snapshot it on the render
-    // stream (HBM -> HBM), then let the copy stream move the snapshot to the host while the next frame renders.
     const int k = c->stage_next;
     c->stage_next ^= 1;
     CU(cudaStreamWaitEvent(c->stream, c->ev_copied[k], 0));       // the D2H that last used this staging buffer is done
-    CU(cudaMemcpyAsync(c->d_stage[k], c->d_image, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (format == PTB_FORMAT_RGBA32F) {
+        CU(cudaMemcpyAsync(c->d_stage[k], c->d_image, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    } else if (format == PTB_FORMAT_RGB32F) {
+        const size_t quads = (n_pixels + 3) / 4;
+        pack_rgb_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, c->stream>>>(c->d_image, n_pixels, reinterpret_cast<float*>(c->d_stage[k]));
+        c->launches++;
+        CU(cudaGetLastError());
+    } else {
+        tonemap_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, c->stream>>>(c->d_image, n_pixels, reinterpret_cast<uchar4*>(c->d_stage[k]));
+        c->launches++;
+        CU(cudaGetLastError());
+    }
     CU(cudaEventRecord(c->ev_snap[k], c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_snap[k], 0));
-    CU(cudaMemcpyAsync(dst, c->d_stage[k], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(c->d_stage[k]);
+    unsigned char* out = static_cast<unsigned char*>(dst);
+    if (!scatter || c->world == 1) {
+        CU(cudaMemcpyAsync(out, src, n_pixels * bpp, cudaMemcpyDeviceToHost, c->copy_stream));
+    } else {
+        // local stripe j (compact, stripe_rows rows each) is global stripe rank + j * world; only the globally last stripe can be ragged
+        const size_t stripe_bytes = (size_t)c->stripe_rows * c->width * bpp;
+        const size_t n_full = (size_t)c->local_rows / c->stripe_rows;
+        const size_t tail_rows = (size_t)c->local_rows % c->stripe_rows;
+        if (n_full)
+            CU(cudaMemcpy2DAsync(out + (size_t)c->rank * stripe_bytes, (size_t)c->world * stripe_bytes, src, stripe_bytes, stripe_bytes, n_full,
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+        if (tail_rows)
+            CU(cudaMemcpyAsync(out + ((size_t)c->rank + n_full * c->world) * stripe_bytes, src + n_full * stripe_bytes, tail_rows * c->width * bpp,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     CU(cudaEventRecord(c->ev_copied[k], c->copy_stream));
     return PTB_OK;
 }
+int ptb_read_result_format_async(ptb_ctx* c, int format, void* dst) { return read_result_impl(c, format, dst, false); }
+int ptb_read_result_scatter_async(ptb_ctx* c, int format, void* full_frame) { return read_result_impl(c, format, full_frame, true); }
 int ptb_read_result(ptb_ctx* c, float* dst)
 {
     if (!c || !dst) return fail(PTB_E_INVALID, "null argument");

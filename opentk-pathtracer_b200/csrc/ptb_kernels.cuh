@@ -1151,6 +1151,26 @@ __global__ void tonemap_kernel(const float4* __restrict__ image, size_t n, uchar
     const float b = linear_to_inverse_gamma(aces_film(c.z + 0.0f), 2.4f);
     out[i] = make_uchar4((unsigned char)unorm8(r), (unsigned char)unorm8(g), (unsigned char)unorm8(b), 255);
 }
+// Read-back snapshot in RGB32F: drops the constant alpha (pt:129 stores 1.0), colour floats copied bit for bit.
+// One thread per four pixels: four 128-bit loads, three 128-bit stores; the last thread finishes a ragged tail.
+__global__ void pack_rgb_kernel(const float4* __restrict__ image, size_t n, float* __restrict__ out)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = q * 4;
+    if (i >= n) return;
+    if (i + 4 <= n) {
+        const float4 a = image[i], b = image[i + 1], c = image[i + 2], d = image[i + 3];
+        float4* o = reinterpret_cast<float4*>(out + i * 3);
+        o[0] = make_float4(a.x, a.y, a.z, b.x);
+        o[1] = make_float4(b.y, b.z, c.x, c.y);
+        o[2] = make_float4(c.z, d.x, d.y, d.z);
+    } else {
+        for (size_t k = i; k < n; ++k) {
+            const float4 a = image[k];
+            out[k * 3] = a.x; out[k * 3 + 1] = a.y; out[k * 3 + 2] = a.z;
+        }
+    }
+}
 // SURVEY 8f N2 — Srgb8Alpha8 skybox faces (Helper.cs:18-50): sRGB decode before filtering (GL 4.5 8.24), alpha linear.
 __global__ void srgb8_decode_kernel(const uchar4* __restrict__ in, size_t n, float4* __restrict__ out)
 {

@@ -217,3 +217,80 @@ class TiledPathTracer:
         if self.fused:
             return self._last_full
         return self._finish_gather()
+
+
+class SharedHostFrame:
+    """`buffers` full-frame host images in ONE pinned mapping shared by every rank of the node (a /dev/shm file, mapped and
+    cudaHostRegister'ed by each process), the destination of PathTracer.ReadResultScatterAsync: each GPU writes its stripes
+    over its own PCIe link and the frame is complete on the host without a device-side gather.
+
+    Collective: every rank of the default process group must construct it together.  Raises on any rank => raises on all."""
+
+    def __init__(self, frame_bytes: int, buffers: int, rank: int, world: int):
+        import os
+        import secrets
+
+        import torch
+        import torch.distributed as dist
+
+        self.frame_bytes, self.buffers = int(frame_bytes), int(buffers)
+        self.nbytes = ((self.frame_bytes + 4095) // 4096 * 4096) * self.buffers
+        self.stride = self.nbytes // self.buffers
+        self._registered = False
+        self.tensor = None
+        name = [None]
+        ok = 1
+        err = ""
+        try:
+            if rank == 0:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < self.nbytes + (16 << 20):
+                    raise OSError(f"/dev/shm has {st.f_bavail * st.f_frsize} bytes free, need {self.nbytes}")
+                name[0] = f"/dev/shm/ptb200_frame_{os.getpid()}_{secrets.token_hex(4)}"
+                with open(name[0], "wb") as f:
+                    f.truncate(self.nbytes)
+        except Exception as exc:      # noqa: BLE001
+            ok, err = 0, str(exc)
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        try:
+            if ok and self.path:
+                self.tensor = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
+                rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 1)     # 1 = cudaHostRegisterPortable
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister failed: {rc}")
+                self._registered = True
+            else:
+                ok = 0
+        except Exception as exc:      # noqa: BLE001
+            ok, err = 0, str(exc)
+        if world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            all_ok = int(flag.item())
+        else:
+            all_ok = ok
+        if rank == 0 and self.path and os.path.exists(self.path):
+            os.unlink(self.path)               # every rank has it mapped (or has given up): the name can go
+        if not all_ok:
+            self.close()
+            raise RuntimeError(f"shared host frame unavailable on some rank ({err or 'see the other ranks'})")
+
+    def ptr(self, k: int) -> int:
+        return self.tensor.data_ptr() + (k % self.buffers) * self.stride
+
+    def view(self, k: int, shape, dtype):
+        import torch
+        n = 1
+        for d in shape:
+            n *= d
+        flat = self.tensor[(k % self.buffers) * self.stride:(k % self.buffers) * self.stride + n * torch.empty((), dtype=dtype).element_size()]
+        return flat.view(dtype).view(*shape)
+
+    def close(self) -> None:
+        import torch
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = None

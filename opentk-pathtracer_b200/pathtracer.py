@@ -16,6 +16,7 @@ import numpy as np
 from . import _lib
 from . import scene as _scene
 
+FORMAT_RGBA32F, FORMAT_RGB32F, FORMAT_RGBA8 = 0, 1, 2      # ptb_read_result_format_async
 KERNEL_MEGA = 0
 KERNEL_NAIVE = 1
 
@@ -237,9 +238,16 @@ class PathTracer:
         a = np.ascontiguousarray(image, dtype=np.float32)
         _lib.check(self._L.ptb_write_result(self._ctx, a.ctypes.data_as(C.c_void_p)))
 
-    def ReadResultAsync(self, pinned_host_ptr: int) -> None:
-        """Enqueue a pipelined read-back of the image into pinned host memory (valid after Synchronize())."""
-        _lib.check(self._L.ptb_read_result_async(self._ctx, C.c_void_p(pinned_host_ptr)))
+    def ReadResultAsync(self, pinned_host_ptr: int, format: int = FORMAT_RGBA32F) -> None:
+        """Enqueue a pipelined read-back of the image into pinned host memory (valid after Synchronize()).
+        format: FORMAT_RGBA32F (16 B/pixel), FORMAT_RGB32F (12 B/pixel: the constant alpha 1.0 stays on the device) or
+        FORMAT_RGBA8 (4 B/pixel: the tone-mapped display frame, ScreenEffect fused into the snapshot)."""
+        _lib.check(self._L.ptb_read_result_format_async(self._ctx, int(format), C.c_void_p(pinned_host_ptr)))
+
+    def ReadResultScatterAsync(self, pinned_full_frame_ptr: int, format: int = FORMAT_RGBA32F) -> None:
+        """Multi-GPU read-back: this rank's stripes go straight into their rows of ONE full-frame host image (a pinned,
+        usually shared mapping), over this GPU's own PCIe link (ptb_read_result_scatter_async)."""
+        _lib.check(self._L.ptb_read_result_scatter_async(self._ctx, int(format), C.c_void_p(pinned_full_frame_ptr)))
 
     def Synchronize(self) -> None:
         _lib.check(self._L.ptb_synchronize(self._ctx))

@@ -416,6 +416,31 @@ def test_tile_union_equals_full_render(ptb, env256, default_scene, camera, world
     full.Dispose()
 
 
+@pytest.mark.parametrize("world,stripe,fmt", [(2, 8, 1), (3, 8, 0), (8, 16, 2), (4, 5, 1), (1, 8, 1)])
+def test_scatter_readback_assembles_the_frame_on_the_host(ptb, oracle, env256, default_scene, camera, world, stripe, fmt):
+    """ptb_read_result_scatter_async: every rank copies its stripes into their rows of ONE full-frame pinned host image
+    (ragged last stripe included, H = 203); the assembled frame equals the single-GPU image in all three formats."""
+    import torch
+    W, H = 320, 203
+    full = make_tracer(ptb, env256, W, H, default_scene, camera)
+    full.Render(2)
+    ref = full.Result
+    full.Dispose()
+    want = {0: ref, 1: ref[..., :3], 2: oracle.tonemap(ref)}[fmt]
+    host = torch.zeros(want.shape, dtype=torch.uint8 if fmt == 2 else torch.float32).pin_memory()
+    for r in range(world):
+        pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+        pt.SetTile(r, world, stripe)
+        pt.Render(2)
+        pt.ReadResultScatterAsync(host.data_ptr(), fmt)
+        pt.Synchronize()
+        pt.Dispose()
+    if fmt == 2:
+        assert (host.numpy() == want).all()
+    else:
+        assert_same(host.numpy(), want, f"world {world}, stripe {stripe}, format {fmt}")
+
+
 # ------------------------------------------------------------------------------- PathTracer class semantics
 def test_reset_setsize_and_resume(ptb, oracle, env256, default_scene, camera):
     pt = make_tracer(ptb, env256, 128, 96, default_scene, camera)
@@ -456,6 +481,39 @@ def test_pipelined_readback(ptb, env256, default_scene, camera):
         ref.Render()
         assert_same(bufs[f].numpy(), ref.Result, f"async read of frame {f}")
     pt.Dispose(); ref.Dispose()
+
+
+def test_readback_formats(ptb, oracle, env256, default_scene, camera):
+    """ptb_read_result_format_async: RGB32F is the colour floats bit for bit (alpha is the constant 1.0 of compute.glsl:129),
+    RGBA8 is ScreenEffect's pass fused into the snapshot; ragged pixel counts exercise the packer's tail."""
+    import torch
+    for W, H in ((320, 200), (67, 3), (1, 1)):
+        pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+        rgb = [torch.empty((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        rgba = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        ldr = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+        pt.Render()
+        pt.ReadResultAsync(rgb[0].data_ptr(), ptb.FORMAT_RGB32F)
+        pt.Render()
+        pt.ReadResultAsync(rgb[1].data_ptr(), ptb.FORMAT_RGB32F)
+        pt.ReadResultAsync(rgba.data_ptr(), ptb.FORMAT_RGBA32F)
+        pt.ReadResultAsync(ldr.data_ptr(), ptb.FORMAT_RGBA8)
+        pt.Synchronize()
+        full = pt.Result
+        assert (full[..., 3] == 1).all()
+        assert_same(rgba.numpy(), full, f"{W}x{H} RGBA32F")
+        assert_same(rgb[1].numpy(), full[..., :3], f"{W}x{H} RGB32F")
+        assert (ldr.numpy() == oracle.tonemap(full)).all(), f"{W}x{H} RGBA8"
+        ref = make_tracer(ptb, env256, W, H, default_scene, camera)
+        ref.Render()
+        assert_same(rgb[0].numpy(), ref.Result[..., :3], f"{W}x{H} RGB32F of the first frame (read while the second rendered)")
+        pt.Dispose(); ref.Dispose()
+    with pytest.raises(ptb.PtbError):
+        pt2 = make_tracer(ptb, env256, 8, 8, default_scene, camera)
+        try:
+            pt2.ReadResultAsync(rgba.data_ptr(), 7)
+        finally:
+            pt2.Dispose()
 
 
 def test_error_codes(ptb, env256):
