@@ -44,6 +44,26 @@ def deinterleave_host(gathered: np.ndarray, height: int, world: int, stripe_rows
     return out
 
 
+def scatter_plan(rank: int, world: int, stripe_rows: int, height: int):
+    """Host mirror of ptb_read_result_scatter_async's copy plan, in ROWS: (first local row, first global row, rows per chunk,
+    chunks, global row pitch) for the strided copy of the full stripes, and (first local row, first global row, rows) for the
+    ragged last stripe (rows == 0 if this rank does not own one)."""
+    n_local = local_row_count(rank, world, stripe_rows, height)
+    n_full, tail = divmod(n_local, stripe_rows)
+    strided = (0, rank * stripe_rows, stripe_rows, n_full, world * stripe_rows)
+    ragged = (n_full * stripe_rows, (rank + n_full * world) * stripe_rows, tail)
+    return strided, ragged
+
+
+def scatter_rows_host(local: np.ndarray, frame: np.ndarray, rank: int, world: int, stripe_rows: int) -> None:
+    """What the scatter read-back does, on host arrays: local (compact stripes, >= local rows) -> rows of `frame`."""
+    (l0, g0, rows, chunks, pitch), (tl, tg, tail) = scatter_plan(rank, world, stripe_rows, frame.shape[0])
+    for k in range(chunks):
+        frame[g0 + k * pitch:g0 + k * pitch + rows] = local[l0 + k * rows:l0 + (k + 1) * rows]
+    if tail:
+        frame[tg:tg + tail] = local[tl:tl + tail]
+
+
 def gather_stripes(local, world: int, dst: int = 0, group=None, async_op: bool = False):
     """One collective: gather every rank's (max_local_rows, W, 4) stripe buffer to `dst`.
     `local` is a torch tensor (CUDA with nccl, CPU with gloo).  Returns (gathered or None, work or None)."""
@@ -226,7 +246,8 @@ class SharedHostFrame:
 
     Collective: every rank of the default process group must construct it together.  Raises on any rank => raises on all."""
 
-    def __init__(self, frame_bytes: int, buffers: int, rank: int, world: int):
+    def __init__(self, frame_bytes: int, buffers: int, rank: int, world: int, register: bool = True):
+        """register=False maps the frame without pinning it for CUDA (CPU-only tests of the collective set-up)."""
         import os
         import secrets
 
@@ -257,16 +278,17 @@ class SharedHostFrame:
         try:
             if ok and self.path:
                 self.tensor = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
-                rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 1)     # 1 = cudaHostRegisterPortable
-                if int(rc) != 0:
-                    raise RuntimeError(f"cudaHostRegister failed: {rc}")
-                self._registered = True
+                if register:
+                    rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 1)     # 1 = cudaHostRegisterPortable
+                    if int(rc) != 0:
+                        raise RuntimeError(f"cudaHostRegister failed: {rc}")
+                    self._registered = True
             else:
                 ok = 0
         except Exception as exc:      # noqa: BLE001
             ok, err = 0, str(exc)
         if world > 1:
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda" if register else "cpu")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             all_ok = int(flag.item())
         else:

@@ -227,6 +227,63 @@ dist.destroy_process_group()
 """
 
 
+_SHARED_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from importlib import import_module
+D = import_module("opentk-pathtracer_b200.distributed")
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+W, H, stripe = 24, 53, 8                       # 7 stripes, the last one ragged (5 rows)
+shared = D.SharedHostFrame(H * W * 12, 2, rank, world, register=False)
+assert shared.path and not os.path.exists(shared.path)        # unlinked once everybody mapped it
+truth = np.arange(H * W * 3, dtype=np.float32).reshape(H, W, 3)
+rows = D.local_rows_of(rank, world, stripe, H)
+for k in (0, 1, 2):                             # buffer index wraps modulo 2
+    local = np.zeros((D.max_local_rows(world, stripe, H), W, 3), np.float32)
+    local[:rows.size] = truth[rows] + k
+    frame = shared.view(k, (H, W, 3), torch.float32).numpy()
+    D.scatter_rows_host(local, frame, rank, world, stripe)
+    dist.barrier()
+    assert (frame == truth + k).all(), "rows written by the other rank are not visible through the shared mapping"
+    dist.barrier()
+assert shared.ptr(2) == shared.ptr(0) and shared.ptr(1) - shared.ptr(0) >= H * W * 12
+shared.close()
+if rank == 0:
+    print("SHARED_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_shared_host_frame(tmp_path):
+    """The host side of the N>1 read-back on CPU: two gloo processes set up one shared frame mapping (no CUDA pinning here),
+    each writes ITS rows with the scatter plan the C ABI uses, and both see the complete frame."""
+    script = tmp_path / "shared_worker.py"
+    script.write_text(_SHARED_WORKER.format(root=ROOT))
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "SHARED_OK" in outs[0]
+
+
+def test_scatter_plan_covers_every_row_once(ptb):
+    from importlib import import_module
+    D = import_module("opentk-pathtracer_b200.distributed")
+    for height, world, stripe in [(1080, 8, 8), (1080, 3, 8), (2160, 8, 16), (203, 8, 16), (203, 4, 5), (7, 8, 8), (64, 1, 8)]:
+        frame = np.full((height, 3), -1.0, np.float32)
+        for r in range(world):
+            rows = D.local_rows_of(r, world, stripe, height)
+            local = np.zeros((D.max_local_rows(world, stripe, height), 3), np.float32)
+            local[:rows.size, 0] = rows
+            D.scatter_rows_host(local, frame, r, world, stripe)
+        assert (frame[:, 0] == np.arange(height)).all(), (height, world, stripe)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
