@@ -6,6 +6,7 @@ This mirrors the reference's C# data surface (it is host logic, numpy only, no G
   Cuboid.GetGPUFriendlyData       src/GameObjects/Cuboid.cs:21-35   (96 B, offset MAX_SPHERES*80 + Instance*96)
   MainWindow.LoadScene            src/MainWindow.cs:208-267  (48 spheres + 7 cuboids)
   Camera / BasicDataUBO writes    src/Camera.cs:16-30,79-82; src/MainWindow.cs:131-132,278-279
+  CPU mouse picking               src/Ray.cs:15-19, Sphere.cs:34-50, Cuboid.cs:38-52, MainWindow.cs:302-322, Gui.cs:229-233
 OpenTK 3.3.2's Matrix4 helpers (LookAt, CreatePerspectiveFieldOfView, Inverted) are a NuGet dependency that is
 not vendored in the reference; they are restated here in float32 from their published algorithms.  Parity with
 the shader is defined at the UBO-byte boundary, so these only have to be self-consistent.
@@ -396,6 +397,84 @@ def basic_data_bytes(camera: Camera, width: int, height: int, fov=FOV) -> bytes:
     buf.SubData(64, 64, inverted(camera.View))
     buf.SubData(128, 16, np.append(np.asarray(camera.Position, dtype=f32), f32(0)))
     return buf.bytes()
+
+
+# ----------------------------------------------------------------------------- CPU picking (host-side, float32 like the C#)
+@dataclass
+class Ray:
+    """src/Ray.cs — the host-side ray used for mouse picking (not the shader's ray: IEEE division, Math.Max / Math.Min)."""
+    Origin: np.ndarray
+    Direction: np.ndarray
+
+    def GetPoint(self, deltaTime) -> np.ndarray:  # Ray.cs:10-13
+        return (np.asarray(self.Origin, f32) + np.asarray(self.Direction, f32) * f32(deltaTime)).astype(f32)
+
+    @staticmethod
+    def GetWorldSpaceRay(inverseProjection: np.ndarray, inverseView: np.ndarray, worldPosition, normalizedDeviceCoords) -> "Ray":
+        """Ray.cs:15-19: row-vector products (`vector * matrix`), rayEye.zw = (-1, 0), normalised direction."""
+        ndc = np.asarray(normalizedDeviceCoords, dtype=f32)
+        eye = _row_times_matrix(np.array([ndc[0], ndc[1], f32(-1.0), f32(1.0)], dtype=f32), inverseProjection)
+        eye[2], eye[3] = f32(-1.0), f32(0.0)
+        d = _row_times_matrix(eye, inverseView)[:3]
+        return Ray(np.asarray(worldPosition, dtype=f32).copy(), _normalize(d))
+
+
+def _row_times_matrix(v: np.ndarray, m: np.ndarray) -> np.ndarray:
+    """OpenTK `Vector4 * Matrix4`: result.X = v.X*M11 + v.Y*M21 + v.Z*M31 + v.W*M41, ... (float32, left to right)."""
+    m = np.asarray(m, dtype=f32)
+    out = np.zeros(4, dtype=f32)
+    for c in range(4):
+        out[c] = f32(f32(f32(v[0] * m[0, c]) + f32(v[1] * m[1, c])) + f32(v[2] * m[2, c])) + f32(v[3] * m[3, c])
+    return out
+
+
+def sphere_intersects_ray(s: Sphere, ray: Ray):
+    """Sphere.IntersectsRay (Sphere.cs:34-50) -> (hit, t1, t2)."""
+    v = (np.asarray(ray.Origin, f32) - np.asarray(s.Position, f32)).astype(f32)
+    d = np.asarray(ray.Direction, f32)
+    b = _dot(d, v)
+    c = f32(_dot(v, v) - f32(f32(s.Radius) * f32(s.Radius)))
+    disc = f32(f32(b * b) - c)
+    if disc < 0:
+        return False, f32(0), f32(0)
+    sq = f32(np.sqrt(disc))
+    return True, f32(-b - sq), f32(-b + sq)
+
+
+def cuboid_intersects_ray(c: Cuboid, ray: Ray):
+    """Cuboid.IntersectsRay (Cuboid.cs:38-52): slab test with IEEE division; Math.Max / Math.Min propagate NaN."""
+    o, d = np.asarray(ray.Origin, f32), np.asarray(ray.Direction, f32)
+    with np.errstate(all="ignore"):
+        t0s = ((c.Min - o) / d).astype(f32)
+        t1s = ((c.Max - o) / d).astype(f32)
+        lo, hi = np.minimum(t0s, t1s), np.maximum(t0s, t1s)          # Vector3.ComponentMin / ComponentMax
+        t1 = np.maximum(f32(np.finfo(f32).min), np.maximum(lo[0], np.maximum(lo[1], lo[2])))
+        t2 = np.minimum(f32(np.finfo(f32).max), np.minimum(hi[0], np.minimum(hi[1], hi[2])))
+    return bool(t1 <= t2), f32(t1), f32(t2)
+
+
+def pick(scene: Scene, ray: Ray):
+    """MainWindow.RayTrace (MainWindow.cs:302-318): the same order-dependent fold as the shader's (accept on
+    hit && t2 > 0 && t1 < tMin, spheres before cuboids as LoadScene adds them) -> (object or None, t1, t2)."""
+    t1 = t2 = f32(0)
+    picked = None
+    t_min = f32(np.finfo(f32).max)
+    for o in scene.objects():
+        hit, a, b = sphere_intersects_ray(o, ray) if isinstance(o, Sphere) else cuboid_intersects_ray(o, ray)
+        if hit and b > 0 and a < t_min:
+            t1, t2 = a, b
+            t_min = b if a < 0 else a          # GetSmallestPositive, MainWindow.cs:319-322
+            picked = o
+    return picked, t1, t2
+
+
+def pick_at_cursor(scene: Scene, camera: Camera, width: int, height: int, x: int, y_from_top: int, fov=FOV):
+    """Gui.cs:229-233: window coordinates (origin top-left) -> NDC -> world ray -> RayTrace."""
+    wy = height - y_from_top
+    ndc = (np.array([x, wy], dtype=f32) / np.array([width, height], dtype=f32) * f32(2.0) - f32(1.0)).astype(f32)
+    inv_proj = inverted(create_perspective_fov(degrees_to_radians(fov), f32(width) / f32(height), *NEAR_FAR))
+    ray = Ray.GetWorldSpaceRay(inv_proj, inverted(camera.View), camera.Position, ndc)
+    return pick(scene, ray) + (ray,)
 
 
 # ----------------------------------------------------------------------------- atmosphere inputs

@@ -303,3 +303,41 @@ def test_two_rank_gloo_gather_equals_single_render(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "GATHER_OK" in outs[0]
+
+
+def test_cpu_picking_matches_the_shader_fold(ptb, oracle):
+    """MainWindow.RayTrace (the mouse-picking fold on the host) mirrored in scene.pick.  It is the same
+    order-dependent fold as compute.glsl's RayTrace, in C# float arithmetic (IEEE division instead of a*rcp(b)), so it must
+    select the same primitive as the oracle for every cursor position, with T equal up to the rounding of the discriminant."""
+    sc = ptb.scene
+    scene, cam = sc.load_default_scene(), sc.default_camera()
+    W, H = 1280, 720
+    rng = np.random.default_rng(9)
+    rays, picks = [], []
+    for _ in range(400):
+        x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+        obj, t1, t2, ray = sc.pick_at_cursor(scene, cam, W, H, x, y)
+        rays.append(np.concatenate([ray.Origin, ray.Direction]))
+        picks.append((obj, t1, t2))
+    ref = oracle.ray_trace(np.asarray(rays, np.float32), scene.ubo_bytes(), 256, 48, 7)
+    objs = scene.objects()
+    kinds = set()
+    for (obj, t1, t2), r in zip(picks, ref):
+        assert (obj is not None) == bool(r[0])
+        if obj is None:
+            continue
+        kinds.add(type(obj).__name__)
+        T = t2 if t1 < 0 else t1
+        assert abs(float(T) - float(r[1])) <= 2e-4 * max(1.0, abs(float(r[1])))     # unfused C# dot products vs the shader model's fma chains, amplified by b*b - c
+        assert np.float32(obj.Material.Albedo[0]) == r[10] and np.float32(obj.Material.Emissiv[0]) == r[11]
+    assert kinds == {"Sphere", "Cuboid"}
+    # known answers: a ray down the axis of sphere 0 hits it at |o - c| -/+ r; from inside a cuboid t1 < 0 < t2
+    s0 = scene.spheres[0]
+    o = (np.asarray(s0.Position, np.float32) + np.array([0, 0, 10], np.float32)).astype(np.float32)
+    obj, t1, t2 = sc.pick(sc.Scene(spheres=[s0]), sc.Ray(o, np.array([0, 0, -1], np.float32)))
+    assert obj is s0 and abs(float(t1) - (10 - float(s0.Radius))) < 1e-5 and abs(float(t2) - (10 + float(s0.Radius))) < 1e-5
+    room = scene.cuboids[0]
+    centre = ((room.Min + room.Max) * np.float32(0.5)).astype(np.float32)
+    hit, t1, t2 = sc.cuboid_intersects_ray(room, sc.Ray(centre, sc._normalize(np.array([0.3, 1.0, 0.2], np.float32))))
+    assert hit and t1 < 0 < t2
+    assert sc.pick(sc.Scene(), sc.Ray(o, np.array([0, 0, -1], np.float32)))[0] is None
