@@ -29,6 +29,9 @@ shader's own.  They are:
       (compute.glsl:113 draws two random numbers inside one constructor).  The script then verifies that no other
       statement contains two RNG-advancing calls whose order C++ would not fix.
   R12 mutable globals (`uint rndSeed;`, fragment outputs / inputs) become `thread_local` so pixels can run on OpenMP threads.
+  R13 (only with --capacity S C, for BASELINE config 3, which does not fit the shader as shipped) the two array lengths of
+      the GameObjectsUBO block, `Spheres[256]` / `Cuboids[64]` (compute.glsl:68-69), become `Spheres[S]` / `Cuboids[C]`;
+      output goes to libglsl_ref_<S>x<C>.so.  Nothing else changes.
 """
 from __future__ import annotations
 
@@ -139,8 +142,13 @@ def _check_evaluation_order(s: str, name: str) -> None:
             raise RuntimeError(f"{name}: two RNG-advancing calls in one expression: {stmt.strip()!r}")
 
 
-def translate(src: str, name: str) -> str:
+def translate(src: str, name: str, capacity=None) -> str:
     s = _strip_comments(src)
+    if capacity is not None:                                                                        # R13
+        s, n1 = re.subn(r"\bSpheres\[256\]", f"Spheres[{int(capacity[0])}]", s)
+        s, n2 = re.subn(r"\bCuboids\[64\]", f"Cuboids[{int(capacity[1])}]", s)
+        if name.startswith("PathTracing") and (n1 != 1 or n2 != 1):
+            raise RuntimeError(f"{name}: expected exactly one Spheres[256] and one Cuboids[64] declaration")
     s = re.sub(r"^[ \t]*#version[^\n]*", "", s, flags=re.M)                                         # R1
     s = re.sub(r"(\d+\.\d+)\.xxx\b", r"vec3(\1)", s)                                                # R7 (literal swizzle)
     s = re.sub(r"\.(xyz|rgb|xy|zw)\b(?!\s*\()", r".\1()", s)                                        # R7
@@ -174,12 +182,16 @@ def shader_paths(reference: str) -> dict[str, str]:
     return {k: os.path.join(base, v[0]) for k, v in SHADERS.items()}
 
 
-def build(reference: str = "/root/reference", keep: bool = False, verbose: bool = False, alt_model: bool = False) -> str:
+def capacity_lib(capacity) -> str:
+    return os.path.join(OUT_DIR, f"libglsl_ref_{int(capacity[0])}x{int(capacity[1])}.so")
+
+
+def build(reference: str = "/root/reference", keep: bool = False, verbose: bool = False, alt_model: bool = False, capacity=None) -> str:
     """alt_model=True builds oracle/_ref/libglsl_ref_alt.so instead: the same shaders under a second admissible evaluation
     model (IEEE division, libm transcendentals, nothing fused) — a measuring instrument for tools/model_sensitivity.py,
     never a parity reference."""
     paths = shader_paths(reference)
-    lib_out = LIB_ALT if alt_model else LIB
+    lib_out = LIB_ALT if alt_model else (capacity_lib(capacity) if capacity is not None else LIB)
     flags = CXXFLAGS + (["-DGLSL_SHIM_ALT_MODEL"] if alt_model else [])
     for p in paths.values():
         if not os.path.exists(p):
@@ -190,7 +202,7 @@ def build(reference: str = "/root/reference", keep: bool = False, verbose: bool 
         objs = []
         for key, (rel, harness, ns) in SHADERS.items():
             with open(paths[key], "r", encoding="utf-8-sig") as f:
-                text = translate(f.read(), rel)
+                text = translate(f.read(), rel, capacity)
             gen = os.path.join(tmp, f"{key}_translated.inc")
             with open(gen, "w") as f:
                 f.write(text)
@@ -208,7 +220,7 @@ def build(reference: str = "/root/reference", keep: bool = False, verbose: bool 
             subprocess.run(cmd, check=True)
             objs.append(obj)
         subprocess.run([CXX, "-shared", "-fopenmp", "-o", lib_out, *objs, "-lm"], check=True)
-        if alt_model:
+        if alt_model or capacity is not None:
             return lib_out
         manifest = {
             "built_from": {k: {"path": os.path.relpath(p, reference), "sha256": _sha256(p)} for k, p in paths.items()},
@@ -233,5 +245,6 @@ if __name__ == "__main__":
     ap.add_argument("--keep", action="store_true", help="leave the translated text in its /tmp directory")
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("--alt-model", action="store_true", help="build libglsl_ref_alt.so (second evaluation model, for tools/model_sensitivity.py)")
+    ap.add_argument("--capacity", type=int, nargs=2, metavar=("SPHERES", "CUBOIDS"), help="R13: build libglsl_ref_<S>x<C>.so with larger UBO arrays (BASELINE config 3)")
     a = ap.parse_args()
-    print(build(a.reference, a.keep, a.verbose, a.alt_model))
+    print(build(a.reference, a.keep, a.verbose, a.alt_model, a.capacity))

@@ -23,6 +23,23 @@ MANIFEST_PATH = os.path.join(_HERE, "_ref", "manifest.json")
 _lib = None
 
 
+def use_library(path: str) -> None:
+    """Point this module at another build of the compiled shaders (build_ref.py --capacity / --alt-model)."""
+    global LIB_PATH, _lib
+    LIB_PATH, _lib = path, None
+
+
+def variant(path: str):
+    """A second, independent instance of this module bound to another build of the compiled shaders."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(f"oracle.ref_variant_{abs(hash(path))}", os.path.abspath(__file__))
+    m = importlib.util.module_from_spec(spec)
+    m.__package__ = "oracle"
+    spec.loader.exec_module(m)
+    m.use_library(path)
+    return m
+
+
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 

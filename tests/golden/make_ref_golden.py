@@ -9,6 +9,8 @@ ref_pt_default.npz    default scene (MainWindow.cs:208-267), 96x54, SPP 2, frame
                       aperture 0.14 (MainWindow.cs:190), 32^2 atmosphere (10 x 4 steps); the running mean after each frame.
 ref_pt_synthetic.npz  256 spheres + 64 cuboids with random materials (scene.synthetic_scene(256, 64, seed=7)), 64x36, SPP 1,
                       rayDepth 8, frames 5..6 on top of a zero image, wide aperture.
+ref_pt_config3.npz    BASELINE config 3's scene (scene.synthetic_scene(1024, 256), capacities 1024 / 256), 96x54, SPP 1, rayDepth 8,
+                      frames 0..1 — from the build with the two UBO array lengths rewritten (build_ref.py --capacity 1024 256).
 ref_atmosphere.npz    AtmosphericScattering/compute.glsl: 16^2 (8 x 4 steps, time 0.5) and 12^2 (6 x 3 steps, time 0.2).
 ref_post.npz          PostProcessing/fragment.glsl over the final ref_pt_default image and over a synthetic HDR ramp.
 """
@@ -64,6 +66,24 @@ def generate(R) -> dict:
         frames2.append(img2.copy())
     out["ref_pt_synthetic.npz"] = dict(basic_ubo=np.frombuffer(basic, np.uint8).copy(), objects_ubo=np.frombuffer(ubo, np.uint8).copy(),
                                        after_frame=np.stack(frames2))
+
+    from oracle import build_ref
+    lib = build_ref.capacity_lib((1024, 256))
+    if not os.path.exists(lib) and os.path.isdir("/root/reference"):
+        build_ref.build(capacity=(1024, 256))
+    if os.path.exists(lib):                                   # absent only on a machine that never saw /root/reference
+        big = R.variant(lib)
+        scene = sc.synthetic_scene(1024, 256)
+        W, H = 96, 54
+        basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+        img3 = np.zeros((H, W, 4), np.float32)
+        frames3 = []
+        for f in (0, 1):
+            big.render(img3, basic, ubo, env32, frame=f, spp=1, ray_depth=8, focal_length=20.0, aperture_diameter=0.14, n_spheres=1024,
+                       n_cuboids=256, max_spheres=1024)
+            frames3.append(img3.copy())
+        out["ref_pt_config3.npz"] = dict(basic_ubo=np.frombuffer(basic, np.uint8).copy(), objects_ubo=np.frombuffer(ubo, np.uint8).copy(),
+                                         after_frame=np.stack(frames3))
 
     ramp = hdr_ramp()
     out["ref_post.npz"] = dict(rendered=R.post(img), ramp=ramp, ramp_rgba8=R.post(ramp))

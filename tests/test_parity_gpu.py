@@ -625,8 +625,8 @@ def test_srgb8_skybox_environment(ptb, oracle, default_scene, camera):
 # tests/golden/ref_*.npz come from the reference's GLSL compiled for the CPU (oracle/build_ref.py; generator
 # tests/golden/make_ref_golden.py).  The CUDA path is driven with the stored input BYTES through the two SubData entry
 # points, exactly as the C# host would, and must reproduce the stored images bit for bit.
-def _tracer_from_bytes(ptb, env, W, H, basic, ubo, ns, nc, **kw):
-    pt = ptb.PathTracer(env, W, H, kw["depth"], kw["spp"], kw["focal"], kw["aperture"])
+def _tracer_from_bytes(ptb, env, W, H, basic, ubo, ns, nc, max_spheres=256, max_cuboids=64, **kw):
+    pt = ptb.PathTracer(env, W, H, kw["depth"], kw["spp"], kw["focal"], kw["aperture"], max_spheres=max_spheres, max_cuboids=max_cuboids)
     pt.BasicDataUBO.SubData(0, len(basic), basic)
     pt.GameObjectsUBO.SubData(0, len(ubo), ubo)
     pt.NumSpheres, pt.NumCuboids = ns, nc
@@ -657,6 +657,20 @@ def test_reference_golden_synthetic_scene(ptb):
     for k in range(n):
         pt.Render()
         assert_same(pt.Result, g["after_frame"][k], f"reference golden, synthetic scene, frame {5 + k}")
+    pt.Dispose()
+
+
+def test_reference_golden_config3_scene(ptb):
+    """BASELINE config 3 (1024 spheres + 256 cuboids, capacities 1024 / 256: BVH fold, materials left in HBM) against the
+    reference shader built with its two UBO array lengths rewritten (build_ref.py --capacity 1024 256)."""
+    g = np.load(os.path.join(GOLD, "ref_pt_config3.npz"))
+    env = np.load(os.path.join(GOLD, "ref_pt_default.npz"))["env"]
+    n, H, W, _ = g["after_frame"].shape
+    pt = _tracer_from_bytes(ptb, env, W, H, g["basic_ubo"].tobytes(), g["objects_ubo"].tobytes(), 1024, 256,
+                            max_spheres=1024, max_cuboids=256, depth=8, spp=1, focal=20.0, aperture=0.14)
+    for f in range(n):
+        pt.Render()
+        assert_same(pt.Result, g["after_frame"][f], f"reference golden, config 3, frame {f}")
     pt.Dispose()
 
 

@@ -307,3 +307,40 @@ def test_older_oracle_written_goldens_are_reference_outputs_too(ref, ptb, defaul
         if f == 0:
             assert f32_same(img, np.load(os.path.join(gold, "c1_64x64_f0.npy"))).all()
     assert f32_same(img, np.load(os.path.join(gold, "c1_64x64_f0_3.npy"))).all()
+
+
+def test_baseline_config3_scene_with_patched_array_lengths(ref, oracle, ptb, env16, camera):
+    """BASELINE config 3 (1024 spheres + 256 cuboids) does not fit the shader as shipped (`Spheres[256]`, `Cuboids[64]`,
+    compute.glsl:68-69).  build_ref.py --capacity 1024 256 rewrites those two integers and nothing else (rule R13); the
+    oracle's large-capacity path (cuboid block at byte 1024 * 80) is pinned against that build on config 3's own scene."""
+    from oracle import build_ref
+    lib = build_ref.capacity_lib((1024, 256))
+    if not os.path.exists(lib):
+        if not os.path.isdir(REFERENCE):
+            pytest.skip("libglsl_ref_1024x256.so not built and /root/reference is absent")
+        build_ref.build(REFERENCE, capacity=(1024, 256))
+    big = ref.variant(lib)
+    assert big.capacity() == (1024, 256)
+    sc = ptb.scene
+    scene = sc.synthetic_scene(1024, 256)                     # the C3 generator (seed 1234), capacities 1024 / 256
+    W, H = 1920, 1080
+    basic, ubo = sc.basic_data_bytes(camera, W, H), scene.ubo_bytes()
+    io, ir = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    for band in ((100, 104), (540, 546), (1000, 1003)):
+        kw = dict(frame=0, spp=1, ray_depth=8, focal_length=20.0, aperture_diameter=0.14, n_spheres=1024, n_cuboids=256,
+                  max_spheres=1024, rows=band, cols=(0, W))
+        oracle.render(io, basic, ubo, env16, **kw)
+        big.render(ir, basic, ubo, env16, **kw)
+    _same_images(io, ir, "config 3 bands at 1080p")
+    assert float(io[540:546, :, :3].mean()) > 0.01
+    # and the closest-hit fold alone, rays from inside the cloud of primitives
+    rng = np.random.default_rng(41)
+    o = (rng.random((20000, 3)).astype(np.float32) * np.array([38, 22, 22], np.float32) + np.array([-19, -11, -21], np.float32)).astype(np.float32)
+    d = rng.standard_normal((20000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    a = oracle.ray_trace(rays, ubo, 1024, 1024, 256)
+    b = big.ray_trace(rays, ubo, 1024, 1024, 256)
+    assert (a[:, 0] == b[:, 0]).all() and a[:, 0].sum() > 15000
+    hit = a[:, 0] == 1
+    _same_images(a[hit], b[hit], "RayTrace over 1280 primitives")

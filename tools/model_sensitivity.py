@@ -17,7 +17,6 @@ fixed arithmetic, which is why the oracle, the compiled reference and the CUDA k
 real driver's arithmetic would leave, and a matched-seed comparison is far more sensitive than a statistical one.
 """
 import argparse
-import importlib.util
 import os
 import sys
 
@@ -31,12 +30,8 @@ def load_alt():
     from oracle import build_ref
     if not os.path.exists(build_ref.LIB_ALT):
         build_ref.build(alt_model=True)
-    spec = importlib.util.spec_from_file_location("oracle.ref_alt", os.path.join(ROOT, "oracle", "ref.py"))
-    m = importlib.util.module_from_spec(spec)
-    m.__package__ = "oracle"
-    spec.loader.exec_module(m)
-    m.LIB_PATH = build_ref.LIB_ALT
-    return m
+    from oracle import ref as R
+    return R.variant(build_ref.LIB_ALT)
 
 
 def main():
