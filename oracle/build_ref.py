@@ -28,7 +28,9 @@ shader's own.  They are:
       of parenthesised arguments unspecified, GLSL §6.1.1 evaluates left to right, braces guarantee it
       (compute.glsl:113 draws two random numbers inside one constructor).  The script then verifies that no other
       statement contains two RNG-advancing calls whose order C++ would not fix.
-  R12 mutable globals (`uint rndSeed;`, fragment outputs / inputs) become `thread_local` so pixels can run on OpenMP threads.
+  R12 GLSL globals are per invocation: mutable globals (`uint rndSeed;`), fragment inputs / outputs, the built-in variables and
+      all functions become members of `struct Invocation` (one object per invocation); types, uniforms and uniform blocks
+      stay shared at namespace scope; forward declarations are dropped.  The same text compiles for the GPU (GLSL_FN).
   R13 (only with --capacity S C, for BASELINE config 3, which does not fit the shader as shipped) the two array lengths of
       the GameObjectsUBO block, `Spheres[256]` / `Cuboids[64]` (compute.glsl:68-69), become `Spheres[S]` / `Cuboids[C]`;
       output goes to libglsl_ref_<S>x<C>.so.  Nothing else changes.
@@ -156,20 +158,75 @@ def translate(src: str, name: str, capacity=None) -> str:
     s = re.sub(r"\bfloat\b", "Float", s)                                                            # R3
     s = re.sub(r"^[ \t]*layout\s*\([^)]*\)\s*in\s*;", "", s, flags=re.M)                            # R4 (local_size)
     s = re.sub(r"^[ \t]*(?:layout\s*\([^)]*\)\s*)?(uniform|in|out)\s+(\w+)\s*\{",                   # R5 (+R12 for in/out)
-               lambda m: ("" if m.group(1) == "uniform" else "thread_local ") + f"struct {m.group(2)} {{", s, flags=re.M)
+               lambda m: ("GLSL_UNIFORM " if m.group(1) == "uniform" else "GLSL_INVOCATION ") + f"struct {m.group(2)} {{", s, flags=re.M)
     s = re.sub(r"^([ \t]*)layout\s*\([^)]*\)\s*", r"\1", s, flags=re.M)                             # R4
     # R4 + R12: remaining global qualifiers.  `uniform` = shared state written by the harness; `in` / `out` = per-invocation.
     s = re.sub(r"\b(?:restrict|writeonly|readonly)\s+", "", s)
     s = re.sub(r"^[ \t]*uniform\s+(\w+)", r"GLSL_UNIFORM \1", s, flags=re.M)
-    s = re.sub(r"^[ \t]*(?:in|out)\s+(\w+\s+\w+\s*;)", r"thread_local \1", s, flags=re.M)
+    s = re.sub(r"^[ \t]*(?:in|out)\s+(\w+\s+\w+\s*;)", r"GLSL_INVOCATION \1", s, flags=re.M)
     s = re.sub(r"\b(?:inout|out)\s+(\w+)\s+(\w+)", r"\1& \2", s)                                    # R6
     s = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void glsl_main()", s)                                   # R8
     s = re.sub(r"^([ \t]*)Material\s+Material\s*;", r"\1struct Material Material;", s, flags=re.M)  # R9
     s = re.sub(r"\b(\w+)\[(\d+)\]\s+(\w+)\s*;", r"\1 \3[\2];", s)                                   # R10
     _check_evaluation_order(s, name)
     s = _brace_constructors(s)                                                                      # R11
-    s = re.sub(r"^(uint|int|Float|vec[234])\s+(\w+)\s*;", r"thread_local \1 \2;", s, flags=re.M)    # R12 (plain globals)
-    return s
+    s = re.sub(r"^(uint|int|Float|vec[234])\s+(\w+)\s*;", r"GLSL_INVOCATION \1 \2;", s, flags=re.M)  # R12 (plain globals)
+    return _wrap_invocation(s, name)                                                                # R12
+
+
+def _top_level_items(s: str) -> list[str]:
+    """Split translated text into top-level items: preprocessor lines, `...;` declarations (struct bodies included) and
+    function definitions (which end at their closing brace)."""
+    items, depth, start, i, n = [], 0, 0, 0, len(s)
+    while i < n:
+        ch = s[i]
+        if depth == 0 and ch == "#" and s[start:i].strip() == "":
+            j = s.find("\n", i)
+            j = n if j < 0 else j
+            items.append(s[i:j])
+            start = i = j + 1
+            continue
+        if ch == "{":
+            depth += 1
+        elif ch == "}":
+            depth -= 1
+            if depth == 0:
+                head = s[start:i]
+                is_function = "(" in head[:head.index("{")] and not re.match(r"\s*(?:GLSL_\w+\s+)?struct\b", head)
+                if is_function:
+                    items.append(s[start:i + 1])
+                    start = i + 1
+        elif ch == ";" and depth == 0:
+            items.append(s[start:i + 1])
+            start = i + 1
+        i += 1
+    if s[start:].strip():
+        raise RuntimeError(f"unterminated top-level item: {s[start:].strip()[:60]!r}")
+    return [it.strip() for it in items if it.strip() and it.strip() != ";"]
+
+
+def _wrap_invocation(s: str, name: str) -> str:
+    """R12: GLSL globals are per invocation.  Everything an invocation owns — its mutable globals, its built-in variables and
+    all functions (they read those globals) — becomes a member of `struct Invocation`, one object per invocation; types,
+    uniforms and uniform blocks stay at namespace scope, shared.  Forward declarations are dropped (members need none).
+    GLSL_FN / GLSL_UNIFORM are empty for g++ and `__host__ __device__` / `__constant__` for nvcc (the same text is compiled
+    for the GPU by the CUDA harness)."""
+    shared, members = [], []
+    for it in _top_level_items(s):
+        if it.startswith("#"):
+            shared.append(it)
+        elif it.startswith("GLSL_INVOCATION"):
+            members.append("    " + it[len("GLSL_INVOCATION"):].strip())
+        elif it.startswith("GLSL_UNIFORM") or re.match(r"struct\b", it):
+            shared.append(it)
+        elif "{" in it:
+            members.append("    GLSL_FN " + it)
+        elif re.match(r"[\w&\s]+?\b\w+\s*\([^{}]*\)\s*;$", it, flags=re.S):
+            continue                                            # forward declaration
+        else:
+            raise RuntimeError(f"{name}: cannot classify top-level item {it[:80]!r}")
+    return ("\n".join(shared) + "\n\nstruct Invocation {\n    uvec3 gl_GlobalInvocationID;\n    vec4 gl_FragCoord;\n"
+            + "\n".join(members) + "\n};\n")
 
 
 def _sha256(path: str) -> str:

@@ -43,42 +43,60 @@
 #include <stdint.h>
 #include <string.h>
 
+/* G_FN: `static inline` for gcc / g++; under nvcc also __host__ __device__, so the SAME model text can be compiled for the
+ * GPU (oracle/build_ref.py --cuda compiles the reference's shaders with nvcc as the GL-compute proxy).  With nvcc's
+ * defaults (-prec-div=true -prec-sqrt=true) and -fmad=false, 1.0f / b, sqrtf and fmaf round exactly as on the host. */
+#ifdef __CUDACC__
+#define G_FN G_FN __host__ __device__
+#else
+#define G_FN static inline
+#endif
+
 typedef struct { float x, y, z; } vec3;
 typedef struct { float x, y, z, w; } vec4;
 
-static inline uint32_t g_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
-static inline float g_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+G_FN uint32_t g_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+G_FN float g_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-static inline float g_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
-static inline float g_rcp(float b) { return 1.0f / b; }
-static inline float g_div(float a, float b) { return a * g_rcp(b); }
-static inline float g_sqrt(float a) { return __builtin_sqrtf(a); }
-static inline float g_abs(float a) { return g_float(g_bits(a) & 0x7fffffffu); }
-static inline int g_isnan(float a) { return a != a; }
+#if defined(__CUDA_ARCH__)
+G_FN float g_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+G_FN float g_rcp(float b) { return __frcp_rn(b); }
+#else
+G_FN float g_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+G_FN float g_rcp(float b) { return 1.0f / b; }
+#endif
+G_FN float g_div(float a, float b) { return a * g_rcp(b); }
+#if defined(__CUDA_ARCH__)
+G_FN float g_sqrt(float a) { return __fsqrt_rn(a); }
+#else
+G_FN float g_sqrt(float a) { return __builtin_sqrtf(a); }
+#endif
+G_FN float g_abs(float a) { return g_float(g_bits(a) & 0x7fffffffu); }
+G_FN int g_isnan(float a) { return a != a; }
 
 /* minNum / maxNum with -0 < +0 (what FMNMX does). */
-static inline float g_min(float a, float b)
+G_FN float g_min(float a, float b)
 {
     if (g_isnan(a)) return b;
     if (g_isnan(b)) return a;
     if (a == b) return (g_bits(a) >> 31) ? a : b;
     return b < a ? b : a;
 }
-static inline float g_max(float a, float b)
+G_FN float g_max(float a, float b)
 {
     if (g_isnan(a)) return b;
     if (g_isnan(b)) return a;
     if (a == b) return (g_bits(a) >> 31) ? b : a;
     return a < b ? b : a;
 }
-static inline float g_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
-static inline float g_sign(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }
-static inline float g_mix(float x, float y, float a) { return g_fma(y, a, x * (1.0f - a)); }
-static inline float g_pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
-static inline float g_pow15(float x) { return x * g_sqrt(x); }
+G_FN float g_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+G_FN float g_sign(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }
+G_FN float g_mix(float x, float y, float a) { return g_fma(y, a, x * (1.0f - a)); }
+G_FN float g_pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
+G_FN float g_pow15(float x) { return x * g_sqrt(x); }
 
 /* float -> int: truncate; NaN -> 0; saturate to +-2^30 (indices are clamped by callers anyway). */
-static inline int g_f2i(float x)
+G_FN int g_f2i(float x)
 {
     if (g_isnan(x)) return 0;
     if (x >= 1073741824.0f) return 1073741824;
@@ -86,7 +104,7 @@ static inline int g_f2i(float x)
     return (int)x;
 }
 /* floor as float, via truncation fix-up (|x| < 2^30 assumed by callers; otherwise x itself). */
-static inline float g_floor(float x)
+G_FN float g_floor(float x)
 {
     if (g_isnan(x)) return x;
     if (!(g_abs(x) < 1073741824.0f)) return x;
@@ -95,27 +113,27 @@ static inline float g_floor(float x)
 }
 
 /* ---- vec3 helpers ---------------------------------------------------------------- */
-static inline vec3 v3(float x, float y, float z) { vec3 r = { x, y, z }; return r; }
-static inline vec3 v_add(vec3 a, vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-static inline vec3 v_sub(vec3 a, vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-static inline vec3 v_mul(vec3 a, vec3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
-static inline vec3 v_scale(vec3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
-static inline vec3 v_neg(vec3 a) { return v3(-a.x, -a.y, -a.z); }
-static inline float v_dot(vec3 a, vec3 b) { return g_fma(a.z, b.z, g_fma(a.y, b.y, a.x * b.x)); }
-static inline float v_length(vec3 a) { return g_sqrt(v_dot(a, a)); }
-static inline vec3 v_normalize(vec3 a) { return v_scale(a, g_rcp(g_sqrt(v_dot(a, a)))); }
-static inline vec3 v_mix(vec3 a, vec3 b, float t)
+G_FN vec3 v3(float x, float y, float z) { vec3 r = { x, y, z }; return r; }
+G_FN vec3 v_add(vec3 a, vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+G_FN vec3 v_sub(vec3 a, vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+G_FN vec3 v_mul(vec3 a, vec3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+G_FN vec3 v_scale(vec3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+G_FN vec3 v_neg(vec3 a) { return v3(-a.x, -a.y, -a.z); }
+G_FN float v_dot(vec3 a, vec3 b) { return g_fma(a.z, b.z, g_fma(a.y, b.y, a.x * b.x)); }
+G_FN float v_length(vec3 a) { return g_sqrt(v_dot(a, a)); }
+G_FN vec3 v_normalize(vec3 a) { return v_scale(a, g_rcp(g_sqrt(v_dot(a, a)))); }
+G_FN vec3 v_mix(vec3 a, vec3 b, float t)
 {
     return v3(g_mix(a.x, b.x, t), g_mix(a.y, b.y, t), g_mix(a.z, b.z, t));
 }
 /* reflect(I,N) = I - 2*dot(N,I)*N */
-static inline vec3 v_reflect(vec3 I, vec3 N)
+G_FN vec3 v_reflect(vec3 I, vec3 N)
 {
     float k = 2.0f * v_dot(N, I);
     return v3(I.x - k * N.x, I.y - k * N.y, I.z - k * N.z);
 }
 /* refract(I,N,eta): k = 1 - eta*eta*(1 - dot(N,I)^2); k<0 -> 0; else eta*I - (eta*dot(N,I)+sqrt(k))*N */
-static inline vec3 v_refract(vec3 I, vec3 N, float eta)
+G_FN vec3 v_refract(vec3 I, vec3 N, float eta)
 {
     float d = v_dot(N, I);
     float k = 1.0f - (eta * eta) * (1.0f - d * d);
@@ -124,7 +142,7 @@ static inline vec3 v_refract(vec3 I, vec3 N, float eta)
     return v3(eta * I.x - s * N.x, eta * I.y - s * N.y, eta * I.z - s * N.z);
 }
 /* (M * v).row r for a column-major mat4 stored as 16 floats (GLSL std140 / OpenTK row-major bytes). */
-static inline float m4_row(const float *M, int r, float x, float y, float z, float w)
+G_FN float m4_row(const float *M, int r, float x, float y, float z, float w)
 {
     float acc = M[0 + r] * x;
     acc = g_fma(M[4 + r], y, acc);
@@ -138,7 +156,7 @@ static inline float m4_row(const float *M, int r, float x, float y, float z, flo
 
 /* sin and cos of x by Cody-Waite reduction to [-pi/4, pi/4] (three-term pi/2) and the
  * classic single-precision minimax kernels.  Exact same operation sequence on both sides. */
-static inline void g_sincos(float x, float *s_out, float *c_out)
+G_FN void g_sincos(float x, float *s_out, float *c_out)
 {
     float t = g_fma(x, 0.636619747f, G_MAGIC);       /* x * 2/pi, rounded to integer */
     float q = t - G_MAGIC;
@@ -162,11 +180,11 @@ static inline void g_sincos(float x, float *s_out, float *c_out)
     *s_out = s;
     *c_out = c;
 }
-static inline float g_sin(float x) { float s, c; g_sincos(x, &s, &c); return s; }
-static inline float g_cos(float x) { float s, c; g_sincos(x, &s, &c); return c; }
+G_FN float g_sin(float x) { float s, c; g_sincos(x, &s, &c); return s; }
+G_FN float g_cos(float x) { float s, c; g_sincos(x, &s, &c); return c; }
 
 /* exp(x): k = rint(x*log2(e)); r = x - k*ln2 (two-term); e^r = 1 + r + r^2*P(r); scale by 2^k in two steps. */
-static inline float g_exp(float x)
+G_FN float g_exp(float x)
 {
     if (g_isnan(x)) return x + x;
     if (x > 88.7228394f) return g_float(0x7f800000u);
@@ -192,7 +210,7 @@ static inline float g_exp(float x)
 
 /* log(x), x > 0: frexp to [sqrt(1/2), sqrt(2)), degree-8 kernel (the classic single-precision coefficients), explicit fma.
  * log(0) = -inf, log(x<0) = NaN.  Used only by pow() in the post-process / sRGB paths. */
-static inline float g_log(float x)
+G_FN float g_log(float x)
 {
     if (g_isnan(x) || x < 0.0f) return g_float(0x7fc00000u);
     if (x == 0.0f) return g_float(0xff800000u);
@@ -221,6 +239,6 @@ static inline float g_log(float x)
     return g_fma(fe, 0.693359375f, r);
 }
 /* pow(x, y) for x >= 0 (GLSL: undefined for x < 0): exp(y * log(x)); pow(0, y > 0) = 0. */
-static inline float g_pow(float x, float y) { return g_exp(y * g_log(x)); }
+G_FN float g_pow(float x, float y) { return g_exp(y * g_log(x)); }
 
 #endif

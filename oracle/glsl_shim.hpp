@@ -35,8 +35,18 @@ extern "C++" {
 }
 }
 
-/* marks what the GLSL declared `uniform` (shared, written by the harness before a dispatch) */
+/* GLSL_UNIFORM marks what the GLSL declared `uniform` (shared, written by the harness before a dispatch); GLSL_FN marks the
+ * shader's functions; GLSL_HD the shim's.  Empty for g++; for nvcc (oracle/build_ref.py --cuda: the same translated text
+ * compiled as the GL-compute proxy) uniforms live in __constant__ memory and every function is __host__ __device__. */
+#ifdef __CUDACC__
+#define GLSL_UNIFORM __constant__
+#define GLSL_FN __device__
+#define GLSL_HD __host__ __device__
+#else
 #define GLSL_UNIFORM
+#define GLSL_FN
+#define GLSL_HD
+#endif
 
 namespace glsl {
 
@@ -46,143 +56,143 @@ typedef unsigned int uint;
 struct Float {
     float v;
     Float() = default;
-    Float(float f) : v(f) {}
-    Float(int i) : v((float)i) {}          /* implicit int -> float (§4.1.10), exact below 2^24 */
-    Float(uint u) : v((float)u) {}         /* float(uint): round to nearest even */
-    explicit operator float() const { return v; }
+    GLSL_HD Float(float f) : v(f) {}
+    GLSL_HD Float(int i) : v((float)i) {}          /* implicit int -> float (§4.1.10), exact below 2^24 */
+    GLSL_HD Float(uint u) : v((float)u) {}         /* float(uint): round to nearest even */
+    GLSL_HD explicit operator float() const { return v; }
 };
-inline Float operator+(Float a, Float b) { return Float(a.v + b.v); }
-inline Float operator-(Float a, Float b) { return Float(a.v - b.v); }
-inline Float operator*(Float a, Float b) { return Float(a.v * b.v); }
+GLSL_HD inline Float operator+(Float a, Float b) { return Float(a.v + b.v); }
+GLSL_HD inline Float operator-(Float a, Float b) { return Float(a.v - b.v); }
+GLSL_HD inline Float operator*(Float a, Float b) { return Float(a.v * b.v); }
 #ifdef GLSL_SHIM_ALT_MODEL
 /* A second, equally admissible evaluation model, used ONLY by tools/model_sensitivity.py to measure how much of the image
  * depends on the choice: IEEE-correct division, libm sinf / cosf / expf / powf, unfused dot / mix / mat*vec. */
 extern "C" { float sinf(float); float cosf(float); float expf(float); float powf(float, float); }
-inline Float operator/(Float a, Float b) { return Float(a.v / b.v); }
+GLSL_HD inline Float operator/(Float a, Float b) { return Float(a.v / b.v); }
 #else
-inline Float operator/(Float a, Float b) { return Float(gm::g_div(a.v, b.v)); }
+GLSL_HD inline Float operator/(Float a, Float b) { return Float(gm::g_div(a.v, b.v)); }
 #endif
-inline Float operator-(Float a) { return Float(-a.v); }
-inline Float &operator+=(Float &a, Float b) { a = a + b; return a; }
-inline Float &operator-=(Float &a, Float b) { a = a - b; return a; }
-inline Float &operator*=(Float &a, Float b) { a = a * b; return a; }
-inline Float &operator/=(Float &a, Float b) { a = a / b; return a; }
-inline bool operator<(Float a, Float b) { return a.v < b.v; }
-inline bool operator>(Float a, Float b) { return a.v > b.v; }
-inline bool operator<=(Float a, Float b) { return a.v <= b.v; }
-inline bool operator>=(Float a, Float b) { return a.v >= b.v; }
-inline bool operator==(Float a, Float b) { return a.v == b.v; }
-inline bool operator!=(Float a, Float b) { return a.v != b.v; }
+GLSL_HD inline Float operator-(Float a) { return Float(-a.v); }
+GLSL_HD inline Float &operator+=(Float &a, Float b) { a = a + b; return a; }
+GLSL_HD inline Float &operator-=(Float &a, Float b) { a = a - b; return a; }
+GLSL_HD inline Float &operator*=(Float &a, Float b) { a = a * b; return a; }
+GLSL_HD inline Float &operator/=(Float &a, Float b) { a = a / b; return a; }
+GLSL_HD inline bool operator<(Float a, Float b) { return a.v < b.v; }
+GLSL_HD inline bool operator>(Float a, Float b) { return a.v > b.v; }
+GLSL_HD inline bool operator<=(Float a, Float b) { return a.v <= b.v; }
+GLSL_HD inline bool operator>=(Float a, Float b) { return a.v >= b.v; }
+GLSL_HD inline bool operator==(Float a, Float b) { return a.v == b.v; }
+GLSL_HD inline bool operator!=(Float a, Float b) { return a.v != b.v; }
 
 struct vec2; struct vec3; struct vec4; struct ivec2; struct ivec3; struct uvec2; struct uvec3; struct bvec3;
 
-struct ivec2 { int x, y; ivec2() = default; ivec2(int a, int b) : x(a), y(b) {} explicit ivec2(const uvec2 &v); };
-struct uvec2 { uint x, y; uvec2() = default; uvec2(uint a, uint b) : x(a), y(b) {} };
+struct ivec2 { int x, y; ivec2() = default; GLSL_HD ivec2(int a, int b) : x(a), y(b) {} GLSL_HD explicit ivec2(const uvec2 &v); };
+struct uvec2 { uint x, y; uvec2() = default; GLSL_HD uvec2(uint a, uint b) : x(a), y(b) {} };
 struct ivec3 {
-    int x, y, z; ivec3() = default; ivec3(int a, int b, int c) : x(a), y(b), z(c) {} explicit ivec3(const uvec3 &v);
-    ivec2 xy() const { return ivec2(x, y); }
+    int x, y, z; ivec3() = default; GLSL_HD ivec3(int a, int b, int c) : x(a), y(b), z(c) {} GLSL_HD explicit ivec3(const uvec3 &v);
+    GLSL_HD ivec2 xy() const { return ivec2(x, y); }
 };
 struct uvec3 {
-    uint x, y, z; uvec3() = default; uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
-    uvec2 xy() const { return uvec2(x, y); }
+    uint x, y, z; uvec3() = default; GLSL_HD uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
+    GLSL_HD uvec2 xy() const { return uvec2(x, y); }
 };
-inline ivec2::ivec2(const uvec2 &v) : x((int)v.x), y((int)v.y) {}
-inline ivec3::ivec3(const uvec3 &v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
+GLSL_HD inline ivec2::ivec2(const uvec2 &v) : x((int)v.x), y((int)v.y) {}
+GLSL_HD inline ivec3::ivec3(const uvec3 &v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
 struct bvec3 { bool x, y, z; };
 
 /* The one-argument "splat" constructors are explicit, as in GLSL (a scalar never converts to a vector implicitly). */
 struct vec2 {
     Float x, y;
     vec2() = default;
-    explicit vec2(Float s) : x(s), y(s) {}
-    vec2(Float a, Float b) : x(a), y(b) {}
-    vec2(const ivec2 &v) : x(v.x), y(v.y) {}                  /* GLSL implicit conversion ivec2 -> vec2 (§4.1.10) */
-    vec2 xy() const { return *this; }
+    GLSL_HD explicit vec2(Float s) : x(s), y(s) {}
+    GLSL_HD vec2(Float a, Float b) : x(a), y(b) {}
+    GLSL_HD vec2(const ivec2 &v) : x(v.x), y(v.y) {}                  /* GLSL implicit conversion ivec2 -> vec2 (§4.1.10) */
+    GLSL_HD vec2 xy() const { return *this; }
 };
 struct vec3 {
     Float x, y, z;
     vec3() = default;
-    explicit vec3(Float s) : x(s), y(s), z(s) {}
-    vec3(Float a, Float b, Float c) : x(a), y(b), z(c) {}
-    explicit vec3(const bvec3 &b) : x(b.x ? 1.0f : 0.0f), y(b.y ? 1.0f : 0.0f), z(b.z ? 1.0f : 0.0f) {}
-    vec2 xy() const { return vec2(x, y); }
-    vec3 xyz() const { return *this; }
-    vec3 rgb() const { return *this; }
+    GLSL_HD explicit vec3(Float s) : x(s), y(s), z(s) {}
+    GLSL_HD vec3(Float a, Float b, Float c) : x(a), y(b), z(c) {}
+    GLSL_HD explicit vec3(const bvec3 &b) : x(b.x ? 1.0f : 0.0f), y(b.y ? 1.0f : 0.0f), z(b.z ? 1.0f : 0.0f) {}
+    GLSL_HD vec2 xy() const { return vec2(x, y); }
+    GLSL_HD vec3 xyz() const { return *this; }
+    GLSL_HD vec3 rgb() const { return *this; }
 };
 /* assignable two-component swizzle (`rayEye.zw = vec2(...)`) */
 struct swz2_ref {
     Float &a, &b;
-    swz2_ref &operator=(const vec2 &v) { a = v.x; b = v.y; return *this; }
-    operator vec2() const { return vec2(a, b); }
+    GLSL_HD swz2_ref &operator=(const vec2 &v) { a = v.x; b = v.y; return *this; }
+    GLSL_HD operator vec2() const { return vec2(a, b); }
 };
 struct vec4 {
     Float x, y, z, w;
     vec4() = default;
-    explicit vec4(Float s) : x(s), y(s), z(s), w(s) {}
-    vec4(Float a, Float b, Float c, Float d) : x(a), y(b), z(c), w(d) {}
-    vec4(const vec2 &v, Float c, Float d) : x(v.x), y(v.y), z(c), w(d) {}
-    vec4(const vec3 &v, Float d) : x(v.x), y(v.y), z(v.z), w(d) {}
-    vec2 xy() const { return vec2(x, y); }
-    vec3 xyz() const { return vec3(x, y, z); }
-    vec3 rgb() const { return vec3(x, y, z); }
-    swz2_ref zw() { return swz2_ref{ z, w }; }
+    GLSL_HD explicit vec4(Float s) : x(s), y(s), z(s), w(s) {}
+    GLSL_HD vec4(Float a, Float b, Float c, Float d) : x(a), y(b), z(c), w(d) {}
+    GLSL_HD vec4(const vec2 &v, Float c, Float d) : x(v.x), y(v.y), z(c), w(d) {}
+    GLSL_HD vec4(const vec3 &v, Float d) : x(v.x), y(v.y), z(v.z), w(d) {}
+    GLSL_HD vec2 xy() const { return vec2(x, y); }
+    GLSL_HD vec3 xyz() const { return vec3(x, y, z); }
+    GLSL_HD vec3 rgb() const { return vec3(x, y, z); }
+    GLSL_HD swz2_ref zw() { return swz2_ref{ z, w }; }
 };
 
 /* ---- arithmetic: component-wise on Float (so `/` is a * rcp(b) everywhere) ----------------------------------------- */
 #define GLSL_SHIM_OP(OP)                                                                                              \
-    inline vec2 operator OP(const vec2 &a, const vec2 &b) { return vec2(a.x OP b.x, a.y OP b.y); }                    \
-    inline vec2 operator OP(const vec2 &a, Float b) { return vec2(a.x OP b, a.y OP b); }                              \
-    inline vec2 operator OP(Float a, const vec2 &b) { return vec2(a OP b.x, a OP b.y); }                              \
-    inline vec3 operator OP(const vec3 &a, const vec3 &b) { return vec3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }        \
-    inline vec3 operator OP(const vec3 &a, Float b) { return vec3(a.x OP b, a.y OP b, a.z OP b); }                    \
-    inline vec3 operator OP(Float a, const vec3 &b) { return vec3(a OP b.x, a OP b.y, a OP b.z); }                    \
-    inline vec4 operator OP(const vec4 &a, const vec4 &b) { return vec4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
-    inline vec4 operator OP(const vec4 &a, Float b) { return vec4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); }          \
-    inline vec4 operator OP(Float a, const vec4 &b) { return vec4(a OP b.x, a OP b.y, a OP b.z, a OP b.w); }
+    GLSL_HD inline vec2 operator OP(const vec2 &a, const vec2 &b) { return vec2(a.x OP b.x, a.y OP b.y); }                    \
+    GLSL_HD inline vec2 operator OP(const vec2 &a, Float b) { return vec2(a.x OP b, a.y OP b); }                              \
+    GLSL_HD inline vec2 operator OP(Float a, const vec2 &b) { return vec2(a OP b.x, a OP b.y); }                              \
+    GLSL_HD inline vec3 operator OP(const vec3 &a, const vec3 &b) { return vec3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }        \
+    GLSL_HD inline vec3 operator OP(const vec3 &a, Float b) { return vec3(a.x OP b, a.y OP b, a.z OP b); }                    \
+    GLSL_HD inline vec3 operator OP(Float a, const vec3 &b) { return vec3(a OP b.x, a OP b.y, a OP b.z); }                    \
+    GLSL_HD inline vec4 operator OP(const vec4 &a, const vec4 &b) { return vec4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
+    GLSL_HD inline vec4 operator OP(const vec4 &a, Float b) { return vec4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); }          \
+    GLSL_HD inline vec4 operator OP(Float a, const vec4 &b) { return vec4(a OP b.x, a OP b.y, a OP b.z, a OP b.w); }
 GLSL_SHIM_OP(+) GLSL_SHIM_OP(-) GLSL_SHIM_OP(*) GLSL_SHIM_OP(/)
 
-inline vec2 operator-(const vec2 &a) { return vec2(-a.x, -a.y); }
-inline vec3 operator-(const vec3 &a) { return vec3(-a.x, -a.y, -a.z); }
-inline vec4 operator-(const vec4 &a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
+GLSL_HD inline vec2 operator-(const vec2 &a) { return vec2(-a.x, -a.y); }
+GLSL_HD inline vec3 operator-(const vec3 &a) { return vec3(-a.x, -a.y, -a.z); }
+GLSL_HD inline vec4 operator-(const vec4 &a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
 
 /* compound assignment: `a op= b` is `a = a op b` (GLSL §5.8) */
 #define GLSL_SHIM_COMPOUND(T)                                                                                        \
-    inline T &operator+=(T &a, const T &b) { a = a + b; return a; }                                                 \
-    inline T &operator-=(T &a, const T &b) { a = a - b; return a; }                                                 \
-    inline T &operator*=(T &a, const T &b) { a = a * b; return a; }                                                 \
-    inline T &operator/=(T &a, const T &b) { a = a / b; return a; }                                                 \
-    inline T &operator+=(T &a, Float b) { a = a + b; return a; }                                                    \
-    inline T &operator-=(T &a, Float b) { a = a - b; return a; }                                                    \
-    inline T &operator*=(T &a, Float b) { a = a * b; return a; }                                                    \
-    inline T &operator/=(T &a, Float b) { a = a / b; return a; }
+    GLSL_HD inline T &operator+=(T &a, const T &b) { a = a + b; return a; }                                                 \
+    GLSL_HD inline T &operator-=(T &a, const T &b) { a = a - b; return a; }                                                 \
+    GLSL_HD inline T &operator*=(T &a, const T &b) { a = a * b; return a; }                                                 \
+    GLSL_HD inline T &operator/=(T &a, const T &b) { a = a / b; return a; }                                                 \
+    GLSL_HD inline T &operator+=(T &a, Float b) { a = a + b; return a; }                                                    \
+    GLSL_HD inline T &operator-=(T &a, Float b) { a = a - b; return a; }                                                    \
+    GLSL_HD inline T &operator*=(T &a, Float b) { a = a * b; return a; }                                                    \
+    GLSL_HD inline T &operator/=(T &a, Float b) { a = a / b; return a; }
 GLSL_SHIM_COMPOUND(vec2) GLSL_SHIM_COMPOUND(vec3) GLSL_SHIM_COMPOUND(vec4)
 
 /* ---- built-in functions (GLSL 4.50 §8) ------------------------------------------------------------------------------ */
-inline Float abs(Float a) { return gm::g_abs(a.v); }
-inline Float sign(Float a) { return gm::g_sign(a.v); }
-inline Float sqrt(Float a) { return gm::g_sqrt(a.v); }
+GLSL_HD inline Float abs(Float a) { return gm::g_abs(a.v); }
+GLSL_HD inline Float sign(Float a) { return gm::g_sign(a.v); }
+GLSL_HD inline Float sqrt(Float a) { return gm::g_sqrt(a.v); }
 #ifdef GLSL_SHIM_ALT_MODEL
-inline Float sin(Float a) { return ::glsl::sinf(a.v); }
-inline Float cos(Float a) { return ::glsl::cosf(a.v); }
-inline Float exp(Float a) { return ::glsl::expf(a.v); }
+GLSL_HD inline Float sin(Float a) { return ::glsl::sinf(a.v); }
+GLSL_HD inline Float cos(Float a) { return ::glsl::cosf(a.v); }
+GLSL_HD inline Float exp(Float a) { return ::glsl::expf(a.v); }
 #else
-inline Float sin(Float a) { return gm::g_sin(a.v); }
-inline Float cos(Float a) { return gm::g_cos(a.v); }
-inline Float exp(Float a) { return gm::g_exp(a.v); }
+GLSL_HD inline Float sin(Float a) { return gm::g_sin(a.v); }
+GLSL_HD inline Float cos(Float a) { return gm::g_cos(a.v); }
+GLSL_HD inline Float exp(Float a) { return gm::g_exp(a.v); }
 #endif
-inline Float min(Float a, Float b) { return gm::g_min(a.v, b.v); }
-inline Float max(Float a, Float b) { return gm::g_max(a.v, b.v); }
-inline Float step(Float edge, Float x) { return gm::g_step(edge.v, x.v); }
+GLSL_HD inline Float min(Float a, Float b) { return gm::g_min(a.v, b.v); }
+GLSL_HD inline Float max(Float a, Float b) { return gm::g_max(a.v, b.v); }
+GLSL_HD inline Float step(Float edge, Float x) { return gm::g_step(edge.v, x.v); }
 #ifdef GLSL_SHIM_ALT_MODEL
-inline Float fma_(Float a, Float b, Float c) { return a * b + c; }
+GLSL_HD inline Float fma_(Float a, Float b, Float c) { return a * b + c; }
 #else
-inline Float fma_(Float a, Float b, Float c) { return gm::g_fma(a.v, b.v, c.v); }
+GLSL_HD inline Float fma_(Float a, Float b, Float c) { return gm::g_fma(a.v, b.v, c.v); }
 #endif
 /* mix(x, y, a) = x*(1-a) + y*a, the y*a product fused into the sum */
-inline Float mix(Float x, Float y, Float a) { return fma_(y, a, x * (Float(1.0f) - a)); }
-inline Float clamp(Float x, Float lo, Float hi) { return min(max(x, lo), hi); }
+GLSL_HD inline Float mix(Float x, Float y, Float a) { return fma_(y, a, x * (Float(1.0f) - a)); }
+GLSL_HD inline Float clamp(Float x, Float lo, Float hi) { return min(max(x, lo), hi); }
 /* pow with the constant exponents the shaders use is strength-reduced as the model states; otherwise exp(y*log(x)). */
-inline Float pow(Float x, Float y)
+GLSL_HD inline Float pow(Float x, Float y)
 {
 #ifdef GLSL_SHIM_ALT_MODEL
     return ::glsl::powf(x.v, y.v);
@@ -193,23 +203,23 @@ inline Float pow(Float x, Float y)
 #endif
 }
 
-inline vec3 exp(const vec3 &a) { return vec3(exp(a.x), exp(a.y), exp(a.z)); }
-inline vec3 min(const vec3 &a, const vec3 &b) { return vec3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); }
-inline vec3 max(const vec3 &a, const vec3 &b) { return vec3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
-inline vec3 pow(const vec3 &a, const vec3 &b) { return vec3(pow(a.x, b.x), pow(a.y, b.y), pow(a.z, b.z)); }
-inline vec3 clamp(const vec3 &v, Float lo, Float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
-inline vec3 mix(const vec3 &x, const vec3 &y, Float a) { return vec3(mix(x.x, y.x, a), mix(x.y, y.y, a), mix(x.z, y.z, a)); }
-inline vec3 mix(const vec3 &x, const vec3 &y, const vec3 &a) { return vec3(mix(x.x, y.x, a.x), mix(x.y, y.y, a.y), mix(x.z, y.z, a.z)); }
-inline bvec3 lessThan(const vec3 &a, const vec3 &b) { return bvec3{ a.x < b.x, a.y < b.y, a.z < b.z }; }
+GLSL_HD inline vec3 exp(const vec3 &a) { return vec3(exp(a.x), exp(a.y), exp(a.z)); }
+GLSL_HD inline vec3 min(const vec3 &a, const vec3 &b) { return vec3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); }
+GLSL_HD inline vec3 max(const vec3 &a, const vec3 &b) { return vec3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
+GLSL_HD inline vec3 pow(const vec3 &a, const vec3 &b) { return vec3(pow(a.x, b.x), pow(a.y, b.y), pow(a.z, b.z)); }
+GLSL_HD inline vec3 clamp(const vec3 &v, Float lo, Float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+GLSL_HD inline vec3 mix(const vec3 &x, const vec3 &y, Float a) { return vec3(mix(x.x, y.x, a), mix(x.y, y.y, a), mix(x.z, y.z, a)); }
+GLSL_HD inline vec3 mix(const vec3 &x, const vec3 &y, const vec3 &a) { return vec3(mix(x.x, y.x, a.x), mix(x.y, y.y, a.y), mix(x.z, y.z, a.z)); }
+GLSL_HD inline bvec3 lessThan(const vec3 &a, const vec3 &b) { return bvec3{ a.x < b.x, a.y < b.y, a.z < b.z }; }
 
 /* dot = FMUL, FFMA, FFMA */
-inline Float dot(const vec3 &a, const vec3 &b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
-inline Float length(const vec3 &a) { return sqrt(dot(a, a)); }
-inline vec3 normalize(const vec3 &a) { return a * (Float(1.0f) / sqrt(dot(a, a))); }
+GLSL_HD inline Float dot(const vec3 &a, const vec3 &b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
+GLSL_HD inline Float length(const vec3 &a) { return sqrt(dot(a, a)); }
+GLSL_HD inline vec3 normalize(const vec3 &a) { return a * (Float(1.0f) / sqrt(dot(a, a))); }
 /* §8.5: reflect = I - 2.0 * dot(N, I) * N */
-inline vec3 reflect(const vec3 &I, const vec3 &N) { return I - Float(2.0f) * dot(N, I) * N; }
+GLSL_HD inline vec3 reflect(const vec3 &I, const vec3 &N) { return I - Float(2.0f) * dot(N, I) * N; }
 /* §8.5: k = 1.0 - eta * eta * (1.0 - dot(N, I) * dot(N, I)); k < 0 ? 0 : eta * I - (eta * dot(N, I) + sqrt(k)) * N */
-inline vec3 refract(const vec3 &I, const vec3 &N, Float eta)
+GLSL_HD inline vec3 refract(const vec3 &I, const vec3 &N, Float eta)
 {
     Float d = dot(N, I);
     Float k = Float(1.0f) - eta * eta * (Float(1.0f) - d * d);
@@ -219,7 +229,7 @@ inline vec3 refract(const vec3 &I, const vec3 &N, Float eta)
 
 /* column-major 4x4 (std140 memory order); M * v per row as an fma chain over the columns */
 struct mat4 { float c[4][4]; };
-inline vec4 operator*(const mat4 &M, const vec4 &v)
+GLSL_HD inline vec4 operator*(const mat4 &M, const vec4 &v)
 {
     Float r[4];
     for (int i = 0; i < 4; i++) {
@@ -234,22 +244,22 @@ inline vec4 operator*(const mat4 &M, const vec4 &v)
 
 /* ---- images ------------------------------------------------------------------------------------------------------------ */
 struct image2D { float *texels; int width, height; };       /* rgba32f, row 0 = y 0 */
-inline ivec2 imageSize(const image2D &im) { return ivec2(im.width, im.height); }
-inline vec4 imageLoad(const image2D &im, const ivec2 &p)
+GLSL_HD inline ivec2 imageSize(const image2D &im) { return ivec2(im.width, im.height); }
+GLSL_HD inline vec4 imageLoad(const image2D &im, const ivec2 &p)
 {
     if (p.x < 0 || p.y < 0 || p.x >= im.width || p.y >= im.height) return vec4(Float(0.0f));      /* OOB load -> 0 */
     const float *t = im.texels + ((size_t)p.y * im.width + p.x) * 4;
     return vec4(t[0], t[1], t[2], t[3]);
 }
-inline void imageStore(image2D &im, const ivec2 &p, const vec4 &v)
+GLSL_HD inline void imageStore(const image2D &im, const ivec2 &p, const vec4 &v)
 {
     if (p.x < 0 || p.y < 0 || p.x >= im.width || p.y >= im.height) return;                 /* OOB store discarded */
     float *t = im.texels + ((size_t)p.y * im.width + p.x) * 4;
     t[0] = v.x.v; t[1] = v.y.v; t[2] = v.z.v; t[3] = v.w.v;
 }
 struct imageCube { float *texels; int size; };               /* 6 layers (+X,-X,+Y,-Y,+Z,-Z) of size x size rgba32f */
-inline ivec2 imageSize(const imageCube &im) { return ivec2(im.size, im.size); }
-inline void imageStore(imageCube &im, const ivec3 &p, const vec4 &v)
+GLSL_HD inline ivec2 imageSize(const imageCube &im) { return ivec2(im.size, im.size); }
+GLSL_HD inline void imageStore(const imageCube &im, const ivec3 &p, const vec4 &v)
 {
     if (p.x < 0 || p.y < 0 || p.z < 0 || p.x >= im.size || p.y >= im.size || p.z >= 6) return;
     float *t = im.texels + (((size_t)p.z * im.size + p.y) * im.size + p.x) * 4;
@@ -259,7 +269,7 @@ inline void imageStore(imageCube &im, const ivec3 &p, const vec4 &v)
 /* ---- sampler2D: only ever sampled 1:1 at texel centres by the full-screen post-process pass (NEAREST == LINEAR there);
  * an unbound unit (texels == nullptr) returns (0,0,0,1) ------------------------------------------------------------------- */
 struct sampler2D { const float *texels; int width, height; };
-inline vec4 texture(const sampler2D &s, const vec2 &uv)
+GLSL_HD inline vec4 texture(const sampler2D &s, const vec2 &uv)
 {
     if (!s.texels) return vec4(0.0f, 0.0f, 0.0f, 1.0f);
     int i = gm::g_f2i(gm::g_floor(uv.x.v * (float)s.width)), j = gm::g_f2i(gm::g_floor(uv.y.v * (float)s.height));
@@ -272,13 +282,18 @@ inline vec4 texture(const sampler2D &s, const vec2 &uv)
 /* ---- samplerCube: the GL texture unit, not shader code.  OpenGL 4.5 §8.13 Table 8.19 face selection, LOD 0 => LINEAR
  * (AtmosphericScatterer.cs:67-69), GL_TEXTURE_CUBE_MAP_SEAMLESS (MainWindow.cs:168).  Written independently of
  * pt_oracle.c's lattice walk: every face is padded once with a one-texel border fetched through the 3-D position of the
- * border texel's centre, then a lookup is four taps + three lerps.  Model choices shared with DESIGN.md §2:
- * s = 0.5 * (sc / |ma| + 1), u = s * N - 0.5, weights = fract, lerp = mix(); a corner border texel is the mean of the
- * three texels meeting at that cube corner (sum in face order, times fl(1/3)); a non-finite or zero direction fetches 0. */
+ * border texel's centre (CubePadder, host side), then a lookup is four taps + three lerps.  Model choices shared with
+ * s = 0.5 * (sc / |ma| + 1), u = s * N - 0.5, weights = fract, lerp = mix(); a corner border texel is the mean of
+ * the three texels meeting at that cube corner (sum in face order, times fl(1/3)); a non-finite or zero direction fetches 0. */
 struct samplerCube {
+    int size;
+    const float *padded;         /* [6][size+2][size+2][4], host or device memory */
+    GLSL_HD const float *at(int f, int i, int j) const { return padded + ((((size_t)f * (size + 2)) + (j + 1)) * (size + 2) + (i + 1)) * 4; }
+};
+/* builds the padded faces on the host */
+struct CubePadder {
     int size = 0;
-    std::vector<float> padded;   /* [6][size+2][size+2][4] */
-    const float *at(int f, int i, int j) const { return &padded[((((size_t)f * (size + 2)) + (j + 1)) * (size + 2) + (i + 1)) * 4]; }
+    std::vector<float> padded;
     float *at(int f, int i, int j) { return &padded[((((size_t)f * (size + 2)) + (j + 1)) * (size + 2) + (i + 1)) * 4]; }
 
     /* Table 8.19 as integer frames: a point of face f is major*N + U*a + V*b with a = 2i+1-N, b = 2j+1-N */
@@ -303,7 +318,7 @@ struct samplerCube {
         }
         *f = 0; *i = 0; *j = 0;
     }
-    void upload(const float *faces, int N)
+    samplerCube upload(const float *faces, int N)
     {
         size = N;
         padded.assign((size_t)6 * (N + 2) * (N + 2) * 4, 0.0f);
@@ -350,9 +365,10 @@ struct samplerCube {
                     }
                 }
         }
+        return samplerCube{ N, padded.data() };
     }
 };
-inline vec4 texture(const samplerCube &s, const vec3 &dir)
+GLSL_HD inline vec4 texture(const samplerCube &s, const vec3 &dir)
 {
     const float FMAX = 3.4028235e+38f;
     const float rx = dir.x.v, ry = dir.y.v, rz = dir.z.v;
@@ -377,9 +393,6 @@ inline vec4 texture(const samplerCube &s, const vec3 &dir)
         out[c] = gm::g_mix(gm::g_mix(t00[c], t10[c], wa), gm::g_mix(t01[c], t11[c], wa), wb);
     return vec4(out[0], out[1], out[2], out[3]);
 }
-
-/* ---- per-invocation built-in variables ------------------------------------------------------------------------------------ */
-inline thread_local uvec3 gl_GlobalInvocationID;
 
 } /* namespace glsl */
 #endif

@@ -47,18 +47,23 @@ def _render_both(O, R, image_o, image_r, basic, ubo, env, **kw):
 def test_translation_rules():
     """The lexical rewrites, on snippets written here (no reference text needed)."""
     from oracle.build_ref import translate
-    t = translate("#version 450 core\nuniform float k;\nfloat f(inout vec3 v, out float o) { o = 2.0 * v.xyz.x / 3e2; return vec3(1, 2.5, 0).x; }\n", "t")
+    t = translate("#version 450 core\nuniform float k;\nfloat f(inout vec3 v, out float o);\nfloat f(inout vec3 v, out float o) { o = 2.0 * v.xyz.x / 3e2; return vec3(1, 2.5, 0).x; }\n", "t")
     assert "#version" not in t
-    assert "GLSL_UNIFORM Float k;" in t
-    assert "vec3& v" in t and "Float& o" in t
+    assert "GLSL_UNIFORM Float k;" in t and t.index("GLSL_UNIFORM Float k;") < t.index("struct Invocation {")     # uniforms stay shared
+    assert t.count("Float f(") == 1 and "GLSL_FN Float f(vec3& v, Float& o)" in t                                  # prototype dropped, definition is a member
     assert "Float(2.0f)" in t and "Float(3e2f)" in t
     assert ".xyz().x" in t
     assert "vec3{1, Float(2.5f), 0}" in t
-    t = translate("layout(std140, binding = 1) uniform Blk\n{\n mat4[6] M;\n} blk;\nuint seed;\nvoid main() { }\n", "t")
-    assert "struct Blk" in t and "mat4 M[6];" in t and "thread_local uint seed;" in t and "void glsl_main()" in t
+    t = translate("layout(std140, binding = 1) uniform Blk\n{\n mat4[6] M;\n} blk;\nuint seed;\nstruct S { int a; };\nvoid main() { }\n", "t")
+    shared, members = t.split("struct Invocation {")
+    assert "GLSL_UNIFORM struct Blk" in shared and "mat4 M[6];" in shared and "struct S" in shared
+    assert "uint seed;" in members and "GLSL_FN void glsl_main()" in members and "gl_GlobalInvocationID" in members
+    t = translate("layout(location = 0) out vec4 FragColor;\nin InOutVars\n{\n vec2 TexCoord;\n} inData;\nvoid main() { FragColor = vec4(inData.TexCoord, 0.0, 1.0); }\n", "t")
+    members = t.split("struct Invocation {")[1]
+    assert "vec4 FragColor;" in members and "struct InOutVars" in members and "} inData;" in members
     # R11's safety net: an argument list whose evaluation order C++ would not fix must be refused, not guessed
     with pytest.raises(RuntimeError):
-        translate("float g(float a, float b);\nvoid main() { float x = g(GetRandomFloat01(), GetRandomFloat01()); }\n", "t")
+        translate("void main() { float x = g(GetRandomFloat01(), GetRandomFloat01()); }\n", "t")
     with pytest.raises(RuntimeError):
         translate("void main() { float x = GetRandomFloat01() - GetRandomFloat01(); }\n", "t")
     # ... while the constructor form the reference uses is accepted (braces order it)
