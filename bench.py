@@ -458,6 +458,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(pt)
+        line["gl_proxy"] = gl_proxy()
     if tiled is not None and fused:
         tiled.exchange_ok()
     if shared is not None:
@@ -488,6 +489,25 @@ def cpu_baseline(pt):
     dt = time.perf_counter() - t0
     return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": O_.max_threads(), "kind": kind,
             "sample": f"{frames} full 1920x1080 frames at SPP 1 ({dt:.1f} s), OpenMP over rows"}
+
+
+def gl_proxy():
+    """The reference's compute.glsl compiled by nvcc and dispatched in the reference's launch shape on this GPU
+    (tools/gl_proxy_probe.py; oracle/build_ref.py --cuda).  Runs in a subprocess after all timed regions: whatever happens
+    there cannot disturb the bench.  Reported next to our numbers; not a parity path, not the optimisation target."""
+    import subprocess
+    from oracle import build_ref
+    if not (os.path.exists(build_ref.cuda_lib(False)) or os.path.exists(build_ref.cuda_lib(True))):
+        return {"unavailable": "oracle/_ref/libglsl_ref_cuda*.so not built (python oracle/build_ref.py --cuda [--fast], needs /root/reference)"}
+    try:
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gl_proxy_probe.py"), "--frames", "20"], capture_output=True,
+                             text=True, timeout=120)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"error": f"probe exited with {res.returncode}: {res.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as exc:      # noqa: BLE001
+        return {"error": str(exc)}
 
 
 def main():

@@ -296,6 +296,53 @@ def build(reference: str = "/root/reference", keep: bool = False, verbose: bool 
     return lib_out
 
 
+def cuda_lib(fast: bool = False, capacity=None) -> str:
+    tag = ("_fast" if fast else "") + (f"_{int(capacity[0])}x{int(capacity[1])}" if capacity is not None else "")
+    return os.path.join(OUT_DIR, f"libglsl_ref_cuda{tag}.so")
+
+
+def build_cuda(reference: str = "/root/reference", fast: bool = False, capacity=None, verbose: bool = False) -> str:
+    """The same translated compute.glsl, compiled by nvcc for sm_100a and dispatched in the reference's own launch shape
+    (oracle/ref_harness_pt_cuda.inc): the GL-compute proxy built from the reference's source.  fast=False: the evaluation
+    model of glsl_model.h (-fmad=false), must equal the oracle bit for bit.  fast=True: -use_fast_math + MUFU built-ins +
+    contraction, roughly a GL driver's code generation; timing only."""
+    path = shader_paths(reference)["pt"]
+    os.makedirs(OUT_DIR, exist_ok=True)
+    out = cuda_lib(fast, capacity)
+    tmp = tempfile.mkdtemp(prefix="glsl_ref_cuda_")
+    try:
+        with open(path, "r", encoding="utf-8-sig") as f:
+            text = translate(f.read(), SHADERS["pt"][0], capacity)
+        gen = os.path.join(tmp, "pt_translated.inc")
+        with open(gen, "w") as f:
+            f.write(text)
+        tu = os.path.join(tmp, "pt.cu")
+        with open(tu, "w") as f:
+            f.write('#include <cstdio>\n#include "glsl_shim.hpp"\nnamespace glsl { namespace pt {\n'
+                    f'#include "{gen}"\n' "}}\n" '#include "ref_harness_pt_cuda.inc"\n')
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+               "-cudart", "static", "-I", HERE]
+        cmd += ["-use_fast_math", "-DGLSL_SHIM_FAST_GPU"] if fast else ["-fmad=false"]
+        if capacity is not None:
+            cmd += ["-DGLSL_UNIFORM_DEVICE"]
+        cmd += ["-o", out, tu]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd))
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--reference", default="/root/reference")
@@ -303,5 +350,10 @@ if __name__ == "__main__":
     ap.add_argument("-v", "--verbose", action="store_true")
     ap.add_argument("--alt-model", action="store_true", help="build libglsl_ref_alt.so (second evaluation model, for tools/model_sensitivity.py)")
     ap.add_argument("--capacity", type=int, nargs=2, metavar=("SPHERES", "CUBOIDS"), help="R13: build libglsl_ref_<S>x<C>.so with larger UBO arrays (BASELINE config 3)")
+    ap.add_argument("--cuda", action="store_true", help="compile compute.glsl with nvcc instead (libglsl_ref_cuda[_fast].so, the GL-compute proxy)")
+    ap.add_argument("--fast", action="store_true", help="with --cuda: -use_fast_math + MUFU built-ins (timing only)")
     a = ap.parse_args()
-    print(build(a.reference, a.keep, a.verbose, a.alt_model, a.capacity))
+    if a.cuda:
+        print(build_cuda(a.reference, a.fast, a.capacity, a.verbose))
+    else:
+        print(build(a.reference, a.keep, a.verbose, a.alt_model, a.capacity))

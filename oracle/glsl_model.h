@@ -47,7 +47,7 @@
  * GPU (oracle/build_ref.py --cuda compiles the reference's shaders with nvcc as the GL-compute proxy).  With nvcc's
  * defaults (-prec-div=true -prec-sqrt=true) and -fmad=false, 1.0f / b, sqrtf and fmaf round exactly as on the host. */
 #ifdef __CUDACC__
-#define G_FN G_FN __host__ __device__
+#define G_FN static inline __host__ __device__
 #else
 #define G_FN static inline
 #endif

@@ -39,7 +39,11 @@ extern "C++" {
  * shader's functions; GLSL_HD the shim's.  Empty for g++; for nvcc (oracle/build_ref.py --cuda: the same translated text
  * compiled as the GL-compute proxy) uniforms live in __constant__ memory and every function is __host__ __device__. */
 #ifdef __CUDACC__
+#ifdef GLSL_UNIFORM_DEVICE              /* uniform blocks too large for the 64 KB constant bank (--capacity builds) */
+#define GLSL_UNIFORM __device__
+#else
 #define GLSL_UNIFORM __constant__
+#endif
 #define GLSL_FN __device__
 #define GLSL_HD __host__ __device__
 #else
@@ -64,7 +68,11 @@ struct Float {
 GLSL_HD inline Float operator+(Float a, Float b) { return Float(a.v + b.v); }
 GLSL_HD inline Float operator-(Float a, Float b) { return Float(a.v - b.v); }
 GLSL_HD inline Float operator*(Float a, Float b) { return Float(a.v * b.v); }
-#ifdef GLSL_SHIM_ALT_MODEL
+#if defined(GLSL_SHIM_FAST_GPU) && defined(__CUDA_ARCH__)
+/* Timing-only model for the nvcc build with -use_fast_math: approximate division and MUFU transcendentals, contraction left
+ * to the compiler — roughly what a GL driver's compiler emits for this shader.  Never a parity reference. */
+GLSL_HD inline Float operator/(Float a, Float b) { return Float(__fdividef(a.v, b.v)); }
+#elif defined(GLSL_SHIM_ALT_MODEL)
 /* A second, equally admissible evaluation model, used ONLY by tools/model_sensitivity.py to measure how much of the image
  * depends on the choice: IEEE-correct division, libm sinf / cosf / expf / powf, unfused dot / mix / mat*vec. */
 extern "C" { float sinf(float); float cosf(float); float expf(float); float powf(float, float); }
@@ -171,7 +179,11 @@ GLSL_SHIM_COMPOUND(vec2) GLSL_SHIM_COMPOUND(vec3) GLSL_SHIM_COMPOUND(vec4)
 GLSL_HD inline Float abs(Float a) { return gm::g_abs(a.v); }
 GLSL_HD inline Float sign(Float a) { return gm::g_sign(a.v); }
 GLSL_HD inline Float sqrt(Float a) { return gm::g_sqrt(a.v); }
-#ifdef GLSL_SHIM_ALT_MODEL
+#if defined(GLSL_SHIM_FAST_GPU) && defined(__CUDA_ARCH__)
+GLSL_HD inline Float sin(Float a) { return __sinf(a.v); }
+GLSL_HD inline Float cos(Float a) { return __cosf(a.v); }
+GLSL_HD inline Float exp(Float a) { return __expf(a.v); }
+#elif defined(GLSL_SHIM_ALT_MODEL)
 GLSL_HD inline Float sin(Float a) { return ::glsl::sinf(a.v); }
 GLSL_HD inline Float cos(Float a) { return ::glsl::cosf(a.v); }
 GLSL_HD inline Float exp(Float a) { return ::glsl::expf(a.v); }
@@ -183,7 +195,7 @@ GLSL_HD inline Float exp(Float a) { return gm::g_exp(a.v); }
 GLSL_HD inline Float min(Float a, Float b) { return gm::g_min(a.v, b.v); }
 GLSL_HD inline Float max(Float a, Float b) { return gm::g_max(a.v, b.v); }
 GLSL_HD inline Float step(Float edge, Float x) { return gm::g_step(edge.v, x.v); }
-#ifdef GLSL_SHIM_ALT_MODEL
+#if defined(GLSL_SHIM_ALT_MODEL) || (defined(GLSL_SHIM_FAST_GPU) && defined(__CUDA_ARCH__))
 GLSL_HD inline Float fma_(Float a, Float b, Float c) { return a * b + c; }
 #else
 GLSL_HD inline Float fma_(Float a, Float b, Float c) { return gm::g_fma(a.v, b.v, c.v); }
@@ -194,7 +206,9 @@ GLSL_HD inline Float clamp(Float x, Float lo, Float hi) { return min(max(x, lo),
 /* pow with the constant exponents the shaders use is strength-reduced as the model states; otherwise exp(y*log(x)). */
 GLSL_HD inline Float pow(Float x, Float y)
 {
-#ifdef GLSL_SHIM_ALT_MODEL
+#if defined(GLSL_SHIM_FAST_GPU) && defined(__CUDA_ARCH__)
+    return __powf(x.v, y.v);
+#elif defined(GLSL_SHIM_ALT_MODEL)
     return ::glsl::powf(x.v, y.v);
 #else
     if (y.v == 5.0f) { Float x2 = x * x; Float x4 = x2 * x2; return x4 * x; }
@@ -215,7 +229,11 @@ GLSL_HD inline bvec3 lessThan(const vec3 &a, const vec3 &b) { return bvec3{ a.x 
 /* dot = FMUL, FFMA, FFMA */
 GLSL_HD inline Float dot(const vec3 &a, const vec3 &b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
 GLSL_HD inline Float length(const vec3 &a) { return sqrt(dot(a, a)); }
+#if defined(GLSL_SHIM_FAST_GPU) && defined(__CUDA_ARCH__)
+GLSL_HD inline vec3 normalize(const vec3 &a) { return a * Float(rsqrtf(dot(a, a).v)); }
+#else
 GLSL_HD inline vec3 normalize(const vec3 &a) { return a * (Float(1.0f) / sqrt(dot(a, a))); }
+#endif
 /* §8.5: reflect = I - 2.0 * dot(N, I) * N */
 GLSL_HD inline vec3 reflect(const vec3 &I, const vec3 &N) { return I - Float(2.0f) * dot(N, I) * N; }
 /* §8.5: k = 1.0 - eta * eta * (1.0 - dot(N, I) * dot(N, I)); k < 0 ? 0 : eta * I - (eta * dot(N, I) + sqrt(k)) * N */

@@ -689,3 +689,21 @@ def test_reference_golden_atmosphere_and_post(ptb):
     pt.WriteResult(final)
     assert (ptb.ScreenEffect().Render(pt) == p["rendered"]).all()
     pt.Dispose()
+
+
+# ------------------------------------------------------------------------------- the reference's shader, compiled for the GPU
+@pytest.mark.skipif(os.environ.get("PTB_TEST_GLSL_CUDA") != "1",
+                    reason="oracle/_ref/libglsl_ref_cuda.so (compute.glsl compiled by nvcc) was cross-compiled but has not run on a GPU "
+                           "yet; set PTB_TEST_GLSL_CUDA=1 to run it — to be un-gated after its first validated GPU run")
+def test_reference_shader_compiled_by_nvcc_equals_the_megakernel(ptb):
+    """The GL-compute proxy built from the reference's own source (build_ref.py --cuda), dispatched in the reference's launch
+    shape, against the product's megakernel on the stored golden inputs: bit for bit."""
+    from oracle import ref_cuda
+    g = np.load(os.path.join(GOLD, "ref_pt_default.npz"))
+    n, H, W, _ = g["after_frame"].shape
+    proxy = ref_cuda.CudaReference(fast=False)
+    img = np.zeros((H, W, 4), np.float32)
+    for f in range(n):
+        proxy.render(img, g["basic_ubo"].tobytes(), g["objects_ubo"].tobytes(), g["env"], frame=f, frames=1, spp=2, ray_depth=13,
+                     focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+        assert_same(img, g["after_frame"][f], f"nvcc build of compute.glsl, frame {f}")
