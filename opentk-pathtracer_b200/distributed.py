@@ -295,6 +295,10 @@ class SharedHostFrame:
             all_ok = ok
         if rank == 0 and self.path and os.path.exists(self.path):
             os.unlink(self.path)               # every rank has it mapped (or has given up): the name can go
+        if world > 1:
+            # second reduction = a barrier that works on both backends: when the constructor returns, the name is gone everywhere
+            done = torch.zeros(1, dtype=torch.int32, device="cuda" if register else "cpu")
+            dist.all_reduce(done)
         if not all_ok:
             self.close()
             raise RuntimeError(f"shared host frame unavailable on some rank ({err or 'see the other ranks'})")
