@@ -153,6 +153,10 @@ int ptb_set_kernel(ptb_ctx* ctx, int kernel);
  * scratch images and folded into the accumulation image by a stream-ordered blend kernel (same arithmetic as
  * compute.glsl:126-129), so the tail of frame f overlaps the start of frame f+1.  n <= 1: one stream, in-place blend. */
 int ptb_set_overlap(ptb_ctx* ctx, int n);
+/* Experiment knob (default 1 = every resident CTA slot): each frame's persistent grid takes 1/d of the slots (never fewer
+ * than one CTA per SM), so that with n >= d frames in flight d frames are co-resident and one frame's drain runs beside
+ * another's bulk instead of beside an empty machine.  Results do not depend on it. */
+int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
 /* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */

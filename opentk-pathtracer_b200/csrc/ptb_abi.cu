@@ -110,6 +110,7 @@ struct ptb_ctx {
     int launches = 0;
     int mega_smem_set = -1;
     int mega_grid = 0;
+    int grid_divisor = 1;            // ptb_set_grid_divisor: launch 1/d of the resident CTA slots per frame (experiments)
     bool mega_ring = true;
     bool mega_bvh_set = false;
 };
@@ -490,7 +491,7 @@ int launch_frame(ptb_ctx* c)
         }
         if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
         c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
-        c->mega_grid = c->sm_count * (c->mega_ring ? with_ring : without);
+        c->mega_grid = std::max(c->sm_count, c->sm_count * (c->mega_ring ? with_ring : without) / c->grid_divisor);
         c->mega_smem_set = smem;
         c->mega_bvh_set = bvh;
     }
@@ -1045,6 +1046,15 @@ int ptb_set_overlap(ptb_ctx* c, int n)
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     c->overlap = n;
     c->launch_seq = 0;
+    return PTB_OK;
+}
+int ptb_set_grid_divisor(ptb_ctx* c, int d)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (d < 1 || d > 8) return fail(PTB_E_INVALID, "grid divisor %d outside [1,8]", d);
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    c->grid_divisor = d;
+    c->mega_smem_set = -1;           // recompute the grid at the next launch
     return PTB_OK;
 }
 int ptb_kernel_launches(ptb_ctx* c) { return c ? c->launches : fail(PTB_E_INVALID, "ctx is null"); }

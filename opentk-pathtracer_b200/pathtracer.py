@@ -228,6 +228,10 @@ class PathTracer:
         """Frames in flight (ptb_set_overlap): >= 2 pipelines consecutive Render() calls, <= 1 renders in place."""
         _lib.check(self._L.ptb_set_overlap(self._ctx, n))
 
+    def SetGridDivisor(self, d: int) -> None:
+        """Each frame's persistent grid takes 1/d of the resident CTA slots (ptb_set_grid_divisor; experiment knob, default 1)."""
+        _lib.check(self._L.ptb_set_grid_divisor(self._ctx, d))
+
     def SetTile(self, rank: int, world: int, stripe_rows: int = 8) -> None:
         _lib.check(self._L.ptb_set_tile(self._ctx, rank, world, stripe_rows))
 

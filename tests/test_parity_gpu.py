@@ -254,6 +254,22 @@ def test_frame_pipelining_modes(ptb, oracle, env256, camera, overlap):
     pt.Dispose()
 
 
+@pytest.mark.parametrize("divisor,overlap", [(2, 2), (3, 4), (8, 3)])
+def test_grid_divisor_does_not_change_the_image(ptb, oracle, env256, default_scene, camera, divisor, overlap):
+    """ptb_set_grid_divisor: each frame's persistent grid takes a fraction of the CTA slots (several frames co-resident);
+    the work counter hands out the same pixels, so the image is the same bits."""
+    W, H = 200, 120
+    pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+    pt.SetOverlap(overlap)
+    pt.SetGridDivisor(divisor)
+    pt.Render(6)
+    ref = oracle_render(oracle, ptb.scene, default_scene, camera, env256, W, H, 6)
+    assert_same(pt.Result, ref, f"grid / {divisor}, {overlap} frames in flight")
+    with pytest.raises(ptb.PtbError):
+        pt.SetGridDivisor(0)
+    pt.Dispose()
+
+
 def test_progressive_accumulation_to_1024_spp(ptb, oracle, env256, default_scene, camera):
     """BASELINE config 2's protocol (frames 0..1023 at SPP 1, running mean) at reduced size: after 1024 pipelined frames the
     accumulation image still equals the oracle's bit for bit — per-channel MSE exactly 0 (the north star asks for < 1e-6)."""

@@ -14,6 +14,9 @@ echo "== 3. frame-tail experiments: CTA size x frames in flight (us/frame; 1920x
 for v in "" variants/t128.so variants/t64.so; do
   if [ -z "$v" ] || [ -f "$v" ]; then echo "-- PTB_LIB=${v:-default}"; PTB_LIB=$v PTB_OVERLAPS=1,2,3,4 timeout 150 python tools/small_probe.py; fi
 done
+echo "-- default library, half / third grids (co-resident frames)"
+PTB_GRID_DIV=2 PTB_OVERLAPS=2,3,4 timeout 150 python tools/small_probe.py
+PTB_GRID_DIV=3 PTB_OVERLAPS=3,4 timeout 150 python tools/small_probe.py
 echo "== 4. full GPU suite"
 timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -n 4
 echo "== 5. bench"
