@@ -11,7 +11,10 @@ exchange the path has: a gather of the stripe buffers to rank 0 + de-interleave.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launching stream, inputs resident in HBM, L2
 flushed before every timed step; `e2e` goes through the same public API with host buffers: the per-frame camera UBO
-upload the C# host does (MainWindow.cs:131-132) and a read-back of the accumulation image into pinned host memory.
+upload the C# host does (MainWindow.cs:131-132) and a read-back of every frame into pinned host memory as RGB32F (the
+colour floats bit for bit; the constant alpha 1.0 is not shipped) — at N > 1 each rank writes its stripes straight into one
+full-frame image in host memory shared by all ranks, over its own PCIe link.  `gl_proxy` (N = 1) is the reference's own
+compute.glsl compiled by nvcc and dispatched in the reference's launch shape, run in a subprocess after the timed regions.
 `--impl reference` times the reference's own compute shader on the host CPUs: compute.glsl compiled by g++ from
 /root/reference through oracle/build_ref.py (oracle/_ref/libglsl_ref.so, kind "reference"), all host threads; where that
 binary is absent it falls back to the oracle's C restatement (kind "port").  The reference's C# + OpenGL host cannot run
