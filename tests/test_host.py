@@ -159,6 +159,13 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pt_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+                assert "glsl_ref" not in text and "glsl_shim" not in text and "build_ref" not in text and "glref_" not in text, f
+    # and the library the product loads links nothing of the checkers
+    import subprocess
+    from importlib import import_module
+    lib = import_module("opentk-pathtracer_b200._lib").lib_path()
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "glsl_ref" not in needed
 
 
 def test_fails_loudly_without_a_gpu(ptb):
