@@ -7,6 +7,7 @@ This mirrors the reference's C# data surface (it is host logic, numpy only, no G
   MainWindow.LoadScene            src/MainWindow.cs:208-267  (48 spheres + 7 cuboids)
   Camera / BasicDataUBO writes    src/Camera.cs:16-30,79-82; src/MainWindow.cs:131-132,278-279
   CPU mouse picking               src/Ray.cs:15-19, Sphere.cs:34-50, Cuboid.cs:38-52, MainWindow.cs:302-322, Gui.cs:229-233
+  Skybox image loading            src/Helper.cs:18-50, MainWindow.cs:177-187 (six PNG faces -> RGBA8, uploaded as Srgb8Alpha8)
 OpenTK 3.3.2's Matrix4 helpers (LookAt, CreatePerspectiveFieldOfView, Inverted) are a NuGet dependency that is
 not vendored in the reference; they are restated here in float32 from their published algorithms.  Parity with
 the shader is defined at the UBO-byte boundary, so these only have to be self-consistent.
@@ -475,6 +476,44 @@ def pick_at_cursor(scene: Scene, camera: Camera, width: int, height: int, x: int
     inv_proj = inverted(create_perspective_fov(degrees_to_radians(fov), f32(width) / f32(height), *NEAR_FAR))
     ray = Ray.GetWorldSpaceRay(inv_proj, inverted(camera.View), camera.Position, ndc)
     return pick(scene, ray) + (ray,)
+
+
+# ----------------------------------------------------------------------------- skybox faces (the other EnvironmentMap)
+SKYBOX_FACE_FILES = ("posx.png", "negx.png", "posy.png", "negy.png", "posz.png", "negz.png")   # MainWindow.cs:179-186: +X,-X,+Y,-Y,+Z,-Z
+
+
+def load_cubemap_images(paths) -> np.ndarray:
+    """Helper.ParallelLoadCubemapImages (Helper.cs:18-50): six image files -> (6, N, N, 4) uint8 RGBA faces, row 0 = the
+    image's top row (`GetPixelRowSpan(0)` is uploaded as texel row 0), ready for PathTracer.SetSkyBox / ptb_set_environment_srgb8.
+    Same checks, same messages: six paths, all present, square, equal sizes.  Decoding is `Image.Load<Rgba32>`: any PNG
+    colour type becomes 8-bit RGBA (opaque alpha where the file has none); PNG is lossless, so Pillow yields the same bytes."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    paths = list(paths)
+    if len(paths) != 6:
+        raise ValueError("Number of images must be equal to six")
+    if not all(os.path.exists(p) for p in paths):
+        raise FileNotFoundError("At least on of the specified paths is invalid")
+    from PIL import Image
+
+    def load(path):
+        with Image.open(path) as im:
+            return np.asarray(im.convert("RGBA"), dtype=np.uint8)
+
+    with ThreadPoolExecutor(max_workers=6) as pool:          # Parallel.For(0, 6, ...)
+        images = list(pool.map(load, paths))
+    if not all(im.shape[0] == im.shape[1] and im.shape[1] == images[0].shape[1] for im in images):
+        raise ValueError("Individual cubemap textures must be squares and every texture must be of the same size")
+    return np.ascontiguousarray(np.stack(images))
+
+
+def skybox_paths(directory: str):
+    """The six face paths of MainWindow.cs:179-186 under `directory`, resolved without regard to case (the host runs on a
+    case-insensitive file system: the code says `posx.png`, the repository ships `posX.png`)."""
+    import os
+    present = {name.lower(): name for name in os.listdir(directory)}
+    return [os.path.join(directory, present.get(f, f)) for f in SKYBOX_FACE_FILES]
 
 
 # ----------------------------------------------------------------------------- atmosphere inputs

@@ -348,3 +348,55 @@ def test_cpu_picking_matches_the_shader_fold(ptb, oracle):
     hit, t1, t2 = sc.cuboid_intersects_ray(room, sc.Ray(centre, sc._normalize(np.array([0.3, 1.0, 0.2], np.float32))))
     assert hit and t1 < 0 < t2
     assert sc.pick(sc.Scene(), sc.Ray(o, np.array([0, 0, -1], np.float32)))[0] is None
+
+
+def test_skybox_image_loading(ptb, tmp_path):
+    """Helper.ParallelLoadCubemapImages mirrored in scene.load_cubemap_images: face order, row order, RGBA expansion of every
+    PNG colour type, and the reference's error cases."""
+    from PIL import Image
+    sc = ptb.scene
+    rng = np.random.default_rng(3)
+    faces = rng.integers(0, 256, (6, 8, 8, 4), dtype=np.uint8)
+    modes = ["RGBA", "RGB", "RGBA", "L", "RGB", "P"]
+    paths, want = [], []
+    for i, (name, mode) in enumerate(zip(sc.SKYBOX_FACE_FILES, modes)):
+        im = Image.fromarray(faces[i], "RGBA").convert(mode)
+        p = tmp_path / (name.upper() if i % 2 else name)            # mixed case on disk, like posX.png in the repository
+        im.save(p, format="PNG")
+        paths.append(str(p))
+        want.append(np.asarray(im.convert("RGBA")))
+    got = sc.load_cubemap_images(sc.skybox_paths(str(tmp_path)))
+    assert got.shape == (6, 8, 8, 4) and got.dtype == np.uint8 and got.flags.c_contiguous
+    assert (got == np.stack(want)).all()
+    assert (got[0] == faces[0]).all() and (got[1][..., :3] == faces[1][..., :3]).all() and (got[1][..., 3] == 255).all()
+    with pytest.raises(ValueError, match="six"):
+        sc.load_cubemap_images(paths[:5])
+    with pytest.raises(FileNotFoundError):
+        sc.load_cubemap_images(paths[:5] + [str(tmp_path / "missing.png")])
+    Image.fromarray(faces[0][:, :4], "RGBA").save(tmp_path / "wide.png")
+    with pytest.raises(ValueError, match="squares"):
+        sc.load_cubemap_images(paths[:5] + [str(tmp_path / "wide.png")])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/OpenTK-PathTracer/res/textures/EnvironmentMap"), reason="the reference's skybox images are not mounted")
+def test_the_references_own_skybox_through_oracle_and_compiled_shader(ptb, oracle):
+    """The six 2048^2 PNG faces the reference ships, loaded like Helper.cs does, decoded like an Srgb8Alpha8 texture, used as
+    the EnvironmentMap: the oracle and the compiled reference shader render the same bits with it."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    sc = ptb.scene
+    faces = sc.load_cubemap_images(sc.skybox_paths("/root/reference/OpenTK-PathTracer/res/textures/EnvironmentMap"))
+    assert faces.shape == (6, 2048, 2048, 4) and (faces[..., 3] == 255).all()
+    small = np.ascontiguousarray(faces[:, ::8, ::8])                 # 256^2 faces keep the test light; decoding is per texel
+    env = oracle.srgb8_to_linear(small)
+    assert env.shape == (6, 256, 256, 4) and 0.0 < float(env[..., :3].mean()) < 1.0
+    scene, cam = sc.load_default_scene(), sc.default_camera()
+    W, H = 96, 54
+    basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
+    a, b = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    for f in range(2):
+        kw = dict(frame=f, spp=2, ray_depth=13, focal_length=20.0, aperture_diameter=0.14, n_spheres=48, n_cuboids=7)
+        oracle.render(a, basic, ubo, env, **kw)
+        R.render(b, basic, ubo, env, **kw)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
