@@ -157,6 +157,12 @@ int ptb_set_overlap(ptb_ctx* ctx, int n);
  * than one CTA per SM), so that with n >= d frames in flight d frames are co-resident and one frame's drain runs beside
  * another's bulk instead of beside an empty machine.  Results do not depend on it. */
 int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
+/* Frame batching (default 1 = off).  With frames >= 2, ptb_render_frames(n) traces up to `frames` consecutive frames per
+ * megakernel launch: the work counter runs over all their pixels, frame-major, each frame's estimate goes to its own scratch
+ * image and the per-frame blends follow in frame order — the same arithmetic in the same order as n single-frame calls, so
+ * the image is bit-identical — but lanes move from the last pixels of one frame straight into the next and only the last
+ * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off. */
+int ptb_set_batch(ptb_ctx* ctx, int frames);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
 /* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */

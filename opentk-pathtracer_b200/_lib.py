@@ -42,6 +42,7 @@ SIGNATURES = {
     "ptb_read_result": (C.c_int, [_P, C.c_void_p]),
     "ptb_read_result_async": (C.c_int, [_P, C.c_void_p]),
     "ptb_set_grid_divisor": (C.c_int, [_P, C.c_int]),
+    "ptb_set_batch": (C.c_int, [_P, C.c_int]),
     "ptb_read_result_format_async": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ptb_read_result_scatter_async": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ptb_write_result": (C.c_int, [_P, C.c_void_p]),

@@ -111,6 +111,18 @@ struct ptb_ctx {
     int mega_smem_set = -1;
     int mega_grid = 0;
     int grid_divisor = 1;            // ptb_set_grid_divisor: launch 1/d of the resident CTA slots per frame (experiments)
+    // frame batching (ptb_set_batch): up to `batch` consecutive frames of one ptb_render_frames call are traced by ONE
+    // megakernel launch into a set of per-frame scratch images; two sets alternate so that the blends of batch k run beside
+    // the trace of batch k+1
+    int batch = 1;
+    float4* d_batch_scratch[2] = {nullptr, nullptr};
+    size_t batch_scratch_frames = 0, batch_scratch_stride = 0;     // frames per set / float4 elements per frame
+    unsigned int* d_batch_counters[2] = {nullptr, nullptr};
+    cudaEvent_t ev_batch_trace[2] = {nullptr, nullptr}, ev_batch_blend[2] = {nullptr, nullptr};
+    bool batch_blend_recorded[2] = {false, false};
+    unsigned long long batch_seq = 0;
+    int batch_smem_set = -1;
+    bool batch_bvh_set = false;
     bool mega_ring = true;
     bool mega_bvh_set = false;
 };
@@ -443,6 +455,8 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.tiles_total = P.tiles_x * (unsigned)((c->local_rows + 3) / 4);
     // umulhi(n, ceil(2^32/d)) == n / d exactly while n * d < 2^32 (error term n*e/(d*2^32) < 1/d); d == 1 needs no division
     P.tiles_magic = (P.tiles_x > 1 && (unsigned long long)P.tiles_total * P.tiles_x < (1ull << 32)) ? (unsigned)(((1ull << 32) + P.tiles_x - 1) / P.tiles_x) : 0u;
+    P.batch = 1;
+    P.scratch_stride = 0ull;
 }
 
 template <class F>
@@ -543,6 +557,113 @@ int launch_frame(ptb_ctx* c)
     return PTB_OK;
 }
 
+// ---- frame batching (ptb_set_batch) -----------------------------------------------------------------------------------
+template <class F>
+int with_mega_batch(ptb_ctx* c, F&& launch)
+{
+    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
+    if (bvh) return c->mega_ring ? launch(megakernel<false, true, true, true>) : launch(megakernel<false, false, true, true>);
+    return c->mega_ring ? launch(megakernel<false, true, false, true>) : launch(megakernel<false, false, false, true>);
+}
+
+bool batch_eligible(const ptb_ctx* c)
+{
+    // the frame slot rides in bits 12..15 of the ring's pixel word; statistics and the proxy kernel stay per frame
+    return c->batch > 1 && c->kernel == PTB_KERNEL_MEGA && c->overlap >= 2 && c->local_rows > 0 && c->width <= 4096 && !c->stats_on;
+}
+
+int ensure_batch(ptb_ctx* c, int frames)
+{
+    { const int rc = ensure_pipeline(c); if (rc != PTB_OK) return rc; }      // trace streams 0/1, blend stream
+    const size_t stride = c->image_bytes / sizeof(float4);
+    if (c->batch_scratch_frames < (size_t)frames || c->batch_scratch_stride != stride) {
+        { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+        for (int s = 0; s < 2; ++s) {
+            if (c->d_batch_scratch[s]) { CU(cudaFree(c->d_batch_scratch[s])); c->d_batch_scratch[s] = nullptr; }
+            CU(cudaMalloc(&c->d_batch_scratch[s], (size_t)frames * c->image_bytes));
+            c->batch_blend_recorded[s] = false;
+        }
+        c->batch_scratch_frames = (size_t)frames;
+        c->batch_scratch_stride = stride;
+    }
+    for (int s = 0; s < 2; ++s) {
+        if (!c->d_batch_counters[s]) {
+            CU(cudaMalloc(&c->d_batch_counters[s], 2 * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(c->d_batch_counters[s], 0, 2 * sizeof(unsigned int), c->stream));
+            CU(cudaEventCreateWithFlags(&c->ev_batch_trace[s], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_batch_blend[s], cudaEventDisableTiming));
+            { const int rc = mark_inputs(c); if (rc != PTB_OK) return rc; }
+        }
+    }
+    return PTB_OK;
+}
+
+// `frames` (2..16) consecutive frames: one trace launch, then the per-frame blends in frame order on the blend stream.
+int launch_batch(ptb_ctx* c, int frames)
+{
+    { const int rc = ensure_batch(c, std::max(frames, c->batch)); if (rc != PTB_OK) return rc; }     // sized once for the configured batch
+    RenderParams P;
+    fill_params(c, P);
+    const int smem = c->stage_bytes;
+    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
+    if (c->mega_smem_set != smem || c->mega_bvh_set != bvh) {
+        // the grid / ring decision belongs to the single-frame path: let one ordinary frame make it
+        const int rc = launch_frame(c);
+        if (rc != PTB_OK) return rc;
+        return frames > 1 ? (frames - 1 >= 2 ? launch_batch(c, frames - 1) : launch_frame(c)) : PTB_OK;
+    }
+    if (c->batch_smem_set != smem || c->batch_bvh_set != bvh) {
+        CU(cudaFuncSetAttribute(megakernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(megakernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(megakernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(megakernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->batch_smem_set = smem;
+        c->batch_bvh_set = bvh;
+    }
+    const int s = (int)(c->batch_seq & 1ull);
+    cudaStream_t ts = c->trace_stream[s];
+    if (c->seen_version[s] != c->inputs_version) { CU(cudaStreamWaitEvent(ts, c->ev_inputs, 0)); c->seen_version[s] = c->inputs_version; }
+    if (c->batch_blend_recorded[s]) CU(cudaStreamWaitEvent(ts, c->ev_batch_blend[s], 0));      // this scratch set has been consumed
+    P.scratch = c->d_batch_scratch[s];
+    P.counters = c->d_batch_counters[s];
+    P.batch = frames;
+    P.scratch_stride = (unsigned long long)c->batch_scratch_stride;
+    const int rc = with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, ts>>>(P); return PTB_OK; });
+    if (rc != PTB_OK) return rc;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_batch_trace[s], ts));
+    cudaStream_t bs = c->blend_stream;
+    if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
+    CU(cudaStreamWaitEvent(bs, c->ev_batch_trace[s], 0));
+    const size_t n = (size_t)c->local_rows * c->width;
+    c->launches++;
+    for (int j = 0; j < frames; ++j) {
+        const int frame = c->frame + j;
+        const float blend = 1.0f * (1.0f / (float)(frame + 1));          // as fill_params: 1.0 / (thisRendererFrame + 1)
+        const float4* estimate = c->d_batch_scratch[s] + (size_t)j * c->batch_scratch_stride;
+        if (c->xch_on) {
+            const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
+            const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
+            if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
+            blend_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(
+                c->d_image, estimate, c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, frame, blend,
+                reinterpret_cast<float4*>(c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes), reinterpret_cast<ExchangeFlags*>(c->xch_block),
+                slot, c->d_xch_blocks);
+            c->xch_seq++;
+        } else {
+            blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, estimate, n, frame, blend);
+        }
+        CU(cudaGetLastError());
+        c->launches++;
+    }
+    CU(cudaEventRecord(c->ev_batch_blend[s], bs));
+    c->batch_blend_recorded[s] = true;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_batch_blend[s], 0));       // whatever the host enqueues next sees these frames
+    c->batch_seq++;
+    c->frame += frames;
+    return PTB_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -599,6 +720,11 @@ void ptb_destroy(ptb_ctx* c)
         if (c->ev_trace_done[i]) cudaEventDestroy(c->ev_trace_done[i]);
         if (c->ev_blend_done[i]) cudaEventDestroy(c->ev_blend_done[i]);
         if (c->trace_stream[i]) cudaStreamDestroy(c->trace_stream[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_batch_scratch[i]); cudaFree(c->d_batch_counters[i]);
+        if (c->ev_batch_trace[i]) cudaEventDestroy(c->ev_batch_trace[i]);
+        if (c->ev_batch_blend[i]) cudaEventDestroy(c->ev_batch_blend[i]);
     }
     exchange_close(c);
     cudaFree(c->d_xch_blocks);
@@ -764,9 +890,11 @@ int ptb_render_frames(ptb_ctx* c, int n)
     int rc = sync_scene(c);
     if (rc != PTB_OK) return rc;
     CU(cudaEventRecord(c->ev0, c->stream));
-    for (int i = 0; i < n; ++i) {
-        rc = launch_frame(c);
+    for (int i = 0; i < n;) {
+        const int b = batch_eligible(c) ? std::min(n - i, c->batch) : 1;
+        rc = b >= 2 ? launch_batch(c, b) : launch_frame(c);
         if (rc != PTB_OK) return rc;
+        i += b >= 2 ? b : 1;
     }
     CU(cudaEventRecord(c->ev1, c->stream));
     c->timed = true;
@@ -1046,6 +1174,14 @@ int ptb_set_overlap(ptb_ctx* c, int n)
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     c->overlap = n;
     c->launch_seq = 0;
+    return PTB_OK;
+}
+int ptb_set_batch(ptb_ctx* c, int frames)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (frames < 1 || frames > 16) return fail(PTB_E_INVALID, "batch %d outside [1,16]", frames);
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    c->batch = frames;
     return PTB_OK;
 }
 int ptb_set_grid_divisor(ptb_ctx* c, int d)

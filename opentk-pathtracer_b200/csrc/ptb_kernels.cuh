@@ -71,6 +71,10 @@ struct RenderParams {
     float inv_width, inv_height, inv_spp, blend;   // 1/W, 1/H, 1/SPP, 1/(frame+1)
     unsigned tiles_x, tiles_total;                  // 8x4 work tiles
     unsigned tiles_magic;                           // ceil(2^32 / tiles_x): tile / tiles_x == umulhi(tile, magic) while tile * tiles_x < 2^32 (0 = divide)
+    // frame batching (megakernel<..., kBatch = true> only; appended so that the offsets above never move): one launch traces
+    // `batch` consecutive frames, frame P.frame + b into scratch + b * scratch_stride; work index = b * tiles_total + tile
+    int batch;
+    unsigned long long scratch_stride;              // float4 elements between the scratch images of consecutive frames
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -304,6 +308,7 @@ struct Path {
     int px, py;         // global pixel coordinates (gl_GlobalInvocationID.xy)
     int lrow;           // row inside this rank's local image
     int sample, depth;
+    int fb;             // frame slot inside a batched launch (kBatch instantiations only; otherwise never touched)
 };
 
 // pt:110-121 — jitter, pinhole ray, thin-lens origin / direction.  Draw order: jitter.x, jitter.y, angle, radius.
@@ -586,12 +591,12 @@ __device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, flo
 
 // pt:125-129 — mean over SPP, running mean over frames, store.  Frame 0 does not read the image: the reference
 // multiplies the stale value by exactly 0 there (mix(x, y, 1.0)), so a zero stands in for it.
-__device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p)
+__device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p, size_t frame_offset = 0)
 {
     const V3 irr = p.irr * P.inv_spp;
     const size_t at = (size_t)p.lrow * P.width + p.px;
     if (P.scratch) {              // pipelined frames: the running mean is applied by blend_kernel, in frame order
-        P.scratch[at] = make_float4(irr.x, irr.y, irr.z, 1.0f);
+        P.scratch[frame_offset + at] = make_float4(irr.x, irr.y, irr.z, 1.0f);
         return;
     }
     float4* px = P.image + at;
@@ -666,7 +671,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // 8x4 tiles so a freshly filled warp starts on a compact footprint.
 // kRing: stage primary rays through the per-warp shared-memory ring (2 KB per warp; the host turns it off when the scene
 // block is so large that the ring would lower the number of resident CTAs).
-template <bool kStats, bool kRing, bool kBvh>
+// kBatch: one launch traces P.batch consecutive frames (ptb_set_batch).  The work counter runs over batch * tiles_total items,
+// frame-major; a tile's frame slot b seeds its pixels with frame P.frame + b and routes their estimates to scratch image b,
+// so lanes move from the last pixels of one frame straight into the next frame and only the last frame of a batch drains.
+// The slot travels in bits 12..15 of the ring's pixel word (the host batches only images up to 4096 pixels wide).
+template <bool kStats, bool kRing, bool kBvh, bool kBatch = false>
 __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const __grid_constant__ RenderParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -713,9 +722,11 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                 unsigned tile = 0;
                 if (lane == 0) tile = atomicAdd(P.counters, 1u);
                 tile = __shfl_sync(0xffffffffu, tile, 0);
-                if (tile >= P.tiles_total) {
+                if (tile >= (kBatch ? P.tiles_total * (unsigned)P.batch : P.tiles_total)) {
                     exhausted = true;
                 } else {
+                    unsigned fb = 0u;
+                    if constexpr (kBatch) { fb = tile / P.tiles_total; tile -= fb * P.tiles_total; }
                     const unsigned tyu = P.tiles_magic ? __umulhi(tile, P.tiles_magic) : tile / P.tiles_x;
                     const int x = (int)(tile - tyu * P.tiles_x) * 8 + (int)(lane & 7u), lr = (int)tyu * 4 + (int)(lane >> 3);
                     const int y = lr < P.local_rows ? global_row(P, lr) : P.height;
@@ -724,13 +735,13 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                     if (valid) {
                         Path g;
                         g.px = x; g.py = y;
-                        g.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
+                        g.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + ((uint32_t)P.frame + fb) * 2699u) | 1u;   // pt:106
                         primary_ray(P, g);
                         const unsigned slot = (q_head + q_count + (unsigned)__popc(vmask & lt_mask)) & (kQueue - 1);
                         ring[0 * kQueue + slot] = __float_as_uint(g.o.x); ring[1 * kQueue + slot] = __float_as_uint(g.o.y);
                         ring[2 * kQueue + slot] = __float_as_uint(g.o.z); ring[3 * kQueue + slot] = __float_as_uint(g.d.x);
                         ring[4 * kQueue + slot] = __float_as_uint(g.d.y); ring[5 * kQueue + slot] = __float_as_uint(g.d.z);
-                        ring[6 * kQueue + slot] = g.rng; ring[7 * kQueue + slot] = (uint32_t)x | ((uint32_t)lr << 16);
+                        ring[6 * kQueue + slot] = g.rng; ring[7 * kQueue + slot] = (uint32_t)x | (fb << 12) | ((uint32_t)lr << 16);
                     }
                     q_count += (unsigned)__popc(vmask);
                     __syncwarp();
@@ -746,7 +757,9 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                     p.d = mk(__uint_as_float(ring[3 * kQueue + slot]), __uint_as_float(ring[4 * kQueue + slot]), __uint_as_float(ring[5 * kQueue + slot]));
                     p.rng = ring[6 * kQueue + slot];
                     const uint32_t xy = ring[7 * kQueue + slot];
-                    p.px = (int)(xy & 0xffffu); p.lrow = (int)(xy >> 16);
+                    if constexpr (kBatch) { p.px = (int)(xy & 0xfffu); p.fb = (int)((xy >> 12) & 0xfu); }
+                    else p.px = (int)(xy & 0xffffu);
+                    p.lrow = (int)(xy >> 16);
                     p.thr = mk(1.0f, 1.0f, 1.0f); p.rad = mk(0.0f, 0.0f, 0.0f); p.irr = mk(0.0f, 0.0f, 0.0f);
                     p.depth = 0; p.sample = 0;
                     alive = true;
@@ -762,17 +775,20 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(P.counters, n_dead);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned total = P.tiles_total * 32u;
+                const unsigned total = (kBatch ? P.tiles_total * (unsigned)P.batch : P.tiles_total) * 32u;
                 if (base + n_dead >= total) exhausted = true;
                 const unsigned idx = base + (unsigned)__popc(dead & lt_mask);
                 if (!alive && idx < total) {
-                    const unsigned tile = idx >> 5, in = idx & 31u;
+                    unsigned tile = idx >> 5;
+                    const unsigned in = idx & 31u;
+                    unsigned fb = 0u;
+                    if constexpr (kBatch) { fb = tile / P.tiles_total; tile -= fb * P.tiles_total; p.fb = (int)fb; }
                     const unsigned tyu = P.tiles_magic ? __umulhi(tile, P.tiles_magic) : tile / P.tiles_x;
                     const int x = (int)(tile - tyu * P.tiles_x) * 8 + (int)(in & 7u), lr = (int)tyu * 4 + (int)(in >> 3);
                     const int y = lr < P.local_rows ? global_row(P, lr) : P.height;
                     if (x < P.width && y < P.height) {
                         p.px = x; p.lrow = lr; p.py = y;
-                        p.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + (uint32_t)P.frame * 2699u) | 1u;   // pt:106
+                        p.rng = ((uint32_t)x * 1973u + (uint32_t)y * 9277u + ((uint32_t)P.frame + fb) * 2699u) | 1u;   // pt:106
                         primary_ray(P, p);
                         p.irr = mk(0.0f, 0.0f, 0.0f);
                         p.sample = 0;
@@ -811,7 +827,11 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
             if (!go) {
                 p.irr = p.irr + p.rad;                // pt:123
                 if (++p.sample < P.spp) fresh = true;
-                else { finish_pixel(P, p); alive = false; }
+                else {
+                    if constexpr (kBatch) finish_pixel(P, p, (size_t)p.fb * (size_t)P.scratch_stride);
+                    else finish_pixel(P, p);
+                    alive = false;
+                }
             }
         }
     }

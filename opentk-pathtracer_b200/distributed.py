@@ -177,6 +177,36 @@ class TiledPathTracer:
         self._last_full = full
         return full
 
+    def step_batch(self, frames: int, consumer=None):
+        """`frames` frames through the fused path with frame batching (PathTracer.SetBatch): every rank traces them with one
+        megakernel launch; the per-frame blend-and-scatter kernels still deliver every frame's pixels to rank 0 in order, so
+        rank 0 acquires / consumes / releases one slot per frame exactly as step_fused does."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        if not self.fused:
+            raise RuntimeError("step_batch needs the fused exchange (per-frame NCCL gathers cannot be batched)")
+        self.tracer.Render(frames)
+        if self.rank != 0:
+            return None
+        L, ctx = self.tracer._L, self.tracer._ctx
+        full = None
+        for _ in range(frames):
+            ptr = C.c_void_p()
+            _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
+            full = self._slot_tensors.get(ptr.value)
+            if full is None:
+                full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+                self._slot_tensors[ptr.value] = full
+            if consumer is not None:
+                consumer(full)
+            _lib.check(L.ptb_exchange_release(ctx))
+        self._last_full = full
+        return full
+
     def exchange_ok(self) -> None:
         from . import _lib
         _lib.check(self.tracer._L.ptb_exchange_status(self.tracer._ctx))

@@ -228,6 +228,10 @@ class PathTracer:
         """Frames in flight (ptb_set_overlap): >= 2 pipelines consecutive Render() calls, <= 1 renders in place."""
         _lib.check(self._L.ptb_set_overlap(self._ctx, n))
 
+    def SetBatch(self, frames: int) -> None:
+        """Render(n) traces up to `frames` consecutive frames per megakernel launch (ptb_set_batch; 1 = off)."""
+        _lib.check(self._L.ptb_set_batch(self._ctx, frames))
+
     def SetGridDivisor(self, d: int) -> None:
         """Each frame's persistent grid takes 1/d of the resident CTA slots (ptb_set_grid_divisor; experiment knob, default 1)."""
         _lib.check(self._L.ptb_set_grid_divisor(self._ctx, d))

@@ -17,6 +17,10 @@ done
 echo "-- default library, half / third grids (co-resident frames)"
 PTB_GRID_DIV=2 PTB_OVERLAPS=2,3,4 timeout 150 python tools/small_probe.py
 PTB_GRID_DIV=3 PTB_OVERLAPS=3,4 timeout 150 python tools/small_probe.py
+echo "-- frame batching (one launch per 4 / 8 / 16 frames)"
+for b in 4 8 16; do PTB_BATCH=$b PTB_OVERLAPS=2 timeout 150 python tools/small_probe.py; done
+echo "-- gated batch tests"
+PTB_TEST_BATCH=1 timeout 300 python -m pytest tests/test_parity_gpu.py -x -q -k "batch" 2>&1 | tail -n 5
 echo "== 4. full GPU suite"
 timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -n 4
 echo "== 5. bench"
