@@ -206,6 +206,14 @@ def run_ours(args, rank, world, local_rank):
     # split over several GPUs (small per-GPU tiles are dominated by the per-frame tail; measured at N = 8: 22.1 -> 25.7 Gsamples/s)
     frames_in_flight = int(os.environ.get("PTB_OVERLAP", "3" if world > 1 else "2"))
     pt.SetOverlap(frames_in_flight)
+    # opt-in experiment knobs (defaults leave everything as measured in round 1): PTB_BATCH = frames per megakernel launch
+    # (ptb_set_batch; the device-timed loops then submit that many steps per call), PTB_GRID_DIV = ptb_set_grid_divisor
+    batch = max(1, int(os.environ.get("PTB_BATCH", "1")))
+    grid_div = max(1, int(os.environ.get("PTB_GRID_DIV", "1")))
+    if batch > 1:
+        pt.SetBatch(batch)
+    if grid_div > 1:
+        pt.SetGridDivisor(grid_div)
     pt.GenerateAtmosphere(256, 50, 15, 0.5, 15.0)      # the default EnvironmentMap, produced on the GPU (MainWindow.cs:174-175)
     pt.LoadScene(scene)
     pt.SetCamera(cam)
@@ -251,11 +259,14 @@ def run_ours(args, rank, world, local_rank):
     snap = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1) else None
     state = {"i": 0}
 
-    def step_device():
+    def step_device(n=1):
         if tiled is None:
-            pt.Render()
+            pt.Render(n)
+        elif n > 1 and fused:
+            tiled.step_batch(n)    # one trace launch for n frames; every frame still reaches rank 0 through its own slot
         else:
-            tiled.step()           # render f; finish gather f-1 (it overlapped this render); start gather f
+            for _ in range(n):
+                tiled.step()       # render f; finish gather f-1 (it overlapped this render); start gather f
 
     def finish_device():
         if tiled is not None:
@@ -330,11 +341,17 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         wall0 = time.perf_counter()
         ev0.record()
-        for _ in range(steps):
+        chunk = batch if (batch > 1 and fn is step_device) else 1
+        for k in range(0, steps, chunk):
+            m = min(chunk, steps - k)
             if flush_l2:
                 with torch.cuda.stream(flush_stream):
-                    flush.zero_()
-            fn()
+                    for _ in range(m):
+                        flush.zero_()
+            if chunk > 1:
+                fn(m)
+            else:
+                fn()
         if finisher is not None:
             finisher()             # drain the pipeline inside the timed region
         ev1.record()
@@ -438,7 +455,8 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "flushed every step by a 160 MiB memset (> 126 MB L2) on a concurrent stream, inside the timed region",
                    "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + ("exchange fused into the blend kernel: peer stores into rank 0's image over NVLink (CUDA IPC), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render") if world > 1 else "single GPU, no collective",
-                   "kernel": f"persistent megakernel (ptb::megakernel) + blend kernel per frame, {frames_in_flight} frames in flight (ptb_set_overlap)"},
+                   "kernel": f"persistent megakernel (ptb::megakernel) + blend kernel per frame, {frames_in_flight} frames in flight (ptb_set_overlap)"
+                             + (f", {batch} frames per trace launch (PTB_BATCH)" if batch > 1 else "") + (f", grid / {grid_div} (PTB_GRID_DIV)" if grid_div > 1 else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "ptb::megakernel<false>",
                      "kernel_ms": kern_ms, "kernel_timing": "megakernel alone, in-place mode (ptb_set_overlap(1)), 20 launches back to back, CUDA events", "algorithmic_bytes_per_launch": algo_bytes,
