@@ -147,15 +147,15 @@ struct vec4 {
 };
 
 /* ---- arithmetic: component-wise on Float (so `/` is a * rcp(b) everywhere) ----------------------------------------- */
-#define GLSL_SHIM_OP(OP)                                                                                              \
-    GLSL_HD inline vec2 operator OP(const vec2 &a, const vec2 &b) { return vec2(a.x OP b.x, a.y OP b.y); }                    \
-    GLSL_HD inline vec2 operator OP(const vec2 &a, Float b) { return vec2(a.x OP b, a.y OP b); }                              \
-    GLSL_HD inline vec2 operator OP(Float a, const vec2 &b) { return vec2(a OP b.x, a OP b.y); }                              \
-    GLSL_HD inline vec3 operator OP(const vec3 &a, const vec3 &b) { return vec3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }        \
-    GLSL_HD inline vec3 operator OP(const vec3 &a, Float b) { return vec3(a.x OP b, a.y OP b, a.z OP b); }                    \
-    GLSL_HD inline vec3 operator OP(Float a, const vec3 &b) { return vec3(a OP b.x, a OP b.y, a OP b.z); }                    \
+#define GLSL_SHIM_OP(OP)                                                                                                           \
+    GLSL_HD inline vec2 operator OP(const vec2 &a, const vec2 &b) { return vec2(a.x OP b.x, a.y OP b.y); }                         \
+    GLSL_HD inline vec2 operator OP(const vec2 &a, Float b) { return vec2(a.x OP b, a.y OP b); }                                   \
+    GLSL_HD inline vec2 operator OP(Float a, const vec2 &b) { return vec2(a OP b.x, a OP b.y); }                                   \
+    GLSL_HD inline vec3 operator OP(const vec3 &a, const vec3 &b) { return vec3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }             \
+    GLSL_HD inline vec3 operator OP(const vec3 &a, Float b) { return vec3(a.x OP b, a.y OP b, a.z OP b); }                         \
+    GLSL_HD inline vec3 operator OP(Float a, const vec3 &b) { return vec3(a OP b.x, a OP b.y, a OP b.z); }                         \
     GLSL_HD inline vec4 operator OP(const vec4 &a, const vec4 &b) { return vec4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
-    GLSL_HD inline vec4 operator OP(const vec4 &a, Float b) { return vec4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); }          \
+    GLSL_HD inline vec4 operator OP(const vec4 &a, Float b) { return vec4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); }               \
     GLSL_HD inline vec4 operator OP(Float a, const vec4 &b) { return vec4(a OP b.x, a OP b.y, a OP b.z, a OP b.w); }
 GLSL_SHIM_OP(+) GLSL_SHIM_OP(-) GLSL_SHIM_OP(*) GLSL_SHIM_OP(/)
 
@@ -164,14 +164,14 @@ GLSL_HD inline vec3 operator-(const vec3 &a) { return vec3(-a.x, -a.y, -a.z); }
 GLSL_HD inline vec4 operator-(const vec4 &a) { return vec4(-a.x, -a.y, -a.z, -a.w); }
 
 /* compound assignment: `a op= b` is `a = a op b` (GLSL §5.8) */
-#define GLSL_SHIM_COMPOUND(T)                                                                                        \
-    GLSL_HD inline T &operator+=(T &a, const T &b) { a = a + b; return a; }                                                 \
-    GLSL_HD inline T &operator-=(T &a, const T &b) { a = a - b; return a; }                                                 \
-    GLSL_HD inline T &operator*=(T &a, const T &b) { a = a * b; return a; }                                                 \
-    GLSL_HD inline T &operator/=(T &a, const T &b) { a = a / b; return a; }                                                 \
-    GLSL_HD inline T &operator+=(T &a, Float b) { a = a + b; return a; }                                                    \
-    GLSL_HD inline T &operator-=(T &a, Float b) { a = a - b; return a; }                                                    \
-    GLSL_HD inline T &operator*=(T &a, Float b) { a = a * b; return a; }                                                    \
+#define GLSL_SHIM_COMPOUND(T)                                               \
+    GLSL_HD inline T &operator+=(T &a, const T &b) { a = a + b; return a; } \
+    GLSL_HD inline T &operator-=(T &a, const T &b) { a = a - b; return a; } \
+    GLSL_HD inline T &operator*=(T &a, const T &b) { a = a * b; return a; } \
+    GLSL_HD inline T &operator/=(T &a, const T &b) { a = a / b; return a; } \
+    GLSL_HD inline T &operator+=(T &a, Float b) { a = a + b; return a; }    \
+    GLSL_HD inline T &operator-=(T &a, Float b) { a = a - b; return a; }    \
+    GLSL_HD inline T &operator*=(T &a, Float b) { a = a * b; return a; }    \
     GLSL_HD inline T &operator/=(T &a, Float b) { a = a / b; return a; }
 GLSL_SHIM_COMPOUND(vec2) GLSL_SHIM_COMPOUND(vec3) GLSL_SHIM_COMPOUND(vec4)
 
