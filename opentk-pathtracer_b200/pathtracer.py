@@ -57,6 +57,47 @@ class ScreenEffect:
         return out
 
 
+class AtmosphericScatterer:
+    """Mirror of src/Render/AtmosphericScatterer.cs for the environment producer: the four push-on-set properties
+    (ISteps, JSteps, Time, LightIntensity — the last clamped at 0 like the C# setter, :51), the constructor defaults
+    (:91-94), Render() and SetSize().  Render() runs the atmosphere kernel of `tracer` and binds the cubemap as its
+    EnvironmentMap (MainWindow.cs:174-175,189 do those two steps separately); Result reads the faces back."""
+
+    def __init__(self, tracer: "PathTracer", size: int):
+        if size <= 0:
+            raise ValueError("size must be positive")
+        self._tracer, self.Size = tracer, int(size)
+        self.Time = 0.5
+        self.ISteps = 50
+        self.JSteps = 15
+        self.LightIntensity = 15.0
+
+    @property
+    def LightIntensity(self) -> float:
+        return self._lightIntensity
+
+    @LightIntensity.setter
+    def LightIntensity(self, value: float) -> None:
+        self._lightIntensity = max(float(value), 0.0)
+
+    @property
+    def LightPos(self) -> np.ndarray:
+        """The `lightPos` uniform the Time setter uploads (AtmosphericScatterer.cs:41)."""
+        return _scene.atmosphere_light_pos(self.Time)
+
+    def Render(self) -> None:
+        self._tracer.GenerateAtmosphere(self.Size, int(self.ISteps), int(self.JSteps), float(self.Time), self._lightIntensity)
+
+    def SetSize(self, size: int) -> None:
+        if size <= 0:
+            raise ValueError("size must be positive")
+        self.Size = int(size)
+
+    @property
+    def Result(self) -> np.ndarray:
+        return self._tracer.ReadEnvironment()
+
+
 class PathTracer:
     def __init__(self, environmentMap, width: int, height: int, rayDepth: int, spp: int, focalLength: float,
                  apertureDiamater: float, *, max_spheres: int = _scene.MAX_GAMEOBJECTS_SPHERES,

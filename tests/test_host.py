@@ -400,3 +400,23 @@ def test_the_references_own_skybox_through_oracle_and_compiled_shader(ptb, oracl
         oracle.render(a, basic, ubo, env, **kw)
         R.render(b, basic, ubo, env, **kw)
     assert (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
+def test_atmospheric_scatterer_mirror_defaults_and_clamp(ptb):
+    """AtmosphericScatterer.cs:11-57,91-94 — property surface without a GPU (Render() is exercised by the GPU tests)."""
+    class FakeTracer:
+        def GenerateAtmosphere(self, *a):
+            self.args = a
+    t = FakeTracer()
+    a = ptb.AtmosphericScatterer(t, 256)
+    assert (a.Size, a.Time, a.ISteps, a.JSteps, a.LightIntensity) == (256, 0.5, 50, 15, 15.0)
+    a.LightIntensity = -3.0
+    assert a.LightIntensity == 0.0                      # Math.Max(value, 0.0f)
+    a.Time, a.ISteps, a.JSteps, a.LightIntensity = 0.25, 20, 5, 22.0
+    a.SetSize(64)
+    a.Render()
+    assert t.args == (64, 20, 5, 0.25, 22.0)
+    lp = a.LightPos
+    assert lp.dtype == np.float32 and lp[0] == 0 and abs(float(lp[1]) - 149600000e3) < 1e6 and abs(float(lp[2])) < 1e5   # noon: sun at the zenith
+    with pytest.raises(ValueError):
+        ptb.AtmosphericScatterer(t, 0)
