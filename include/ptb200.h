@@ -161,7 +161,8 @@ int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
  * megakernel launch: the work counter runs over all their pixels, frame-major, each frame's estimate goes to its own scratch
  * image and the per-frame blends follow in frame order — the same arithmetic in the same order as n single-frame calls, so
  * the image is bit-identical — but lanes move from the last pixels of one frame straight into the next and only the last
- * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off. */
+ * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off;
+ * with the fused exchange a batch is capped at the number of exchange slots. */
 int ptb_set_batch(ptb_ctx* ctx, int frames);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */

@@ -891,7 +891,11 @@ int ptb_render_frames(ptb_ctx* c, int n)
     if (rc != PTB_OK) return rc;
     CU(cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < n;) {
-        const int b = batch_eligible(c) ? std::min(n - i, c->batch) : 1;
+        // fused exchange: blend j of a batch waits for the release of frame (seq_j - slots), and rank 0 enqueues this batch's
+        // acquires / releases only after the whole batch (its stream waits for the batch's last blend) — so a batch may not be
+        // longer than the slot ring, or its own later blends would wait for its own earlier releases
+        const int bmax = c->xch_on ? std::min(c->batch, c->xch_slots) : c->batch;
+        const int b = batch_eligible(c) ? std::min(n - i, bmax) : 1;
         rc = b >= 2 ? launch_batch(c, b) : launch_frame(c);
         if (rc != PTB_OK) return rc;
         i += b >= 2 ? b : 1;

@@ -19,7 +19,7 @@ PY
 }
 run default PTB_BATCH=1
 run batch4 PTB_BATCH=4
-run batch8 PTB_BATCH=8
+run batch8 PTB_BATCH=8 PTB_SLOTS=8          # a batch cannot be longer than the exchange's slot ring
 run griddiv2 PTB_GRID_DIV=2 PTB_OVERLAP=4
 run nccl PTB_EXCHANGE=nccl
 python tools/multigpu_check.py 2>&1 | tail -n 12
