@@ -139,6 +139,7 @@ class TiledPathTracer:
         from . import _lib
 
         L, ctx = self.tracer._L, self.tracer._ctx
+        self.slots = int(slots)
         _lib.check(L.ptb_exchange_init(ctx, slots))
         handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
         if self.rank == 0:
@@ -189,21 +190,28 @@ class TiledPathTracer:
 
         if not self.fused:
             raise RuntimeError("step_batch needs the fused exchange (per-frame NCCL gathers cannot be batched)")
-        self.tracer.Render(frames)
-        if self.rank != 0:
-            return None
         L, ctx = self.tracer._L, self.tracer._ctx
         full = None
-        for _ in range(frames):
-            ptr = C.c_void_p()
-            _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
-            full = self._slot_tensors.get(ptr.value)
-            if full is None:
-                full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
-                self._slot_tensors[ptr.value] = full
-            if consumer is not None:
-                consumer(full)
-            _lib.check(L.ptb_exchange_release(ctx))
+        left = int(frames)
+        while left > 0:
+            # a chunk never exceeds the slot ring: its blends may only wait for releases that are already enqueued
+            chunk = min(left, self.slots)
+            left -= chunk
+            self.tracer.Render(chunk)
+            if self.rank != 0:
+                continue
+            for _ in range(chunk):
+                ptr = C.c_void_p()
+                _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
+                full = self._slot_tensors.get(ptr.value)
+                if full is None:
+                    full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+                    self._slot_tensors[ptr.value] = full
+                if consumer is not None:
+                    consumer(full)
+                _lib.check(L.ptb_exchange_release(ctx))
+        if self.rank != 0:
+            return None
         self._last_full = full
         return full
 
