@@ -349,3 +349,46 @@ def test_baseline_config3_scene_with_patched_array_lengths(ref, oracle, ptb, env
     assert (a[:, 0] == b[:, 0]).all() and a[:, 0].sum() > 15000
     hit = a[:, 0] == 1
     _same_images(a[hit], b[hit], "RayTrace over 1280 primitives")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_randomised_configurations(ref, oracle, ptb, env16, seed):
+    """Forty random dispatches: camera anywhere (also inside boxes and spheres, looking along axes), any field of view and image
+    shape, random SPP / rayDepth / lens / frame number, random object counts, raw material bytes drawn beyond the C# clamps."""
+    sc = ptb.scene
+    rng = np.random.default_rng(1000 + seed)
+    base = sc.synthetic_scene(256, 64, seed=50 + seed)
+    raw0 = np.frombuffer(base.ubo_bytes(), np.float32).copy()
+    for trial in range(10):
+        raw = raw0.copy()
+        sph = raw[:256 * 20].reshape(256, 20)
+        cub = raw[256 * 20:].reshape(64, 24)
+        k = rng.integers(0, 256, 24)
+        sph[k, 7] = rng.uniform(-0.2, 1.3, k.size)            # SpecularChance
+        sph[k, 15] = rng.uniform(-0.2, 1.3, k.size)           # RefractionChance
+        sph[k, 16] = rng.choice([0.0, 0.3, 1.0], k.size)      # RefractionRoughness (0 -> total internal reflection -> NaN direction)
+        sph[k, 17] = rng.uniform(0.5, 2.5, k.size)            # IOR
+        cub[rng.integers(0, 64, 6), 15 + 4] = rng.uniform(0.0, 1.0, 6)     # glassy boxes
+        W, H = int(rng.integers(1, 70)), int(rng.integers(1, 40))
+        cam = sc.default_camera()
+        mode = trial % 4
+        if mode == 0:
+            cam.Position = (np.asarray(base.spheres[int(rng.integers(0, 256))].Position, np.float32)).copy()
+        elif mode == 1:
+            c = base.cuboids[int(rng.integers(7, 64))]
+            cam.Position = ((c.Min + c.Max) * np.float32(0.5)).astype(np.float32)
+        elif mode == 2:
+            cam.Position = rng.uniform([-19, -11, -21], [19, 11, 1]).astype(np.float32)
+        cam.LookX = float(rng.choice([0.0, 90.0, -90.0, 180.0, rng.uniform(-180, 180)]))
+        cam.LookY = float(rng.choice([0.0, 89.0, -89.0, rng.uniform(-80, 80)]))
+        fov = np.float32(rng.uniform(20, 140))
+        basic, ubo = sc.basic_data_bytes(cam, W, H, fov), raw.tobytes()
+        ns, nc = float(rng.choice([256, 0, rng.integers(0, 257), rng.uniform(0, 256)])), float(rng.choice([64, 0, rng.integers(0, 65)]))
+        start = rng.random((H, W, 4)).astype(np.float32)
+        io, ir = start.copy(), start.copy()
+        first = int(rng.choice([0, 1, 2, 77, 4095, 1 << 20]))
+        kw = dict(spp=int(rng.integers(1, 4)), ray_depth=int(rng.choice([0, 1, 2, 8, 13, 30])), focal_length=float(rng.uniform(0.5, 60)),
+                  aperture_diameter=float(rng.choice([0.0, 0.14, rng.uniform(0, 2)])), n_spheres=ns, n_cuboids=nc)
+        for f in range(first, first + 2):
+            _render_both(oracle, ref, io, ir, basic, ubo, env16, frame=f, **kw)
+            _same_images(io, ir, f"seed {seed} trial {trial} frame {f}: {W}x{H} {kw} counts=({ns},{nc}) look=({cam.LookX:.1f},{cam.LookY:.1f}) fov={float(fov):.1f}")
