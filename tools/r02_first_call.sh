@@ -8,6 +8,8 @@ O=gpurun_out/r02_first
 {
 echo "== 1. gated GPU test of the nvcc-compiled reference shader + the config-3 golden (never run on a GPU in round 1)"
 PTB_TEST_GLSL_CUDA=1 timeout 120 python -m pytest tests/test_parity_gpu.py -x -q -k "nvcc or config3 or reference_golden" 2>&1 | tail -n 5
+echo "== 1b. randomised CUDA-vs-oracle dispatches (gated in round 1)"
+PTB_TEST_FUZZ=1 timeout 200 python -m pytest tests/test_parity_gpu.py -x -q -k "randomised" 2>&1 | tail -n 6
 echo "== 2. GL-compute proxy from the reference's source (exact + fast builds), 1080p"
 timeout 120 python tools/gl_proxy_probe.py --frames 50
 echo "== 3. frame-tail experiments: CTA size x frames in flight (us/frame; 1920x135 = the 8-GPU share)"
