@@ -164,7 +164,16 @@ int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
  * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off;
  * with the fused exchange a batch is capped at the number of exchange slots. */
 int ptb_set_batch(ptb_ctx* ctx, int frames);
+/* Scenes with at least this many primitives are traced through the shared-memory BVH, smaller ones by the brute-force fold
+ * (default 96).  Results do not depend on it (the hierarchy only removes primitives that fail the exact test). */
+int ptb_set_bvh_threshold(ptb_ctx* ctx, int primitives);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
+/* Introspection of the packed scene / launch shape (syncs the scene first): what the last LoadScene turned into. */
+#define PTB_INFO_BVH_NODES 0      /* nodes of the shared-memory BVH (0: brute-force fold) */
+#define PTB_INFO_ALWAYS_TESTED 1  /* primitives outside the hierarchy (scene-sized or non-finite), tested for every ray */
+#define PTB_INFO_STAGED_BYTES 2   /* bytes of the scene block each CTA stages into shared memory */
+#define PTB_INFO_GRID_CTAS 3      /* CTAs of the persistent grid of the last launch */
+int ptb_scene_info(ptb_ctx* ctx, int what);
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
 /* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */
 int ptb_set_stats(ptb_ctx* ctx, int enabled);

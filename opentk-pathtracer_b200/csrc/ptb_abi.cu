@@ -132,7 +132,7 @@ namespace {
 int sync_all(ptb_ctx* c)
 {
     CU(cudaSetDevice(c->device));
-    if (c->stream) CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->stream));      // handle 0 (the legacy default stream) is a valid stream too
     for (int i = 0; i < kMaxOverlap; ++i) if (c->trace_stream[i]) CU(cudaStreamSynchronize(c->trace_stream[i]));
     if (c->blend_stream) CU(cudaStreamSynchronize(c->blend_stream));
     if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
@@ -552,6 +552,17 @@ int launch_frame(ptb_ctx* c)
             c->launches += 2;
             c->launch_seq++;
         }
+    } else if (c->xch_on) {
+        // no rows on this rank (more ranks than stripes): it still has to arrive at the frame's slot, or rank 0 would wait for ever
+        { const int rc = ensure_pipeline(c); if (rc != PTB_OK) return rc; }
+        cudaStream_t bs = c->blend_stream;
+        const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
+        const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
+        if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
+        exchange_arrive_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), slot);
+        CU(cudaGetLastError());
+        c->launches++;
+        c->xch_seq++;
     }
     c->frame++;   // PathTracer.cs:117 thisRenderNumFrame++
     return PTB_OK;
@@ -736,7 +747,7 @@ void ptb_destroy(ptb_ctx* c)
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_stage[i]); if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -744,7 +755,8 @@ int ptb_set_size(ptb_ctx* c, int width, int height)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(PTB_E_INVALID, "bad size %dx%d (1..65535)", width, height);
-    CU(cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    exchange_close(c);                               // the slots were sized for the old image: a fresh ptb_exchange_init is required
     c->width = width; c->height = height;
     c->frame = 0;                                    // PathTracer.cs:133
     return alloc_image(c);
@@ -889,6 +901,14 @@ int ptb_render_frames(ptb_ctx* c, int n)
     }
     int rc = sync_scene(c);
     if (rc != PTB_OK) return rc;
+    // fused exchange: the blend of frame k waits until frame k - slots was released, and rank 0's releases can only be enqueued
+    // after this call has returned (its stream waits for every blend): more un-released frames than slots would wait on itself
+    if (c->xch_on && c->local_rows > 0) {
+        const unsigned long long in_flight = c->rank == 0 ? c->xch_seq - c->xch_released : 0ull;
+        if (in_flight + (unsigned long long)n > (unsigned long long)c->xch_slots)
+            return fail(PTB_E_STATE, "fused exchange: %d frame(s) requested with %llu not yet released and %d slot(s); acquire/release between calls "
+                                     "(TiledPathTracer.render does) or raise ptb_exchange_init's slot count", n, in_flight, c->xch_slots);
+    }
     CU(cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < n;) {
         // fused exchange: blend j of a batch waits for the release of frame (seq_j - slots), and rank 0 enqueues this batch's
@@ -1040,7 +1060,7 @@ int ptb_set_stream(ptb_ctx* c, void* s)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
-    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
     return mark_inputs(c);
@@ -1052,7 +1072,8 @@ int ptb_set_tile(ptb_ctx* c, int rank, int world, int stripe_rows)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     if (world < 1 || rank < 0 || rank >= world || stripe_rows < 1) return fail(PTB_E_INVALID, "bad tile rank=%d world=%d stripe_rows=%d", rank, world, stripe_rows);
-    CU(cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    exchange_close(c);                               // arrival targets and row mapping depend on the partition
     c->rank = rank; c->world = world; c->stripe_rows = stripe_rows;
     c->frame = 0;
     return alloc_image(c);
@@ -1197,7 +1218,27 @@ int ptb_set_grid_divisor(ptb_ctx* c, int d)
     c->mega_smem_set = -1;           // recompute the grid at the next launch
     return PTB_OK;
 }
+int ptb_set_bvh_threshold(ptb_ctx* c, int primitives)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (primitives < 1) return fail(PTB_E_INVALID, "threshold %d < 1", primitives);
+    c->bvh_threshold = primitives;
+    c->scene_dirty = true;
+    return PTB_OK;
+}
 int ptb_kernel_launches(ptb_ctx* c) { return c ? c->launches : fail(PTB_E_INVALID, "ctx is null"); }
+int ptb_scene_info(ptb_ctx* c, int what)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    { const int rc = sync_scene(c); if (rc != PTB_OK) return rc; }
+    switch (what) {
+    case PTB_INFO_BVH_NODES: return c->n_nodes;
+    case PTB_INFO_ALWAYS_TESTED: return c->n_unbounded;
+    case PTB_INFO_STAGED_BYTES: return c->stage_bytes;
+    case PTB_INFO_GRID_CTAS: return c->mega_grid;
+    default: return fail(PTB_E_INVALID, "unknown info %d", what);
+    }
+}
 float ptb_last_render_ms(ptb_ctx* c)
 {
     if (!c || !c->timed) return -1.0f;

@@ -540,7 +540,7 @@ __device__ __forceinline__ bool bvh_box(const float4 lo, const float4 hi, V3 o, 
     return tn <= tf && tf >= -tau && tn <= best + tau;
 }
 __device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, V3 inv, int after, float limit, float best,
-                                         uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2)
+                                         uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2, int* visits = nullptr)
 {
     key = 0xffffffffu; idx = 0x7fffffff; t1b = kFloatMax; t2b = 0.0f; k_idx = -1; k_t2 = 0.0f;
     for (int u = 0; u < sc.n_unbounded; ++u) bvh_consider(sc, sc.pidx[u], o, d, inv, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
@@ -550,6 +550,7 @@ __device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, V3 i
     while (true) {
         const float4 A = sc.nodes[2 * node], B = sc.nodes[2 * node + 1];
         const int count = __float_as_int(B.w), first = __float_as_int(A.w);
+        if (visits) ++*visits;
         if (count > 0) {
             for (int j = 0; j < count; ++j) bvh_consider(sc, sc.pidx[first + j], o, d, inv, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
         } else {
@@ -568,14 +569,14 @@ __device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, V3 i
         node = stack[--sp];
     }
 }
-__device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
+__device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside, int* visits = nullptr)
 {
     // non-finite rays (normalize(0) after total internal reflection, ...) take the plain fold: nothing to cull by
     const float fin = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
     if (!(fin <= kFloatMax)) { trace(sc, o, d, T, prim, inside); return; }
     const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
     uint32_t key; int idx, k_idx; float t1, t2, k_t2;
-    bvh_pass(sc, o, d, inv, -1, kFloatMax, kFloatMax, key, idx, t1, t2, k_idx, k_t2);
+    bvh_pass(sc, o, d, inv, -1, kFloatMax, kFloatMax, key, idx, t1, t2, k_idx, k_t2, visits);
     if (k_idx < 0) {
         const bool found = key != 0xffffffffu;
         T = found ? t1 : kFloatMax; prim = found ? idx : -1; inside = found && (t1 == t2);
@@ -584,7 +585,7 @@ __device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, flo
     const int K = k_idx;
     const float t2K = k_t2;
     int k2; float k2t;
-    bvh_pass(sc, o, d, inv, K, __uint_as_float(0x7f800000u), t2K, key, idx, t1, t2, k2, k2t);
+    bvh_pass(sc, o, d, inv, K, __uint_as_float(0x7f800000u), t2K, key, idx, t1, t2, k2, k2t, visits);
     if (key != 0xffffffffu && t1 < t2K) { T = t1; prim = idx; inside = (t1 == t2); }
     else { T = t2K; prim = K; inside = true; }
 }
@@ -656,11 +657,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "PTB_WAIT:\n"
+        "PTB_WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra PTB_DONE;\n"
-        "bra PTB_WAIT;\n"
-        "PTB_DONE:\n"
+        "@p bra PTB_DONE_%=;\n"
+        "bra PTB_WAIT_%=;\n"
+        "PTB_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
@@ -1123,6 +1124,12 @@ __global__ void exchange_acquire_kernel(ExchangeFlags* flags, int slot, unsigned
 {
     wait_at_least(&flags->arrived[slot], target, &flags->error);
 }
+// a rank that owns no rows of the image (more ranks than stripes) still counts towards the slot's arrival target
+__global__ void exchange_arrive_kernel(ExchangeFlags* flags, int slot)
+{
+    __threadfence_system();
+    atomicAdd_system(&flags->arrived[slot], 1u);
+}
 __global__ void exchange_release_kernel(ExchangeFlags* flags, unsigned consumed)
 {
     __threadfence_system();
@@ -1252,7 +1259,7 @@ __device__ __forceinline__ void dbg_trace_one(const Scene& sc, const float* rays
 __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const float* rays, int n, float* out, int use_raw)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (!use_raw) {
+    if (use_raw != 1) {
         const float4* src = P.scene;
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int k = threadIdx.x; k < P.stage_bytes / 16; k += blockDim.x) dst[k] = src[k];
@@ -1260,17 +1267,19 @@ __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const f
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (use_raw) {
+    if (use_raw == 1) {
         RawScene sc; sc.ubo = P.raw_objects; sc.nS = P.n_spheres; sc.nC = P.n_cuboids; sc.max_spheres = P.max_spheres;
         dbg_trace_one(sc, rays, i, out);
     } else if (use_raw == 2) {
         const PackedScene sc = PTB_PACKED_SCENE(P, reinterpret_cast<const float4*>(smem_raw));
         const V3 o = mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
         float T; int prim; bool inside;
-        trace_bvh(sc, o, d, T, prim, inside);
+        int visits = 0;
+        trace_bvh(sc, o, d, T, prim, inside, &visits);
         float* q = out + 12 * i;
         const bool hit = T != kFloatMax;
-        q[0] = hit ? 1.0f : 0.0f; q[1] = T; q[2] = (hit && inside) ? 1.0f : 0.0f; q[3] = 0.0f;
+        // q[3]: BVH nodes visited (0 = the ray took the brute-force fold: non-finite ray, or nothing but the always-tested list)
+        q[0] = hit ? 1.0f : 0.0f; q[1] = T; q[2] = (hit && inside) ? 1.0f : 0.0f; q[3] = (float)visits;
         for (int k = 4; k < 12; ++k) q[k] = 0.0f;
         if (hit) {
             const V3 pos = o + d * T;

@@ -220,7 +220,13 @@ class TiledPathTracer:
         _lib.check(self.tracer._L.ptb_exchange_status(self.tracer._ctx))
 
     def render(self, frames: int = 1) -> None:
-        self.tracer.Render(frames)
+        """Render `frames` frames.  With the fused exchange every frame occupies a slot on rank 0 until it is released, so the
+        frames go through step_batch, which acquires and releases in chunks no longer than the slot ring (a plain
+        PathTracer.Render(frames) with frames > slots is refused by the library: it would wait for its own releases)."""
+        if self.fused:
+            self.step_batch(frames)
+        else:
+            self.tracer.Render(frames)
 
     def _start_gather(self):
         """Snapshot the local stripes (the next frame overwrites them in place) and start the one collective of the frame."""

@@ -308,6 +308,17 @@ class PathTracer:
     def KernelLaunches(self) -> int:
         return _lib.check(self._L.ptb_kernel_launches(self._ctx))
 
+    def SetBvhThreshold(self, primitives: int) -> None:
+        _lib.check(self._L.ptb_set_bvh_threshold(self._ctx, int(primitives)))
+
+    def SceneInfo(self, what: int) -> int:
+        return _lib.check(self._L.ptb_scene_info(self._ctx, int(what)))
+
+    @property
+    def BvhNodes(self) -> int:
+        """Nodes of the shared-memory BVH the current scene was packed into (0 = brute-force fold)."""
+        return self.SceneInfo(0)
+
     def ResultDevicePtr(self):
         p, n = C.c_void_p(), C.c_size_t()
         _lib.check(self._L.ptb_result_device_ptr(self._ctx, C.byref(p), C.byref(n)))

@@ -170,7 +170,14 @@ def test_bvh_fold_bit_exact(ptb, oracle, env256, camera):
         rays = np.concatenate([o, d], 1).astype(np.float32)
         ref = oracle.ray_trace(rays, scene.ubo_bytes(), scene.max_spheres, len(scene.spheres), len(scene.cuboids))
         assert ref[:, 2].sum() > 3000 and ref[:, 0].sum() > 30000
-        got = pt.DebugEval(9, rays, n, 12 * n).reshape(-1, 12)
+        got = pt.DebugEval(9, rays, n, 12 * n).reshape(-1, 12).copy()
+        # column 3 of probe 9 is the number of BVH nodes the ray visited: the probe must really have walked the hierarchy
+        # (round 1's probe silently took the brute-force fold), and a hierarchy that visits every node culls nothing
+        visits = got[:, 3].copy()
+        got[:, 3] = 0
+        finite = np.isfinite(rays).all(axis=1)
+        assert (visits[finite] >= 1).all(), "a finite ray did not enter the BVH"
+        assert visits[finite].mean() < 0.5 * pt.BvhNodes, f"mean {visits[finite].mean():.1f} of {pt.BvhNodes} nodes visited: nothing is culled"
         assert_same(got, ref, f"BVH fold, {len(scene.spheres)} spheres + {len(scene.cuboids)} cuboids")
         pt.Dispose()
     small = make_tracer(ptb, env256, 16, 16, ptb.load_default_scene(), camera)
@@ -270,12 +277,6 @@ def test_grid_divisor_does_not_change_the_image(ptb, oracle, env256, default_sce
     pt.Dispose()
 
 
-_BATCH_GATE = pytest.mark.skipif(os.environ.get("PTB_TEST_BATCH") != "1",
-                                 reason="frame batching (ptb_set_batch) was written after round 1's GPU minutes were spent and has not run on a "
-                                        "GPU yet; PTB_TEST_BATCH=1 runs it — to be un-gated after its first validated run")
-
-
-@_BATCH_GATE
 @pytest.mark.parametrize("batch", [2, 3, 8, 16])
 def test_batched_frames_equal_single_frames(ptb, oracle, env256, default_scene, camera, batch):
     """ptb_set_batch: up to `batch` frames per megakernel launch, per-frame blends in order — the same bits as frame by frame,
@@ -303,7 +304,6 @@ def test_batched_frames_equal_single_frames(ptb, oracle, env256, default_scene, 
     pt.Dispose()
 
 
-@_BATCH_GATE
 def test_batched_frames_bvh_scene_and_tiles(ptb, oracle, env256, camera):
     sc = ptb.scene
     scene = sc.synthetic_scene(256, 64, seed=5)             # 320 primitives: the BVH instantiation
@@ -764,9 +764,6 @@ def test_reference_golden_atmosphere_and_post(ptb):
 
 
 # ------------------------------------------------------------------------------- the reference's shader, compiled for the GPU
-@pytest.mark.skipif(os.environ.get("PTB_TEST_GLSL_CUDA") != "1",
-                    reason="oracle/_ref/libglsl_ref_cuda.so (compute.glsl compiled by nvcc) was cross-compiled but has not run on a GPU "
-                           "yet; set PTB_TEST_GLSL_CUDA=1 to run it — to be un-gated after its first validated GPU run")
 def test_reference_shader_compiled_by_nvcc_equals_the_megakernel(ptb):
     """The GL-compute proxy built from the reference's own source (build_ref.py --cuda), dispatched in the reference's launch
     shape, against the product's megakernel on the stored golden inputs: bit for bit."""
@@ -781,9 +778,6 @@ def test_reference_shader_compiled_by_nvcc_equals_the_megakernel(ptb):
         assert_same(img, g["after_frame"][f], f"nvcc build of compute.glsl, frame {f}")
 
 
-@pytest.mark.skipif(os.environ.get("PTB_TEST_FUZZ") != "1",
-                    reason="randomised CUDA-vs-oracle dispatches, written after round 1's GPU minutes were spent; PTB_TEST_FUZZ=1 runs them "
-                           "(first item of tools/r02_first_call.sh) — to be un-gated once they have passed on a GPU")
 @pytest.mark.parametrize("seed", range(4))
 def test_randomised_configurations_on_the_gpu(ptb, oracle, seed):
     """The CPU pin's forty random dispatches (tests/test_reference_pin.py::test_randomised_configurations), replayed through the
