@@ -135,6 +135,15 @@ def physical_gpu_index(local_rank):
 
 
 # ================================================================================================ reference arm
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed on.  torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would silently turn the reference arm into a single-core run at N > 1 — the count is passed explicitly instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference():
     """(module, kind, description): the compiled reference shaders when oracle/_ref was built, else the oracle port."""
     from oracle import oracle as O, ref as R
@@ -152,12 +161,12 @@ def run_reference(args, rank, world):
     from oracle import oracle as O_
     O, kind, kind_text = cpu_reference()
     sc = ptb200.scene
-    threads = O_.max_threads()
-    env = O.atmosphere(256, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 50, 15)
+    threads = host_threads()
+    env = O.atmosphere(256, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 50, 15, threads)
     scene, cam = sc.load_default_scene(), sc.default_camera()
     basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
     img = np.zeros((H, W, 4), np.float32)
-    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7)
+    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7, n_threads=threads)
     # calibrate on one full frame, then bound the per-step sample so warmup + steps stay under ~150 s
     t = time.perf_counter()
     O.render(img, basic, ubo, env, frame=0, **kw)
@@ -501,14 +510,15 @@ def cpu_baseline(pt):
     scene, cam = sc.load_default_scene(), sc.default_camera()
     basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
     img = np.zeros((H, W, 4), np.float32)
-    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7)
+    threads = host_threads()
+    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7, n_threads=threads)
     O.render(img, basic, ubo, env, frame=0, **kw)                 # warm-up / thread pool start
     frames, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < 10.0 and frames < 64:
         frames += 1
         O.render(img, basic, ubo, env, frame=frames, **kw)
     dt = time.perf_counter() - t0
-    return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": O_.max_threads(), "kind": kind,
+    return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
             "sample": f"{frames} full 1920x1080 frames at SPP 1 ({dt:.1f} s), OpenMP over rows"}
 
 
