@@ -164,6 +164,11 @@ int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
  * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off;
  * with the fused exchange a batch is capped at the number of exchange slots. */
 int ptb_set_batch(ptb_ctx* ctx, int frames);
+/* Ray classification for scenes of 4..64 primitives (default on): rays are classed by origin cell x direction bucket and a
+ * table gives each class the set of primitives any of its rays can hit; RayTrace() then tests only those, in index order.
+ * cells = grid cells along the longest scene axis (default 13), buckets = direction buckets per cube-face axis (default 12).
+ * The table is rebuilt on the GPU when geometry changes (not on material edits).  Results do not depend on it. */
+int ptb_set_ray_classification(ptb_ctx* ctx, int mode, int cells, int buckets);
 /* Scenes with at least this many primitives are traced through the shared-memory BVH, smaller ones by the brute-force fold
  * (default 96).  Results do not depend on it (the hierarchy only removes primitives that fail the exact test). */
 int ptb_set_bvh_threshold(ptb_ctx* ctx, int primitives);
@@ -173,6 +178,8 @@ int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this
 #define PTB_INFO_ALWAYS_TESTED 1  /* primitives outside the hierarchy (scene-sized or non-finite), tested for every ray */
 #define PTB_INFO_STAGED_BYTES 2   /* bytes of the scene block each CTA stages into shared memory */
 #define PTB_INFO_GRID_CTAS 3      /* CTAs of the persistent grid of the last launch */
+#define PTB_INFO_FOLD 4           /* how RayTrace() runs: 0 brute force, 1 BVH, 2 ray-classification table */
+#define PTB_INFO_RCT_KBYTES 5     /* size of the ray-classification table in KiB (0: none) */
 int ptb_scene_info(ptb_ctx* ctx, int what);
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
 /* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */
@@ -183,7 +190,8 @@ int ptb_read_stats(ptb_ctx* ctx, unsigned long long* counters3);
  * op: 0 sincos (in n, out 2n)  1 exp (n -> n)  2 pcg stream (in: 1 seed as uint32 bits, out n floats)
  *     3 texture(samplerCube) (in 3n dirs, out 3n)  4 RayTrace fold over the packed scene (in 6n rays, out 12n)
  *     5 min/max/rcp/sqrt probe (in 2n, out 4n)  6 RayTrace fold over the raw UBO bytes (proxy view; as 4)
- *     8 log (n -> n)  9 RayTrace fold through the BVH (scenes of >= 96 primitives; as 4)
+ *     8 log (n -> n)  9 RayTrace fold through the BVH (scenes of >= 96 primitives; as 4; out[12i+3] = nodes visited)
+ *     10 RayTrace fold through the ray-classification table (as 4; out[12i+3] = candidates left, 65 = full mask)
  *     7 group-cooperative fold of the frame tail: rays are processed k = in[6n] at a time per warp (in 6n+1, out 12n) */
 int ptb_debug_eval(ptb_ctx* ctx, int op, const float* in, int n, float* out);
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ptb_kernel_launches": (C.c_int, [_P]),
     "ptb_scene_info": (C.c_int, [_P, C.c_int]),
     "ptb_set_bvh_threshold": (C.c_int, [_P, C.c_int]),
+    "ptb_set_ray_classification": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "ptb_last_render_ms": (C.c_float, [_P]),
     "ptb_set_stats": (C.c_int, [_P, C.c_int]),
     "ptb_read_stats": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),

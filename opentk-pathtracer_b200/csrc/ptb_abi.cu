@@ -68,6 +68,16 @@ struct ptb_ctx {
     std::vector<float4> bvh_nodes;
     std::vector<int> bvh_pidx;
     SceneExtent bvh_extent = {};
+    // ray-classification table for small scenes (<= 64 primitives): see trace_rct / rct_build_kernel
+    int rct_mode = 1;                // 0 off, 1 on when the scene qualifies
+    int rct_cells = 13, rct_G = 12;  // cells along the longest scene axis, direction buckets per cube-face axis
+    unsigned long long* d_rct = nullptr;
+    size_t rct_capacity = 0;
+    bool rct_on = false;
+    float rct_lo[3] = {}, rct_inv[3] = {};
+    int rct_n[3] = {};
+    unsigned rct_sm0 = 0, rct_sm1 = 0;
+    std::vector<unsigned char> rct_geometry;   // the geometry bytes the table was built from (material edits do not rebuild it)
     float4* d_env_faces = nullptr;   // unpadded 6*N*N
     float4* d_env = nullptr;         // padded 6*(N+2)^2
     int env_size = 0;
@@ -121,10 +131,8 @@ struct ptb_ctx {
     cudaEvent_t ev_batch_trace[2] = {nullptr, nullptr}, ev_batch_blend[2] = {nullptr, nullptr};
     bool batch_blend_recorded[2] = {false, false};
     unsigned long long batch_seq = 0;
-    int batch_smem_set = -1;
-    bool batch_bvh_set = false;
     bool mega_ring = true;
-    bool mega_bvh_set = false;
+    int mega_fold_set = -1;
 };
 
 namespace {
@@ -386,6 +394,80 @@ void build_bvh(ptb_ctx* c)
     c->n_nodes = (int)(c->bvh_nodes.size() / 2);
 }
 
+// Geometry bytes only (sphere centre + radius, cuboid min + max): what the classification table depends on.
+void geometry_bytes(const ptb_ctx* c, std::vector<unsigned char>& out)
+{
+    out.clear();
+    const int hdr[6] = {c->n_spheres, c->n_cuboids, c->rct_cells, c->rct_G, 0, 0};
+    out.insert(out.end(), (const unsigned char*)hdr, (const unsigned char*)hdr + sizeof hdr);
+    for (int i = 0; i < c->n_spheres; ++i) { const unsigned char* p = c->objects.data() + (size_t)i * kSphereStride; out.insert(out.end(), p, p + 16); }
+    for (int i = 0; i < c->n_cuboids; ++i) { const unsigned char* p = c->objects.data() + (size_t)c->max_spheres * kSphereStride + (size_t)i * kCuboidStride; out.insert(out.end(), p, p + 32); }
+}
+
+bool rct_eligible(const ptb_ctx* c)
+{
+    const int n = c->n_spheres + c->n_cuboids;
+    return c->rct_mode != 0 && n >= 4 && n <= 64 && n < c->bvh_threshold;
+}
+
+// Plans and (re)builds the table on c->stream.  Returns PTB_OK with c->rct_on = false when the scene has no finite extent.
+int build_rct(ptb_ctx* c)
+{
+    c->rct_on = false;
+    if (!rct_eligible(c)) { c->rct_geometry.clear(); return PTB_OK; }
+    std::vector<Box> boxes; std::vector<char> bounded;
+    raw_boxes(c, 0.0, 0.0, boxes, bounded);
+    std::vector<Box> finite;
+    for (size_t i = 0; i < boxes.size(); ++i) if (bounded[i]) finite.push_back(boxes[i]);
+    if (finite.empty()) { c->rct_geometry.clear(); return PTB_OK; }
+    const SceneExtent e = scene_extent(finite);
+    // D bounds every coordinate and every origin-to-primitive distance of a ray that starts inside the grid (rays from
+    // outside take the full mask): the same error margins as the BVH, without the camera term
+    double diag2 = 0.0, ext[3], longest = 0.0;
+    for (int k = 0; k < 3; ++k) { ext[k] = e.hi[k] - e.lo[k]; diag2 += ext[k] * ext[k]; longest = std::max(longest, ext[k]); }
+    if (!(longest > 0.0) || !std::isfinite(longest)) { c->rct_geometry.clear(); return PTB_OK; }
+    const double D = 1.01 * (std::sqrt(diag2) + e.maxabs) + 1.0;
+    const double E = 4e-6 * D * D, m = 1e-5 * D + 1e-6;
+    const double pad = 2.0 * m + 1e-3 * longest;
+    RctBuild B = {};
+    const double target = longest / std::max(1, c->rct_cells);
+    unsigned long long cells = 1;
+    for (int k = 0; k < 3; ++k) {
+        const double lo = e.lo[k] - pad, hi = e.hi[k] + pad;
+        int n = (int)std::lround((hi - lo) / target);
+        n = std::min(std::max(n, 1), 64);
+        B.n[k] = n; B.lo[k] = lo; B.cell[k] = (hi - lo) / n;
+        c->rct_n[k] = n; c->rct_lo[k] = (float)lo; c->rct_inv[k] = (float)(1.0 / B.cell[k]);
+        cells *= (unsigned long long)n;
+    }
+    B.G = c->rct_G;
+    B.total = cells * 6ull * (unsigned long long)(B.G * B.G);
+    // classification rounds in fp32: (o - lo) * inv is off by < 4 ulp of a cell index <= 64, the grid origin / cell size by one
+    // rounding each; u = d_a * rcp(|d_m|) by < 2 ulp.  1e-4 of a cell and 1e-5 in u are far above both.
+    B.eps_cell = 1e-4 * std::max(B.cell[0], std::max(B.cell[1], B.cell[2])) + 4e-7 * e.maxabs;
+    B.eps_u = 1e-5;
+    B.E = E; B.m = m;
+    B.nS = c->n_spheres; B.nC = c->n_cuboids; B.max_spheres = c->max_spheres;
+    B.ubo = c->d_objects;
+    const size_t bytes = (size_t)B.total * sizeof(unsigned long long);
+    if (bytes > ((size_t)64 << 20)) return fail(PTB_E_INVALID, "ray-classification table of %zu bytes (cells %d, buckets %d) exceeds 64 MiB", bytes, c->rct_cells, c->rct_G);
+    if (bytes > c->rct_capacity) {
+        if (c->d_rct) CU(cudaFree(c->d_rct));
+        c->d_rct = nullptr;
+        CU(cudaMalloc(&c->d_rct, bytes));
+        c->rct_capacity = bytes;
+    }
+    B.table = c->d_rct;
+    rct_build_kernel<<<(unsigned)((B.total + 127) / 128), 128, 0, c->stream>>>(B);      // after the H2D of the UBO on the same stream
+    c->launches++;
+    CU(cudaGetLastError());
+    const int nS = c->n_spheres;
+    c->rct_sm0 = nS >= 32 ? 0xffffffffu : ((1u << nS) - 1u);
+    c->rct_sm1 = nS >= 64 ? 0xffffffffu : (nS > 32 ? ((1u << (nS - 32)) - 1u) : 0u);
+    c->rct_on = true;
+    return PTB_OK;
+}
+
 void layout_block(ptb_ctx* c)
 {
     // float4 units: [spheres][1/r][cuboid lo][cuboid hi][BVH nodes][BVH index list] | [materials]
@@ -425,6 +507,16 @@ int sync_scene(ptb_ctx* c)
         c->launches++;
         CU(cudaGetLastError());
     }
+    {
+        std::vector<unsigned char> geo;
+        geometry_bytes(c, geo);
+        if (!rct_eligible(c)) { c->rct_on = false; c->rct_geometry.clear(); }
+        else if (geo != c->rct_geometry || !c->d_rct) {
+            const int rc = build_rct(c);
+            if (rc != PTB_OK) return rc;
+            c->rct_geometry.swap(geo);
+        }
+    }
     if (c->n_nodes > 0) CU(cudaMemcpyAsync(c->d_block + c->off_nodes, c->bvh_nodes.data(), c->bvh_nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     if (!c->bvh_pidx.empty()) CU(cudaMemcpyAsync(c->d_block + c->off_pidx, c->bvh_pidx.data(), c->bvh_pidx.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (c->n_nodes > 0 || !c->bvh_pidx.empty()) CU(cudaStreamSynchronize(c->stream));     // the host vectors may be rebuilt before the copy ran
@@ -457,18 +549,42 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.tiles_magic = (P.tiles_x > 1 && (unsigned long long)P.tiles_total * P.tiles_x < (1ull << 32)) ? (unsigned)(((1ull << 32) + P.tiles_x - 1) / P.tiles_x) : 0u;
     P.batch = 1;
     P.scratch_stride = 0ull;
+    P.rct = c->rct_on ? c->d_rct : nullptr;
+    for (int k = 0; k < 3; ++k) { P.rct_lo[k] = c->rct_lo[k]; P.rct_inv[k] = c->rct_inv[k]; P.rct_n[k] = c->rct_n[k]; }
+    P.rct_G = c->rct_G; P.rct_halfG = 0.5f * (float)c->rct_G;
+    P.rct_sm0 = c->rct_sm0; P.rct_sm1 = c->rct_sm1;
 }
 
+int fold_of(const ptb_ctx* c) { return (c->n_nodes > 0 || c->n_unbounded > 0) ? 1 : (c->rct_on ? 2 : 0); }
+
+template <int kFold, class F>
+int with_mega_fold(ptb_ctx* c, bool stats, F&& launch)
+{
+    if (c->mega_ring) return stats ? launch(megakernel<true, true, kFold>) : launch(megakernel<false, true, kFold>);
+    return stats ? launch(megakernel<true, false, kFold>) : launch(megakernel<false, false, kFold>);
+}
 template <class F>
 int with_mega(ptb_ctx* c, bool stats, F&& launch)
 {
-    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
-    if (bvh) {
-        if (c->mega_ring) return stats ? launch(megakernel<true, true, true>) : launch(megakernel<false, true, true>);
-        return stats ? launch(megakernel<true, false, true>) : launch(megakernel<false, false, true>);
+    switch (fold_of(c)) {
+    case 1: return with_mega_fold<1>(c, stats, launch);
+    case 2: return with_mega_fold<2>(c, stats, launch);
+    default: return with_mega_fold<0>(c, stats, launch);
     }
-    if (c->mega_ring) return stats ? launch(megakernel<true, true, false>) : launch(megakernel<false, true, false>);
-    return stats ? launch(megakernel<true, false, false>) : launch(megakernel<false, false, false>);
+}
+
+template <int kFold>
+int prepare_mega(ptb_ctx* c, int smem, int& with_ring, int& without)
+{
+    CU(cudaFuncSetAttribute(megakernel<false, true, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<true, true, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, false, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<true, false, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, true, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, false, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true, kFold>, kMegaThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false, kFold>, kMegaThreads, smem));
+    return PTB_OK;
 }
 
 int launch_frame(ptb_ctx* c)
@@ -485,29 +601,16 @@ int launch_frame(ptb_ctx* c)
         return mark_inputs(c);      // the image changed on the user-visible stream
     }
     const int smem = c->stage_bytes;
-    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
-    if (c->mega_smem_set != smem || c->mega_bvh_set != bvh) {
+    const int fold = fold_of(c);
+    if (c->mega_smem_set != smem || c->mega_fold_set != fold) {
         int with_ring = 0, without = 0;
-        if (bvh) {
-            CU(cudaFuncSetAttribute(megakernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true, true>, kMegaThreads, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false, true>, kMegaThreads, smem));
-        } else {
-            CU(cudaFuncSetAttribute(megakernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(megakernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true, false>, kMegaThreads, smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false, false>, kMegaThreads, smem));
-        }
+        const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, without) : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, without) : prepare_mega<0>(c, smem, with_ring, without));
+        if (rc != PTB_OK) return rc;
         if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
         c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
         c->mega_grid = std::max(c->sm_count, c->sm_count * (c->mega_ring ? with_ring : without) / c->grid_divisor);
         c->mega_smem_set = smem;
-        c->mega_bvh_set = bvh;
+        c->mega_fold_set = fold;
     }
     if (c->local_rows > 0) {
         if (c->overlap <= 1) {
@@ -572,9 +675,11 @@ int launch_frame(ptb_ctx* c)
 template <class F>
 int with_mega_batch(ptb_ctx* c, F&& launch)
 {
-    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
-    if (bvh) return c->mega_ring ? launch(megakernel<false, true, true, true>) : launch(megakernel<false, false, true, true>);
-    return c->mega_ring ? launch(megakernel<false, true, false, true>) : launch(megakernel<false, false, false, true>);
+    switch (fold_of(c)) {
+    case 1: return c->mega_ring ? launch(megakernel<false, true, 1, true>) : launch(megakernel<false, false, 1, true>);
+    case 2: return c->mega_ring ? launch(megakernel<false, true, 2, true>) : launch(megakernel<false, false, 2, true>);
+    default: return c->mega_ring ? launch(megakernel<false, true, 0, true>) : launch(megakernel<false, false, 0, true>);
+    }
 }
 
 bool batch_eligible(const ptb_ctx* c)
@@ -616,20 +721,11 @@ int launch_batch(ptb_ctx* c, int frames)
     RenderParams P;
     fill_params(c, P);
     const int smem = c->stage_bytes;
-    const bool bvh = c->n_nodes > 0 || c->n_unbounded > 0;
-    if (c->mega_smem_set != smem || c->mega_bvh_set != bvh) {
-        // the grid / ring decision belongs to the single-frame path: let one ordinary frame make it
+    if (c->mega_smem_set != smem || c->mega_fold_set != fold_of(c)) {
+        // the grid / ring decision (and the shared-memory attributes of every instantiation) belong to the single-frame path
         const int rc = launch_frame(c);
         if (rc != PTB_OK) return rc;
         return frames > 1 ? (frames - 1 >= 2 ? launch_batch(c, frames - 1) : launch_frame(c)) : PTB_OK;
-    }
-    if (c->batch_smem_set != smem || c->batch_bvh_set != bvh) {
-        CU(cudaFuncSetAttribute(megakernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(megakernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(megakernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(megakernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        c->batch_smem_set = smem;
-        c->batch_bvh_set = bvh;
     }
     const int s = (int)(c->batch_seq & 1ull);
     cudaStream_t ts = c->trace_stream[s];
@@ -741,6 +837,7 @@ void ptb_destroy(ptb_ctx* c)
     cudaFree(c->d_xch_blocks);
     if (c->blend_stream) cudaStreamDestroy(c->blend_stream);
     if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
+    cudaFree(c->d_rct);
     cudaFree(c->d_objects); cudaFree(c->d_block); cudaFree(c->d_env_faces); cudaFree(c->d_env);
     cudaFree(c->d_image); cudaFree(c->d_counters); cudaFree(c->d_stats);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -1218,6 +1315,16 @@ int ptb_set_grid_divisor(ptb_ctx* c, int d)
     c->mega_smem_set = -1;           // recompute the grid at the next launch
     return PTB_OK;
 }
+int ptb_set_ray_classification(ptb_ctx* c, int mode, int cells, int buckets)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (mode < 0 || mode > 1) return fail(PTB_E_INVALID, "mode %d outside [0,1]", mode);
+    if (cells < 1 || cells > 64 || buckets < 1 || buckets > 64) return fail(PTB_E_INVALID, "cells %d / buckets %d outside [1,64]", cells, buckets);
+    c->rct_mode = mode; c->rct_cells = cells; c->rct_G = buckets;
+    c->rct_geometry.clear();
+    c->scene_dirty = true;
+    return PTB_OK;
+}
 int ptb_set_bvh_threshold(ptb_ctx* c, int primitives)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
@@ -1236,6 +1343,8 @@ int ptb_scene_info(ptb_ctx* c, int what)
     case PTB_INFO_ALWAYS_TESTED: return c->n_unbounded;
     case PTB_INFO_STAGED_BYTES: return c->stage_bytes;
     case PTB_INFO_GRID_CTAS: return c->mega_grid;
+    case PTB_INFO_FOLD: return fold_of(c);
+    case PTB_INFO_RCT_KBYTES: return c->rct_on ? (int)(((size_t)c->rct_n[0] * c->rct_n[1] * c->rct_n[2] * 6 * c->rct_G * c->rct_G * 8) >> 10) : 0;
     default: return fail(PTB_E_INVALID, "unknown info %d", what);
     }
 }
@@ -1273,7 +1382,7 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
     case 1: in_f = n; out_f = n; break;
     case 2: in_f = 1; out_f = n; break;
     case 3: in_f = 3 * (size_t)n; out_f = 3 * (size_t)n; break;
-    case 4: case 6: case 9: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
+    case 4: case 6: case 9: case 10: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
     case 5: in_f = 2 * (size_t)n; out_f = 4 * (size_t)n; break;
     case 7: in_f = 6 * (size_t)n + 1; out_f = 12 * (size_t)n; break;
     case 8: in_f = n; out_f = n; break;
@@ -1292,15 +1401,16 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
         else if (op == 3) {
             if (!c->d_env) { rc = fail(PTB_E_STATE, "no environment map set"); break; }
             dbg_env_kernel<<<gb, tb, 0, c->stream>>>(c->d_env, c->env_size, d_in, n, d_out);
-        } else if (op == 4 || op == 6 || op == 9) {
+        } else if (op == 4 || op == 6 || op == 9 || op == 10) {
             rc = sync_scene(c);
             if (rc != PTB_OK) break;
             RenderParams P;
             fill_params(c, P);
             const int smem = op == 6 ? 0 : c->stage_bytes;
             if (op == 9 && c->n_nodes == 0 && c->n_unbounded == 0) { rc = fail(PTB_E_STATE, "the current scene has no BVH (fewer than %d primitives)", c->bvh_threshold); break; }
+            if (op == 10 && !c->rct_on) { rc = fail(PTB_E_STATE, "the current scene has no ray-classification table (more than 64 primitives, or switched off)"); break; }
             if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->stage_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
-            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : (op == 9 ? 2 : 0));
+            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : (op == 9 ? 2 : (op == 10 ? 3 : 0)));
         } else if (op == 5) dbg_arith_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 8) dbg_log_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 7) {

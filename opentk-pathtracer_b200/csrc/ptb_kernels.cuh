@@ -75,6 +75,13 @@ struct RenderParams {
     // `batch` consecutive frames, frame P.frame + b into scratch + b * scratch_stride; work index = b * tiles_total + tile
     int batch;
     unsigned long long scratch_stride;              // float4 elements between the scratch images of consecutive frames
+    // ray-classification table (megakernel<kFold = 2>; scenes of at most 64 primitives): one 64-bit candidate mask per
+    // (origin cell, direction bucket); bit i = primitive i (spheres first) may be hit by some ray of that class
+    const unsigned long long* rct;
+    float rct_lo[3], rct_inv[3];                    // grid origin, 1 / cell size
+    int rct_n[3], rct_G;                            // cells per axis, direction buckets per cube-face axis
+    float rct_halfG;
+    unsigned rct_sm0, rct_sm1;                      // which bits of the mask's low / high word are spheres
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -590,6 +597,138 @@ __device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, flo
     else { T = t2K; prim = K; inside = true; }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Small scenes (<= 64 primitives): ray classification (Arvo & Kirk's 5-D idea, as a flat table).  Rays are classed by the
+// grid cell of their origin and by a direction bucket (cube face x G x G); the table holds, per class, the 64-bit set of
+// primitives that ANY ray of the class can hit (rct_build_kernel: an interval test of the class's beam against every
+// primitive's box, inflated by more than the rounding error of the exact fp32 tests — the same margins as the BVH).  A lane
+// then runs the exact tests of pt:231-255 over the set bits of its own mask only, in ascending index order.  A primitive
+// outside the set fails `hit && t2 > 0`, and a failing primitive never changes the fold's state, so the order-dependent fold
+// over the subset equals the fold over all primitives bit for bit.  Rays that start outside the grid, non-finite rays and
+// zero directions take the full mask (= the plain fold).  The default scene tests ~6 primitives per ray instead of 55; the
+// loop runs for the lane with the most candidates of its warp (~12 spheres + ~4 cuboids).
+__device__ __forceinline__ unsigned long long rct_lookup(const RenderParams& P, V3 o, V3 d, V3 inv)
+{
+    const float fin = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+    const int cx = __float2int_rd((o.x - P.rct_lo[0]) * P.rct_inv[0]);
+    const int cy = __float2int_rd((o.y - P.rct_lo[1]) * P.rct_inv[1]);
+    const int cz = __float2int_rd((o.z - P.rct_lo[2]) * P.rct_inv[2]);
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int f;
+    float im, ua, ub;
+    if (ax >= ay && ax >= az) { f = d.x < 0.0f ? 1 : 0; im = fabsf(inv.x); ua = d.y; ub = d.z; }
+    else if (ay >= az) { f = d.y < 0.0f ? 3 : 2; im = fabsf(inv.y); ua = d.x; ub = d.z; }
+    else { f = d.z < 0.0f ? 5 : 4; im = fabsf(inv.z); ua = d.x; ub = d.y; }
+    const bool ok = fin <= kFloatMax && im <= 2.0f && (unsigned)cx < (unsigned)P.rct_n[0] && (unsigned)cy < (unsigned)P.rct_n[1] &&
+                    (unsigned)cz < (unsigned)P.rct_n[2];       // im <= 2: the major component of a unit vector is >= 0.577
+    if (!ok) return ~0ull;
+    const int G = P.rct_G;
+    const int gu = min(G - 1, max(0, __float2int_rd((ua * im + 1.0f) * P.rct_halfG)));
+    const int gv = min(G - 1, max(0, __float2int_rd((ub * im + 1.0f) * P.rct_halfG)));
+    const size_t cell = ((size_t)cz * P.rct_n[1] + cy) * P.rct_n[0] + cx;
+    return __ldg(P.rct + (cell * 6 + f) * (size_t)(G * G) + gv * G + gu);
+}
+__device__ __forceinline__ void trace_rct(const RenderParams& P, const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
+{
+    T = kFloatMax;
+    prim = -1;
+    inside = false;
+    const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
+    const unsigned long long mask = rct_lookup(P, o, d, inv);
+    const unsigned w0 = (unsigned)mask, w1 = (unsigned)(mask >> 32);
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) {                       // spheres 0..31, then 32..63
+        unsigned bits = w ? (w1 & P.rct_sm1) : (w0 & P.rct_sm0);
+        const float4* base = sc.base + 32 * w;
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            float b, disc;
+            sphere_terms(base[j], o, d, b, disc);
+            accept_sphere(b, disc, 32 * w + j, T, prim, inside);
+        }
+    }
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) {                       // cuboids, bits nS..nS+nC-1
+        unsigned bits = w ? (w1 & ~P.rct_sm1) : (w0 & ~P.rct_sm0);
+        const int first = 32 * w - sc.nS;
+        while (bits) {
+            const int i = first + __ffs(bits) - 1;
+            bits &= bits - 1u;
+            if (i >= sc.nC) break;                      // bits beyond the last primitive (full mask of the fallback)
+            const float4 lo = sc.cmin(i), hi = sc.cmax(i);
+            const float ax = (lo.x - o.x) * inv.x, ay = (lo.y - o.y) * inv.y, az = (lo.z - o.z) * inv.z;
+            const float bx = (hi.x - o.x) * inv.x, by = (hi.y - o.y) * inv.y, bz = (hi.z - o.z) * inv.z;
+            const float t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
+            const float t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
+            if (t1 <= t2 && t2 > 0.0f && t1 < T) {
+                T = t1 < 0.0f ? t2 : t1;
+                inside = (T == t2);
+                prim = sc.nS + i;
+            }
+        }
+    }
+}
+
+// Table build: one thread per (cell, face, gv, gu).  The class's rays are { o + s * (sgn e_m + u e_a + v e_b) : o in the
+// cell, u in [u0,u1], v in [v0,v1], s >= 0 } (s = distance along the major axis m).  Such a ray meets the box [klo,khi] iff
+// some s >= 0 satisfies three interval conditions — on the major axis directly, on each minor axis through
+// s*u in [klo_a - chi_a, khi_a - clo_a], i.e. s*u1 >= A0 and s*u0 <= A1, both half-lines in s — so the test is an
+// intersection of half-lines.  Cells and buckets are widened by eps (classification rounds in fp32), boxes by the margins.
+struct RctBuild {
+    const unsigned char* ubo;
+    unsigned long long* table;
+    double lo[3], cell[3];
+    double eps_cell, eps_u, E, m;
+    int n[3], G, nS, nC, max_spheres;
+    unsigned long long total;
+};
+__global__ void rct_build_kernel(const __grid_constant__ RctBuild B)
+{
+    const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B.total) return;
+    const int G = B.G;
+    const int gu = (int)(id % G), gv = (int)((id / G) % G), f = (int)((id / ((unsigned long long)G * G)) % 6);
+    const unsigned long long cell = id / ((unsigned long long)G * G * 6);
+    const int c[3] = {(int)(cell % B.n[0]), (int)((cell / B.n[0]) % B.n[1]), (int)(cell / ((unsigned long long)B.n[0] * B.n[1]))};
+    double clo[3], chi[3];
+    for (int k = 0; k < 3; ++k) { clo[k] = B.lo[k] + c[k] * B.cell[k] - B.eps_cell; chi[k] = B.lo[k] + (c[k] + 1) * B.cell[k] + B.eps_cell; }
+    const int m = f >> 1, a = m == 0 ? 1 : 0, b = m == 2 ? 1 : 2;
+    const bool neg = f & 1;
+    const double ulo[2] = {-1.0 + 2.0 * gu / G - B.eps_u, -1.0 + 2.0 * gv / G - B.eps_u};
+    const double uhi[2] = {-1.0 + 2.0 * (gu + 1) / G + B.eps_u, -1.0 + 2.0 * (gv + 1) / G + B.eps_u};
+    const int ax2[2] = {a, b};
+    unsigned long long mask = 0ull;
+    for (int p = 0; p < B.nS + B.nC; ++p) {
+        double klo[3], khi[3];
+        if (p < B.nS) {
+            const float* g = reinterpret_cast<const float*>(B.ubo + (size_t)p * kSphereStride);
+            const double r = sqrt((double)g[3] * (double)g[3] + B.E) + B.m;
+            for (int k = 0; k < 3; ++k) { klo[k] = (double)g[k] - r; khi[k] = (double)g[k] + r; }
+        } else {
+            const float* g = reinterpret_cast<const float*>(B.ubo + (size_t)B.max_spheres * kSphereStride + (size_t)(p - B.nS) * kCuboidStride);
+            for (int k = 0; k < 3; ++k) { klo[k] = fmin((double)g[k], (double)g[4 + k]) - B.m; khi[k] = fmax((double)g[k], (double)g[4 + k]) + B.m; }
+        }
+        const double sum = klo[0] + klo[1] + klo[2] + khi[0] + khi[1] + khi[2];
+        bool cand = !(fabs(sum) <= 1e300);                      // NaN / Inf geometry: never culled
+        if (!cand) {
+            // major axis: sgn * s in [klo_m - chi_m, khi_m - clo_m]
+            const double L = klo[m] - chi[m], U = khi[m] - clo[m];
+            double s0 = neg ? -U : L, s1 = neg ? -L : U;
+            if (s0 < 0.0) s0 = 0.0;
+            for (int q = 0; q < 2 && s0 <= s1; ++q) {
+                const double A0 = klo[ax2[q]] - chi[ax2[q]], A1 = khi[ax2[q]] - clo[ax2[q]];
+                const double u0 = ulo[q], u1 = uhi[q];
+                if (u1 > 0.0) s0 = fmax(s0, A0 / u1); else if (u1 < 0.0) s1 = fmin(s1, A0 / u1); else if (A0 > 0.0) s1 = -1.0;      // s*u1 >= A0
+                if (u0 > 0.0) s1 = fmin(s1, A1 / u0); else if (u0 < 0.0) s0 = fmax(s0, A1 / u0); else if (A1 < 0.0) s1 = -1.0;      // s*u0 <= A1
+            }
+            cand = s0 <= s1;
+        }
+        if (cand) mask |= 1ull << p;
+    }
+    B.table[id] = mask;
+}
+
 // pt:125-129 — mean over SPP, running mean over frames, store.  Frame 0 does not read the image: the reference
 // multiplies the stale value by exactly 0 there (mix(x, y, 1.0)), so a zero stands in for it.
 __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p, size_t frame_offset = 0)
@@ -676,7 +815,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // frame-major; a tile's frame slot b seeds its pixels with frame P.frame + b and routes their estimates to scratch image b,
 // so lanes move from the last pixels of one frame straight into the next frame and only the last frame of a batch drains.
 // The slot travels in bits 12..15 of the ring's pixel word (the host batches only images up to 4096 pixels wide).
-template <bool kStats, bool kRing, bool kBvh, bool kBatch = false>
+// kFold: 0 = brute-force fold, 1 = shared-memory BVH (large scenes), 2 = ray-classification table (<= 64 primitives).
+template <bool kStats, bool kRing, int kFold, bool kBatch = false>
 __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const __grid_constant__ RenderParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -820,7 +960,8 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
         if (starved && n_live <= (unsigned)PTB_COOP_MAX && P.ray_depth > 0) {
             trace_group(sc, lane, live, n_live, p.o, p.d, T, prim, inside);
         } else if (alive && P.ray_depth > 0) {
-            if constexpr (kBvh) trace_bvh(sc, p.o, p.d, T, prim, inside);
+            if constexpr (kFold == 1) trace_bvh(sc, p.o, p.d, T, prim, inside);
+            else if constexpr (kFold == 2) trace_rct(P, sc, p.o, p.d, T, prim, inside);
             else trace_any(sc, p.o, p.d, T, prim, inside);
         }
         if (alive) {
@@ -1270,12 +1411,18 @@ __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const f
     if (use_raw == 1) {
         RawScene sc; sc.ubo = P.raw_objects; sc.nS = P.n_spheres; sc.nC = P.n_cuboids; sc.max_spheres = P.max_spheres;
         dbg_trace_one(sc, rays, i, out);
-    } else if (use_raw == 2) {
+    } else if (use_raw == 2 || use_raw == 3) {
         const PackedScene sc = PTB_PACKED_SCENE(P, reinterpret_cast<const float4*>(smem_raw));
         const V3 o = mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
         float T; int prim; bool inside;
         int visits = 0;
-        trace_bvh(sc, o, d, T, prim, inside, &visits);
+        if (use_raw == 2) trace_bvh(sc, o, d, T, prim, inside, &visits);
+        else {
+            // q[3]: candidates the table left for this ray (65 = the ray took the full mask: outside the grid / non-finite)
+            trace_rct(P, sc, o, d, T, prim, inside);
+            const unsigned long long mk64 = rct_lookup(P, o, d, mk(rcp(d.x), rcp(d.y), rcp(d.z)));
+            visits = mk64 == ~0ull ? 65 : __popcll(mk64);
+        }
         float* q = out + 12 * i;
         const bool hit = T != kFloatMax;
         // q[3]: BVH nodes visited (0 = the ray took the brute-force fold: non-finite ray, or nothing but the always-tested list)

@@ -308,6 +308,10 @@ class PathTracer:
     def KernelLaunches(self) -> int:
         return _lib.check(self._L.ptb_kernel_launches(self._ctx))
 
+    def SetRayClassification(self, mode: int = 1, cells: int = 13, buckets: int = 12) -> None:
+        """Ray-classification table for scenes of <= 64 primitives (ptb_set_ray_classification); mode 0 = plain fold."""
+        _lib.check(self._L.ptb_set_ray_classification(self._ctx, int(mode), int(cells), int(buckets)))
+
     def SetBvhThreshold(self, primitives: int) -> None:
         _lib.check(self._L.ptb_set_bvh_threshold(self._ctx, int(primitives)))
 

@@ -186,6 +186,107 @@ def test_bvh_fold_bit_exact(ptb, oracle, env256, camera):
     small.Dispose()
 
 
+def test_ray_classification_fold_bit_exact(ptb, oracle, env256, camera):
+    """Scenes of <= 64 primitives: RayTrace() runs over the candidates of the ray's class only (origin cell x direction
+    bucket -> 64-bit set).  The table may only drop primitives that fail the exact test, so the fold must equal the oracle's
+    fold over all primitives bit for bit — for rays starting inside (overlapping) primitives, on cell boundaries, axis-parallel
+    rays, rays from outside the grid (full mask), non-finite rays, and degenerate / non-finite / inverted geometry."""
+    rng = np.random.default_rng(23)
+    poisoned = ptb.synthetic_scene(40, 24, seed=9)
+    poisoned.spheres[5].Position = np.array([np.nan, 0, 0], np.float32)
+    poisoned.spheres[6].Radius = np.float32(0.0)
+    poisoned.spheres[7].Radius = np.float32(-0.7)
+    poisoned.cuboids[10].Dimensions = np.array([np.inf, 1, 1], np.float32)
+    poisoned.cuboids[11].Dimensions = np.array([-1.0, 2.0, -0.5], np.float32)
+    for scene, cells, buckets in ((ptb.load_default_scene(), 13, 12), (ptb.load_default_scene(), 5, 3), (poisoned, 13, 12),
+                                  (ptb.synthetic_scene(2, 1, seed=2), 9, 16)):
+        pt = make_tracer(ptb, env256, 16, 16, scene, camera)
+        pt.SetRayClassification(1, cells, buckets)
+        n = 120000
+        o = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.array([44, 36, 28], np.float32) + np.array([0, 2, -10], np.float32)
+        centres = np.nan_to_num(np.stack([s.Position for s in scene.spheres]))
+        pick = rng.integers(0, len(scene.spheres), n // 3)
+        radii = np.abs(np.array([s.Radius for s in scene.spheres], np.float32))[pick, None]
+        o[: n // 3] = centres[pick] + (rng.random((n // 3, 3)).astype(np.float32) - np.float32(0.5)) * radii * np.float32(2.2)
+        cpick = rng.integers(0, len(scene.cuboids), n // 6)
+        cmin = np.stack([c.Min for c in scene.cuboids])[cpick]; cmax = np.stack([c.Max for c in scene.cuboids])[cpick]
+        with np.errstate(all="ignore"):
+            inside_box = cmin + rng.random((n // 6, 3)).astype(np.float32) * (cmax - cmin)
+        o[n // 3: n // 3 + n // 6] = np.nan_to_num(inside_box, posinf=5.0, neginf=-5.0)
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        d[-600:-400, 0] = 0; d[-400:-200, 1] = 0; d[-200:-100, :2] = 0; d[-200:-100, 2] = 1       # axis-parallel: infinite reciprocals
+        d[-700:-600, 1] = d[-700:-600, 0]                                                        # |dx| == |dy|: major-axis ties
+        d[-700:-600] /= np.linalg.norm(d[-700:-600], axis=1, keepdims=True).astype(np.float32)
+        o[-100:-50] *= np.float32(40.0)                                                          # far outside the grid
+        o[-50:-40] = np.nan; d[-40:-30] = np.nan; d[-30:-20] = 0; o[-20:-10, 0] = np.inf          # non-finite / zero rays
+        o[-1000:-700] = np.round(o[-1000:-700] / np.float32(0.5)) * np.float32(0.5)              # lattice points: cell boundaries
+        rays = np.concatenate([o, d], 1).astype(np.float32)
+        ref = oracle.ray_trace(rays, scene.ubo_bytes(), scene.max_spheres, len(scene.spheres), len(scene.cuboids))
+        if len(scene.spheres) + len(scene.cuboids) < 4:
+            with pytest.raises(ptb.PtbError):      # too small to be worth a table: plain fold, nothing to probe
+                pt.DebugEval(10, rays[:1], 1, 12)
+            pt.Dispose()
+            continue
+        assert pt.SceneInfo(4) == 2 and pt.SceneInfo(5) > 0
+        got = pt.DebugEval(10, rays, n, 12 * n).reshape(-1, 12).copy()
+        cand = got[:, 3].copy()
+        got[:, 3] = 0
+        assert_same(got, ref, f"ray-classification fold, {len(scene.spheres)} spheres + {len(scene.cuboids)} cuboids, {cells} cells, {buckets} buckets")
+        finite = np.isfinite(rays).all(axis=1) & (np.abs(rays[:, 3:]).sum(axis=1) > 0)
+        assert (cand[~finite] == 65).all(), "a non-finite or zero ray must take the full mask"
+        assert (cand[-100:-50] == 65).all(), "rays from outside the grid must take the full mask"
+        n_prims = len(scene.spheres) + len(scene.cuboids)
+        in_grid = finite & (cand < 65)
+        assert in_grid.mean() > 0.5
+        if cells >= 9:
+            assert cand[in_grid].mean() < 0.35 * n_prims, f"mean {cand[in_grid].mean():.1f} candidates of {n_prims}: the table culls nothing"
+        hits_per_ray = ref[in_grid, 0].mean()
+        assert cand[in_grid].mean() >= hits_per_ray
+        pt.Dispose()
+
+
+def test_ray_classification_does_not_change_the_image(ptb, oracle, env256, default_scene, camera):
+    """Table on / off / coarse / fine, geometry edits (rebuild) and material edits (no rebuild): always the oracle's image."""
+    sc = ptb.scene
+    W, H = 192, 108
+    ref = oracle_render(oracle, sc, default_scene, camera, env256, W, H, 3, spp=2)
+    for mode, cells, buckets in ((0, 13, 12), (1, 13, 12), (1, 1, 1), (1, 32, 4), (1, 6, 24)):
+        pt = make_tracer(ptb, env256, W, H, default_scene, camera, spp=2)
+        pt.SetRayClassification(mode, cells, buckets)
+        pt.Render(3)
+        assert pt.SceneInfo(4) == (2 if mode else 0)
+        assert_same(pt.Result, ref, f"ray classification mode {mode}, {cells} cells, {buckets} buckets")
+        pt.Dispose()
+    # camera outside the room (every primary ray takes the full mask) and inside a glass sphere
+    for pos in ([-60.0, 30.0, 40.0], list(default_scene.spheres[40].Position + np.float32(0.2))):
+        cam = sc.Camera(np.array(pos, np.float32), np.array([0, 1, 0], np.float32), -32.2, 0.8)
+        pt = make_tracer(ptb, env256, W, H, default_scene, cam)
+        pt.Render(2)
+        assert_same(pt.Result, oracle_render(oracle, sc, default_scene, cam, env256, W, H, 2), f"camera at {pos}")
+        pt.Dispose()
+    # edits: move a sphere / resize a box (table rebuilt), then change a material only (table kept)
+    import copy
+    scene = copy.deepcopy(default_scene)
+    pt = make_tracer(ptb, env256, W, H, scene, camera)
+    pt.Render(1)
+    launches = pt.KernelLaunches
+    scene.spheres[14].Position = scene.spheres[14].Position + np.array([1.5, -2.0, 3.0], np.float32)
+    scene.spheres[14].Upload(pt.GameObjectsUBO)
+    scene.cuboids[6].Dimensions = scene.cuboids[6].Dimensions * np.float32(1.7)
+    scene.cuboids[6].Upload(pt.GameObjectsUBO)
+    pt.ResetRenderer(); pt.Render(2)
+    assert_same(pt.Result, oracle_render(oracle, sc, scene, camera, env256, W, H, 2), "after geometry edits")
+    rebuilt = pt.KernelLaunches - launches
+    scene.spheres[3].Material.Albedo = np.array([0.9, 0.1, 0.2], np.float32)
+    scene.spheres[3].Upload(pt.GameObjectsUBO)
+    launches = pt.KernelLaunches
+    pt.ResetRenderer(); pt.Render(2)
+    assert_same(pt.Result, oracle_render(oracle, sc, scene, camera, env256, W, H, 2), "after a material edit")
+    assert pt.KernelLaunches - launches == rebuilt - 1, "a material edit must repack the scene but not rebuild the table"
+    pt.Dispose()
+
+
 def test_bvh_survives_camera_leaving_the_scene(ptb, oracle, env256):
     """The BVH's safety margins scale with an extent that includes the camera; moving the camera far away must rebuild them."""
     scene = ptb.synthetic_scene(160, 40, seed=8)
