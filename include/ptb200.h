@@ -164,6 +164,19 @@ int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
  * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off;
  * with the fused exchange a batch is capped at the number of exchange slots. */
 int ptb_set_batch(ptb_ctx* ctx, int frames);
+/* Arithmetic of the megakernel (protocols P1 / P2).
+ *   PTB_PRECISION_EXACT (default): the evaluation model of DESIGN.md §2 — IEEE fp32, no contraction, correctly rounded 1/x and
+ *     sqrt, polynomial sin/cos/exp — bit-identical to the CPU oracle and to the reference's shaders compiled for the CPU.
+ *   PTB_PRECISION_FAST: the same kernel source compiled with fused multiply-adds and the GPU's special-function unit
+ *     (MUFU rcp / rsq / sin / cos / ex2, ~1-2 ulp, denormals flushed) — what a GL driver's compiler may do with compute.glsl
+ *     (GLSL 4.50 §4.7.1).  Same RNG stream and control flow; results differ from the exact build in the last bits of most
+ *     samples and, where a discrete decision flips, in individual paths: held to per-channel MSE < 1e-6 against the exact
+ *     build at matched seeds after 1024 frames (the north star's tolerance; tests/test_parity_gpu.py).
+ * The proxy kernel, the statistics counters and the debug probes always run the exact arithmetic. */
+#define PTB_PRECISION_EXACT 0
+#define PTB_PRECISION_FAST 1
+int ptb_set_precision(ptb_ctx* ctx, int precision);
+int ptb_precision(ptb_ctx* ctx);
 /* Ray classification for scenes of 4..64 primitives (default on): rays are classed by origin cell x direction bucket and a
  * table gives each class the set of primitives any of its rays can hit; RayTrace() then tests only those, in index order.
  * cells = grid cells along the longest scene axis (default 13), buckets = direction buckets per cube-face axis (default 12).

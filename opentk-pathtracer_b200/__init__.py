@@ -8,10 +8,10 @@ reference's interface for that path.  Import as `import ptb200` (shim at the rep
 from . import scene
 from ._build import build as build_library
 from ._lib import PtbError, lib_path, load as load_library
-from .pathtracer import (FORMAT_RGB32F, FORMAT_RGBA8, FORMAT_RGBA32F, KERNEL_MEGA, KERNEL_NAIVE, AtmosphericScatterer, BufferObject,
+from .pathtracer import (FORMAT_RGB32F, FORMAT_RGBA8, FORMAT_RGBA32F, KERNEL_MEGA, KERNEL_NAIVE, PRECISION_EXACT, PRECISION_FAST, AtmosphericScatterer, BufferObject,
                          PathTracer, ScreenEffect)
 from .scene import Camera, Cuboid, Material, Scene, Sphere, default_camera, load_default_scene, synthetic_scene
 
 __all__ = ["scene", "build_library", "load_library", "lib_path", "PtbError", "PathTracer", "ScreenEffect", "AtmosphericScatterer", "BufferObject", "KERNEL_MEGA",
-           "KERNEL_NAIVE", "FORMAT_RGBA32F", "FORMAT_RGB32F", "FORMAT_RGBA8", "Camera", "Cuboid", "Material", "Scene", "Sphere", "default_camera", "load_default_scene",
+           "KERNEL_NAIVE", "PRECISION_EXACT", "PRECISION_FAST", "FORMAT_RGBA32F", "FORMAT_RGB32F", "FORMAT_RGBA8", "Camera", "Cuboid", "Material", "Scene", "Sphere", "default_camera", "load_default_scene",
            "synthetic_scene"]

@@ -66,6 +66,8 @@ SIGNATURES = {
     "ptb_kernel_launches": (C.c_int, [_P]),
     "ptb_scene_info": (C.c_int, [_P, C.c_int]),
     "ptb_set_bvh_threshold": (C.c_int, [_P, C.c_int]),
+    "ptb_set_precision": (C.c_int, [_P, C.c_int]),
+    "ptb_precision": (C.c_int, [_P]),
     "ptb_set_ray_classification": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "ptb_last_render_ms": (C.c_float, [_P]),
     "ptb_set_stats": (C.c_int, [_P, C.c_int]),

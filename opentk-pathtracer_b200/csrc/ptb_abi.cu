@@ -3,6 +3,7 @@
 // the packed scene block, and launches the kernels of ptb_kernels.cuh on the context's stream.
 #include "../../include/ptb200.h"
 #include "ptb_kernels.cuh"
+#include "ptb_fast.h"
 
 #include <algorithm>
 #include <cmath>
@@ -133,6 +134,7 @@ struct ptb_ctx {
     unsigned long long batch_seq = 0;
     bool mega_ring = true;
     int mega_fold_set = -1;
+    int precision = PTB_PRECISION_EXACT, mega_precision_set = -1;   // ptb_set_precision: which translation unit's megakernel runs
 };
 
 namespace {
@@ -563,6 +565,9 @@ int with_mega_fold(ptb_ctx* c, bool stats, F&& launch)
     if (c->mega_ring) return stats ? launch(megakernel<true, true, kFold>) : launch(megakernel<false, true, kFold>);
     return stats ? launch(megakernel<true, false, kFold>) : launch(megakernel<false, false, kFold>);
 }
+// One megakernel launch of the current configuration (exact or fast translation unit) on `stream`.
+int launch_mega(ptb_ctx* c, const RenderParams& P, bool batch, int smem, cudaStream_t stream);
+
 template <class F>
 int with_mega(ptb_ctx* c, bool stats, F&& launch)
 {
@@ -602,20 +607,25 @@ int launch_frame(ptb_ctx* c)
     }
     const int smem = c->stage_bytes;
     const int fold = fold_of(c);
-    if (c->mega_smem_set != smem || c->mega_fold_set != fold) {
+    if (c->mega_smem_set != smem || c->mega_fold_set != fold || c->mega_precision_set != c->precision) {
         int with_ring = 0, without = 0;
-        const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, without) : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, without) : prepare_mega<0>(c, smem, with_ring, without));
-        if (rc != PTB_OK) return rc;
+        if (c->precision == PTB_PRECISION_FAST) {
+            CU(ptb_fast_api::prepare(fold, smem, &with_ring, &without));
+        } else {
+            const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, without) : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, without) : prepare_mega<0>(c, smem, with_ring, without));
+            if (rc != PTB_OK) return rc;
+        }
         if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
         c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
         c->mega_grid = std::max(c->sm_count, c->sm_count * (c->mega_ring ? with_ring : without) / c->grid_divisor);
         c->mega_smem_set = smem;
         c->mega_fold_set = fold;
+        c->mega_precision_set = c->precision;
     }
     if (c->local_rows > 0) {
         if (c->overlap <= 1) {
             // classic: accumulate in place on the user-visible stream
-            const int rc = with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, c->stream>>>(P); return PTB_OK; });
+            const int rc = launch_mega(c, P, false, smem, c->stream);
             if (rc != PTB_OK) return rc;
             c->launches++;
             CU(cudaGetLastError());
@@ -628,9 +638,8 @@ int launch_frame(ptb_ctx* c)
             if (c->blend_recorded[s]) CU(cudaStreamWaitEvent(ts, c->ev_blend_done[s], 0));      // scratch[s] has been consumed
             P.scratch = c->d_scratch[s];
             P.counters = c->d_slot_counters[s];
-            const int rc = with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, ts>>>(P); return PTB_OK; });
+            const int rc = launch_mega(c, P, false, smem, ts);
             if (rc != PTB_OK) return rc;
-            CU(cudaGetLastError());
             CU(cudaEventRecord(c->ev_trace_done[s], ts));
             cudaStream_t bs = c->blend_stream;
             if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
@@ -682,6 +691,19 @@ int with_mega_batch(ptb_ctx* c, F&& launch)
     }
 }
 
+int launch_mega(ptb_ctx* c, const RenderParams& P, bool batch, int smem, cudaStream_t stream)
+{
+    if (c->precision == PTB_PRECISION_FAST) {
+        CU(ptb_fast_api::launch(&P, fold_of(c), c->mega_ring, batch, c->mega_grid, smem, stream));
+        return PTB_OK;
+    }
+    const int rc = batch ? with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; })
+                         : with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; });
+    if (rc != PTB_OK) return rc;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
 bool batch_eligible(const ptb_ctx* c)
 {
     // the frame slot rides in bits 12..15 of the ring's pixel word; statistics and the proxy kernel stay per frame
@@ -721,7 +743,7 @@ int launch_batch(ptb_ctx* c, int frames)
     RenderParams P;
     fill_params(c, P);
     const int smem = c->stage_bytes;
-    if (c->mega_smem_set != smem || c->mega_fold_set != fold_of(c)) {
+    if (c->mega_smem_set != smem || c->mega_fold_set != fold_of(c) || c->mega_precision_set != c->precision) {
         // the grid / ring decision (and the shared-memory attributes of every instantiation) belong to the single-frame path
         const int rc = launch_frame(c);
         if (rc != PTB_OK) return rc;
@@ -735,9 +757,8 @@ int launch_batch(ptb_ctx* c, int frames)
     P.counters = c->d_batch_counters[s];
     P.batch = frames;
     P.scratch_stride = (unsigned long long)c->batch_scratch_stride;
-    const int rc = with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, ts>>>(P); return PTB_OK; });
+    const int rc = launch_mega(c, P, true, smem, ts);
     if (rc != PTB_OK) return rc;
-    CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_batch_trace[s], ts));
     cudaStream_t bs = c->blend_stream;
     if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
@@ -1315,6 +1336,20 @@ int ptb_set_grid_divisor(ptb_ctx* c, int d)
     c->mega_smem_set = -1;           // recompute the grid at the next launch
     return PTB_OK;
 }
+int ptb_set_precision(ptb_ctx* c, int precision)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (precision != PTB_PRECISION_EXACT && precision != PTB_PRECISION_FAST) return fail(PTB_E_INVALID, "unknown precision %d", precision);
+    if (precision == PTB_PRECISION_FAST) {
+        if (ptb_fast_api::params_size() != sizeof(RenderParams) || ptb_fast_api::threads() != kMegaThreads)
+            return fail(PTB_E_STATE, "the fast translation unit was built with a different RenderParams layout");
+        if (c->stats_on) return fail(PTB_E_STATE, "path statistics are collected by the exact build only (ptb_set_stats(0) first)");
+    }
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    c->precision = precision;
+    return PTB_OK;
+}
+int ptb_precision(ptb_ctx* c) { return c ? c->precision : fail(PTB_E_INVALID, "ctx is null"); }
 int ptb_set_ray_classification(ptb_ctx* c, int mode, int cells, int buckets)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
@@ -1359,6 +1394,7 @@ float ptb_last_render_ms(ptb_ctx* c)
 int ptb_set_stats(ptb_ctx* c, int enabled)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (enabled && c->precision == PTB_PRECISION_FAST) return fail(PTB_E_STATE, "path statistics are collected by the exact build only (ptb_set_precision(PTB_PRECISION_EXACT) first)");
     c->stats_on = enabled != 0;
     CU(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
     return mark_inputs(c);

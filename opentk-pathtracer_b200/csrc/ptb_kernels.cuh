@@ -670,6 +670,7 @@ __device__ __forceinline__ void trace_rct(const RenderParams& P, const PackedSce
     }
 }
 
+#ifndef PTB_MEGA_ONLY      // (the fast-arithmetic translation unit compiles the megakernel only)
 // Table build: one thread per (cell, face, gv, gu).  The class's rays are { o + s * (sgn e_m + u e_a + v e_b) : o in the
 // cell, u in [u0,u1], v in [v0,v1], s >= 0 } (s = distance along the major axis m).  Such a ray meets the box [klo,khi] iff
 // some s >= 0 satisfies three interval conditions — on the major axis directly, on each minor axis through
@@ -729,6 +730,8 @@ __global__ void rct_build_kernel(const __grid_constant__ RctBuild B)
     B.table[id] = mask;
 }
 
+#endif  // PTB_MEGA_ONLY
+
 // pt:125-129 — mean over SPP, running mean over frames, store.  Frame 0 does not read the image: the reference
 // multiplies the stale value by exactly 0 there (mix(x, y, 1.0)), so a zero stands in for it.
 __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& p, size_t frame_offset = 0)
@@ -749,6 +752,7 @@ __device__ __forceinline__ void finish_pixel(const RenderParams& P, const Path& 
     *px = make_float4(out.x, out.y, out.z, 1.0f);
 }
 
+#ifndef PTB_MEGA_ONLY
 // pt:126-129 for pipelined frames: image = mix(image, this frame's estimate, 1/(frame+1)) — the same operations, in the same
 // order, as finish_pixel's in-place path; one thread per pixel, 128-bit loads and stores.
 __global__ void blend_kernel(float4* __restrict__ image, const float4* __restrict__ estimate, size_t n, int frame, float blend)
@@ -764,6 +768,8 @@ __global__ void blend_kernel(float4* __restrict__ image, const float4* __restric
     const V3 out = mix(last, mk(e.x, e.y, e.z), blend);
     image[i] = make_float4(out.x, out.y, out.z, 1.0f);
 }
+
+#endif  // PTB_MEGA_ONLY
 
 // local row -> global y for the stripe partition
 __device__ __forceinline__ int global_row(const RenderParams& P, int lrow)
@@ -986,6 +992,7 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
     }
 }
 
+#ifndef PTB_MEGA_ONLY
 // ------------------------------------------------------------------------------------------------------------
 // The labelled GL-compute proxy: the reference's own launch shape (8x8 groups, one invocation per pixel,
 // ceil(W/8) x ceil(H/8) groups — PathTracer.cs:121, pt:8) reading the raw std140 UBO bytes.  Baseline only.
@@ -1480,5 +1487,7 @@ __global__ void dbg_arith_kernel(const float* in, int n, float* out)
         out[4 * i] = fmin_(a, b); out[4 * i + 1] = fmax_(a, b); out[4 * i + 2] = rcp(a); out[4 * i + 3] = fsqrt(b);
     }
 }
+
+#endif  // PTB_MEGA_ONLY
 
 } // namespace ptb

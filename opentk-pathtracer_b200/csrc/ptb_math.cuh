@@ -21,9 +21,20 @@ __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y *
 __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
 
+#ifdef PTB_FAST
+// The fast build (ptb_fast.cu, ptb_set_precision(PTB_PRECISION_FAST)): the hardware's special-function unit for 1/x, sqrt,
+// 1/sqrt, sin, cos, 2^x (MUFU, ~1-2 ulp, denormals flushed) and, through -fmad=true, fused multiply-adds wherever the
+// compiler finds them — roughly what a GL driver's compiler does with the same GLSL.  Not bit-comparable with anything;
+// held to the exact build by the north star's tolerance (per-channel MSE < 1e-6 at matched seeds, tests/).
+__device__ __forceinline__ float rcp(float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * rcp(b); }
+__device__ __forceinline__ float fsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float frsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+#else
 __device__ __forceinline__ float rcp(float b) { return __frcp_rn(b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return a * __frcp_rn(b); }
 __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+#endif
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }   // FMNMX: NaN loses, -0 < +0
 __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
@@ -31,11 +42,15 @@ __device__ __forceinline__ float stepf(float edge, float x) { return x < edge ? 
 __device__ __forceinline__ float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 __device__ __forceinline__ float mixf(float x, float y, float a) { return __fmaf_rn(y, a, x * (1.0f - a)); }
 __device__ __forceinline__ float pow5(float x) { float x2 = x * x; float x4 = x2 * x2; return x4 * x; }
-__device__ __forceinline__ float pow15(float x) { return x * __fsqrt_rn(x); }
+__device__ __forceinline__ float pow15(float x) { return x * fsqrt(x); }
 
 __device__ __forceinline__ float dot(V3 a, V3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
-__device__ __forceinline__ float length(V3 a) { return __fsqrt_rn(dot(a, a)); }
+__device__ __forceinline__ float length(V3 a) { return fsqrt(dot(a, a)); }
+#ifdef PTB_FAST
+__device__ __forceinline__ V3 normalize(V3 a) { return a * frsqrt(dot(a, a)); }
+#else
 __device__ __forceinline__ V3 normalize(V3 a) { return a * __frcp_rn(__fsqrt_rn(dot(a, a))); }
+#endif
 __device__ __forceinline__ V3 mix(V3 a, V3 b, float t) { return mk(mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t)); }
 
 // GLSL reflect: I - 2*dot(N,I)*N
@@ -50,7 +65,7 @@ __device__ __forceinline__ V3 refract(V3 I, V3 N, float eta)
     const float d = dot(N, I);
     const float k = 1.0f - (eta * eta) * (1.0f - d * d);
     if (k < 0.0f) return mk(0.0f, 0.0f, 0.0f);
-    const float s = eta * d + __fsqrt_rn(k);
+    const float s = eta * d + fsqrt(k);
     return mk(eta * I.x - s * N.x, eta * I.y - s * N.y, eta * I.z - s * N.z);
 }
 
@@ -67,6 +82,11 @@ __device__ __forceinline__ float mat_row(const float* __restrict__ M, int r, flo
 // sin & cos by 3-term Cody-Waite reduction modulo pi/2 and degree-7 / degree-8 minimax kernels.
 __device__ __forceinline__ void sincos_(float x, float& s, float& c)
 {
+#ifdef PTB_FAST
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
+    return;
+#endif
     const float magic = 12582912.0f;                     // 1.5 * 2^23
     const float t = __fmaf_rn(x, 0.636619747f, magic);   // round(x * 2/pi) in the low mantissa bits
     const float q = t - magic;
@@ -93,6 +113,11 @@ __device__ __forceinline__ void sincos_(float x, float& s, float& c)
 // exp(x) = 2^k * e^r, k = round(x log2 e), r = x - k ln2 (two-term), degree-5 kernel on r^2, two-step scaling.
 __device__ __forceinline__ float exp_(float x)
 {
+#ifdef PTB_FAST
+    float e2;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x * 1.44269504f));
+    return e2;
+#endif
     if (x != x) return x + x;
     if (x > 88.7228394f) return __uint_as_float(0x7f800000u);
     if (x < -103.972084f) return 0.0f;

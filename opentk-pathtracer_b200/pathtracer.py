@@ -19,6 +19,7 @@ from . import scene as _scene
 FORMAT_RGBA32F, FORMAT_RGB32F, FORMAT_RGBA8 = 0, 1, 2      # ptb_read_result_format_async
 KERNEL_MEGA = 0
 KERNEL_NAIVE = 1
+PRECISION_EXACT, PRECISION_FAST = 0, 1                      # ptb_set_precision
 
 
 def _as_bytes(data) -> bytes:
@@ -307,6 +308,14 @@ class PathTracer:
     @property
     def KernelLaunches(self) -> int:
         return _lib.check(self._L.ptb_kernel_launches(self._ctx))
+
+    def SetPrecision(self, precision: int) -> None:
+        """PRECISION_EXACT (default; bit-identical to the oracle) or PRECISION_FAST (MUFU + FMA build of the same kernel)."""
+        _lib.check(self._L.ptb_set_precision(self._ctx, int(precision)))
+
+    @property
+    def Precision(self) -> int:
+        return _lib.check(self._L.ptb_precision(self._ctx))
 
     def SetRayClassification(self, mode: int = 1, cells: int = 13, buckets: int = 12) -> None:
         """Ray-classification table for scenes of <= 64 primitives (ptb_set_ray_classification); mode 0 = plain fold."""

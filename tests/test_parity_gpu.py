@@ -442,6 +442,69 @@ def test_progressive_accumulation_to_1024_spp(ptb, oracle, env256, default_scene
     pt.Dispose()
 
 
+def test_fast_precision_meets_the_north_star_tolerance(ptb, env256, default_scene, camera):
+    """SURVEY 8c protocol P2: the fast build (MUFU rcp/rsq/sin/cos/ex2 + FMA contraction, ptb_set_precision) against the exact
+    build on BASELINE config 2 itself — default scene, 1920x1080, frames 0..1023 at SPP 1, matched seeds.  Tolerance (north
+    star): per-channel MSE < 1e-6 on the accumulated linear image.  Also reported: how many pixels of frame 0 took another
+    path (differ by more than rounding), and that the fast build is deterministic."""
+    W, H, FRAMES = 1920, 1080, 1024
+    images, first = {}, {}
+    for prec in (ptb.PRECISION_EXACT, ptb.PRECISION_FAST):
+        pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+        pt.SetPrecision(prec)
+        assert pt.Precision == prec
+        pt.Render(1)
+        first[prec] = pt.Result[..., :3].astype(np.float64)
+        pt.Render(FRAMES - 1)
+        images[prec] = pt.Result[..., :3].astype(np.float64)
+        if prec == ptb.PRECISION_FAST:
+            pt.ResetRenderer(); pt.Render(1)
+            assert (pt.Result[..., :3] == first[prec].astype(np.float32)).all(), "the fast build is not deterministic"
+            with pytest.raises(ptb.PtbError):
+                pt.SetStats(True)                  # statistics are the exact build's
+        pt.Dispose()
+    a, b = images[ptb.PRECISION_EXACT], images[ptb.PRECISION_FAST]
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    mse = ((a - b) ** 2).mean(axis=(0, 1))
+    d0 = np.abs(first[ptb.PRECISION_EXACT] - first[ptb.PRECISION_FAST])
+    rel = d0 / np.maximum(np.abs(first[ptb.PRECISION_EXACT]), 1e-3)
+    diverged = (rel > 1e-3).any(axis=2).mean()
+    touched = (d0 > 0).any(axis=2).mean()
+    print(f"fast vs exact after {FRAMES} frames: per-channel MSE {mse}, frame 0: {touched * 100:.1f} % of pixels differ in some bit, "
+          f"{diverged * 100:.3f} % took another path; mean radiance {a.mean():.4f} vs {b.mean():.4f}")
+    assert (mse < 1e-6).all(), f"per-channel MSE {mse} exceeds the north star's 1e-6"
+    assert diverged < 0.02
+    assert abs(a.mean() - b.mean()) < 1e-3 * a.mean()
+
+
+def test_fast_precision_other_paths(ptb, oracle, env256, camera):
+    """The fast build through the other instantiations: BVH scene, plain fold (table off), SPP > 1, batches, tiles — each
+    close to the exact build (same seeds; a few paths per thousand may differ), never NaN where the exact build is finite."""
+    sc = ptb.scene
+    cases = [("BVH scene", sc.synthetic_scene(256, 64, seed=5), dict(depth=8), {}),
+             ("plain fold", sc.load_default_scene(), {}, dict(rct=0)),
+             ("SPP 3, batch 4", sc.load_default_scene(), dict(spp=3), dict(batch=4)),
+             ("stripes 1 of 3", sc.load_default_scene(), {}, dict(tile=(1, 3, 8)))]
+    W, H = 320, 180
+    for name, scene, kw, opt in cases:
+        res = {}
+        for prec in (ptb.PRECISION_EXACT, ptb.PRECISION_FAST):
+            pt = make_tracer(ptb, env256, W, H, scene, camera, **kw)
+            pt.SetPrecision(prec)
+            if "rct" in opt: pt.SetRayClassification(opt["rct"])
+            if "batch" in opt: pt.SetBatch(opt["batch"])
+            if "tile" in opt: pt.SetTile(*opt["tile"])
+            pt.Render(24)
+            res[prec] = pt.Result[..., :3].astype(np.float64)
+            pt.Dispose()
+        a, b = res[ptb.PRECISION_EXACT], res[ptb.PRECISION_FAST]
+        assert np.isfinite(b[np.isfinite(a)]).all(), name
+        fin = np.isfinite(a) & np.isfinite(b)
+        close = np.abs(a - b) <= 1e-3 * np.maximum(np.abs(a), 1e-2)
+        assert close[fin].mean() > 0.97, f"{name}: only {close[fin].mean() * 100:.1f} % of the channels agree to 1e-3"
+        assert abs(a[fin].mean() - b[fin].mean()) < 0.02 * a[fin].mean(), name
+
+
 def test_golden_image(ptb, default_scene, camera):
     env16 = np.load(os.path.join(GOLD, "env16.npy"))
     pt = make_tracer(ptb, env16, 64, 64, default_scene, camera)
