@@ -1,24 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — Msamples/s of the path-tracing pass on the default demo scene at 1920x1080 (BASELINE.json configs[1]).
+"""bench.py — Msamples/s of the path-tracing pass (BASELINE.json's metric) on one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4] [--precision auto|fast|exact]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A step = one PathTracer.Render() of the whole frame (one dispatch in the reference, PathTracer.cs:114-129): 1920*1080
-pixels x SPP 1 = 2 073 600 samples, rayDepth 13, focal 20, aperture 0.14, default camera, 256^2 atmosphere cubemap.
-At N > 1 the same frame is cut into interleaved 8-row stripes (one process per GPU), and every step ends with the one
-exchange the path has: a gather of the stripe buffers to rank 0 + de-interleave.  Fixed total work => "strong" scaling.
+Workloads (BASELINE.json `configs`):  c2 (default) = default demo scene, 1920x1080, progressive accumulation at SPP 1 per
+frame — the configuration the metric is quoted on;  c3 = synthetic 1024 spheres + 256 cuboids, 1080p, rayDepth 8;
+c4 = the default scene at 3840x2160 (the 8-GPU tile-partition case).
 
-Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the launching stream, inputs resident in HBM, L2
-flushed before every timed step; `e2e` goes through the same public API with host buffers: the per-frame camera UBO
-upload the C# host does (MainWindow.cs:131-132) and a read-back of every frame into pinned host memory as RGB32F (the
-colour floats bit for bit; the constant alpha 1.0 is not shipped) — at N > 1 each rank writes its stripes straight into one
-full-frame image in host memory shared by all ranks, over its own PCIe link.  `gl_proxy` (N = 1) is the reference's own
-compute.glsl compiled by nvcc and dispatched in the reference's launch shape, run in a subprocess after the timed regions.
-`--impl reference` times the reference's own compute shader on the host CPUs: compute.glsl compiled by g++ from
-/root/reference through oracle/build_ref.py (oracle/_ref/libglsl_ref.so, kind "reference"), all host threads; where that
-binary is absent it falls back to the oracle's C restatement (kind "port").  The reference's C# + OpenGL host cannot run
-here (no .NET, no GL).
+A step = one PathTracer.Render() of the whole frame (one dispatch in the reference, PathTracer.cs:114-129) = W*H*SPP samples.
+Consecutive steps are consecutive frames of ONE progressive render (static camera), which is what configs[1] describes; the
+library traces them in batches of up to 16 frames per persistent-kernel launch (ptb_set_batch) and folds each batch into the
+accumulation image with one blend kernel — bit-identical to frame-by-frame dispatches.  At N > 1 the frame is cut into
+interleaved 8-row stripes, one process per GPU, and every frame still reaches rank 0 through the path's one exchange (fused
+into the blend kernel: peer stores over NVLink; PTB_EXCHANGE=nccl selects an NCCL gather).  Fixed total work => "strong".
+
+Arithmetic: `value` is measured with the precision named in config.precision.  `--precision auto` (default) first checks
+the fast build (MUFU + FMA) against the exact build on this very workload at matched seeds — per-channel MSE of the
+accumulated image must be below the north star's 1e-6 — and uses it when it passes; the exact build (bit-identical to the
+CPU oracle and the compiled reference shaders) is timed beside it and reported under `exact`.
+
+Prints ONE JSON line (rank 0).  `value`: CUDA events on the launching stream around K steps, inputs resident in HBM.
+L2: no flush kernel runs inside the timed region — the frame estimates rotate through 2 x 16 scratch images per rank
+(>= 0.5 GB at 1080p on one GPU), far more than the 126 MB L2, so no step finds its inputs or outputs cached.
+`e2e`: the same metric through the public API with host buffers, one Render() per step: the per-frame camera UBO upload
+the C# host does (MainWindow.cs:131-132) and a read-back of every frame into pinned host memory as RGB32F.
+`--impl reference` times the reference's own compute shader on the host CPUs (oracle/_ref: compute.glsl compiled by g++ from
+/root/reference, kind "reference"; else the oracle port), all host threads, a bounded sample per step.
 """
 import argparse
 import json
@@ -32,12 +40,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 1920, 1080
-RAY_DEPTH, SPP, FOCAL, APERTURE = 13, 1, 20.0, 0.14
-WORKLOAD = "default demo scene (48 spheres + 7 cuboids), 1920x1080, SPP 1 per frame, rayDepth 13, 256^2 atmosphere env (BASELINE configs[1])"
+SPP, FOCAL, APERTURE = 1, 20.0, 0.14
+CONFIGS = {
+    "c2": dict(W=1920, H=1080, ray_depth=13, scene="default", gate_frames=1024,
+               workload="default demo scene (48 spheres + 7 cuboids), 1920x1080, SPP 1 per frame, rayDepth 13, 256^2 atmosphere env (BASELINE configs[1])"),
+    "c3": dict(W=1920, H=1080, ray_depth=8, scene="synthetic", gate_frames=128,
+               workload="synthetic scene (1024 spheres + 256 cuboids, seed 1234), 1920x1080, SPP 1 per frame, rayDepth 8, 256^2 atmosphere env (BASELINE configs[2])"),
+    "c4": dict(W=3840, H=2160, ray_depth=13, scene="default", gate_frames=256,
+               workload="default demo scene (48 spheres + 7 cuboids), 3840x2160, SPP 1 per frame, rayDepth 13, 256^2 atmosphere env (BASELINE configs[3])"),
+}
 STRIPE_ROWS = 8
-EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "4"))      # full-image buffers on rank 0: how far the ranks may drift apart
-L2_FLUSH_BYTES = 160 << 20      # larger than the 126 MB L2
+BATCH = max(1, min(16, int(os.environ.get("PTB_BATCH", "16"))))
+EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "16"))      # full-image buffers on rank 0 (>= the batch: every frame of a batch has its own)
+MSE_TOLERANCE = 1e-6                                         # north star: per-channel MSE at matched seed
 
 
 def measured_peaks():
@@ -50,20 +65,8 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def issue_roofline(ncu, kern_ms, world):
-    """The bound that actually binds: warp-instructions issued per second against 148 SMs x 4 schedulers x SM clock.
-    Instruction count per launch comes from the committed ncu capture (full frame); duration is measured live."""
-    inst = ncu.get("inst_executed_per_launch")
-    if not inst:
-        return None
-    achieved = inst / world / (kern_ms * 1e-3) / 1e12
-    peak = 148 * 4 * 1.965e9 / 1e12
-    return {"achieved": achieved, "peak": peak, "unit": "T warp-inst/s", "frac": achieved / peak,
-            "note": "peak = 148 SMs x 4 issue slots x 1.965 GHz; instructions per launch from profiles/ncu_summary.json"}
-
-
 def ncu_summary():
-    """Per-launch DRAM traffic of the megakernel from the committed `ncu --set full` capture (profiles/), if any."""
+    """Figures of the committed `ncu --set full` capture of the megakernel (profiles/ncu_summary.json), if any."""
     p = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(p):
         try:
@@ -105,7 +108,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -134,6 +137,12 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def load_scene(cfg):
+    import ptb200
+    sc = ptb200.scene
+    return sc.load_default_scene() if cfg["scene"] == "default" else sc.synthetic_scene(1024, 256)
+
+
 # ================================================================================================ reference arm
 def host_threads():
     """Threads the CPU arm may use: the cores this process is allowed on.  torchrun exports OMP_NUM_THREADS=1 to its workers,
@@ -144,11 +153,14 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference():
+def cpu_reference(max_spheres=256):
     """(module, kind, description): the compiled reference shaders when oracle/_ref was built, else the oracle port."""
     from oracle import oracle as O, ref as R
-    if R.available():
+    if max_spheres == 256 and R.available():
         return R, "reference", "the reference's compute.glsl compiled for the CPU (g++, oracle/build_ref.py -> oracle/_ref/libglsl_ref.so); its C# + OpenGL host needs .NET + GL 4.5, absent here"
+    big = os.path.join(ROOT, "oracle", "_ref", f"libglsl_ref_{max_spheres}x256.so")
+    if max_spheres != 256 and os.path.exists(big):
+        return R.variant(big), "reference", f"the reference's compute.glsl with its two UBO array lengths rewritten to {max_spheres}/256 (build_ref.py --capacity), compiled for the CPU"
     return O, "port", "CPU oracle (C restatement of compute.glsl); oracle/_ref not built on this machine"
 
 
@@ -159,18 +171,22 @@ def run_reference(args, rank, world):
         return
     import ptb200
     from oracle import oracle as O_
-    O, kind, kind_text = cpu_reference()
+    cfg = CONFIGS[args.config]
+    W, H = cfg["W"], cfg["H"]
+    scene = load_scene(cfg)
+    O, kind, kind_text = cpu_reference(scene.max_spheres)
     sc = ptb200.scene
     threads = host_threads()
-    env = O.atmosphere(256, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 50, 15, threads)
-    scene, cam = sc.load_default_scene(), sc.default_camera()
+    env = O_.atmosphere(256, sc.atmosphere_ubo_bytes(), sc.atmosphere_light_pos(0.5), 15.0, 50, 15, threads)
+    cam = sc.default_camera()
     basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
     img = np.zeros((H, W, 4), np.float32)
-    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7, n_threads=threads)
-    # calibrate on one full frame, then bound the per-step sample so warmup + steps stay under ~150 s
+    kw = dict(spp=SPP, ray_depth=cfg["ray_depth"], focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=len(scene.spheres),
+              n_cuboids=len(scene.cuboids), max_spheres=scene.max_spheres, n_threads=threads)
+    # calibrate on a sparse sample, then bound the per-step sample so warmup + steps stay under ~150 s
     t = time.perf_counter()
-    O.render(img, basic, ubo, env, frame=0, **kw)
-    full_s = time.perf_counter() - t
+    O.render(img, basic, ubo, env, frame=0, y_step=16, **kw)
+    full_s = (time.perf_counter() - t) * 16
     budget = 150.0 / max(1, args.steps + args.warmup)
     y_step = max(1, min(64, int(np.ceil(full_s / budget))))          # every y_step-th row: spread over sky, spheres and floor
     rows_per_step = len(range(0, H, y_step))
@@ -186,11 +202,11 @@ def run_reference(args, rank, world):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     value = px_per_step * SPP * args.steps / dt / 1e6
-    sample = f"every {y_step}-th row of the 1920x1080 frame per step ({rows_per_step} rows, {px_per_step} samples/step)" if y_step > 1 else "the full 1920x1080 frame per step"
+    sample = f"every {y_step}-th row of the {W}x{H} frame per step ({rows_per_step} rows, {px_per_step} samples/step)" if y_step > 1 else f"the full {W}x{H} frame per step"
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference_kind": kind_text},
+            "config": {"workload": cfg["workload"], "name": args.config, "reference_kind": kind_text},
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -205,24 +221,17 @@ def run_ours(args, rank, world, local_rank):
     from importlib import import_module
     D = import_module("opentk-pathtracer_b200.distributed")
 
+    cfg = CONFIGS[args.config]
+    W, H, RAY_DEPTH = cfg["W"], cfg["H"], cfg["ray_depth"]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     sc = ptb200.scene
-    scene, cam = sc.load_default_scene(), sc.default_camera()
-    pt = ptb200.PathTracer(None, W, H, RAY_DEPTH, SPP, FOCAL, APERTURE, device=local_rank)
+    scene, cam = load_scene(cfg), sc.default_camera()
+    pt = ptb200.PathTracer(None, W, H, RAY_DEPTH, SPP, FOCAL, APERTURE, max_spheres=scene.max_spheres, max_cuboids=scene.max_cuboids, device=local_rank)
     pt.SetStream(torch.cuda.current_stream(dev).cuda_stream)
-    # frames in flight: 2 on one GPU (a third starves the read-back snapshot of SM slots and costs e2e), 3 when the frame is
-    # split over several GPUs (small per-GPU tiles are dominated by the per-frame tail; measured at N = 8: 22.1 -> 25.7 Gsamples/s)
-    frames_in_flight = int(os.environ.get("PTB_OVERLAP", "3" if world > 1 else "2"))
+    frames_in_flight = int(os.environ.get("PTB_OVERLAP", "2"))
     pt.SetOverlap(frames_in_flight)
-    # opt-in experiment knobs (defaults leave everything as measured in round 1): PTB_BATCH = frames per megakernel launch
-    # (ptb_set_batch; the device-timed loops then submit that many steps per call), PTB_GRID_DIV = ptb_set_grid_divisor
-    batch = max(1, int(os.environ.get("PTB_BATCH", "1")))
-    grid_div = max(1, int(os.environ.get("PTB_GRID_DIV", "1")))
-    if batch > 1:
-        pt.SetBatch(batch)
-    if grid_div > 1:
-        pt.SetGridDivisor(grid_div)
+    pt.SetBatch(BATCH)
     pt.GenerateAtmosphere(256, 50, 15, 0.5, 15.0)      # the default EnvironmentMap, produced on the GPU (MainWindow.cs:174-175)
     pt.LoadScene(scene)
     pt.SetCamera(cam)
@@ -244,15 +253,122 @@ def run_ours(args, rank, world, local_rank):
                 fused, tiled = False, None
         if tiled is None:
             tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=False)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     inv_view = sc.matrix_bytes(sc.inverted(cam.View))
     view_pos = np.append(np.asarray(cam.Position, np.float32), np.float32(0)).tobytes()
     rows_local = pt.Result.shape[0]
+    samples_per_step = W * H * SPP
 
-    # e2e read-back format: RGB32F — the colour floats bit for bit; the alpha the shader stores is the constant 1.0
-    # (compute.glsl:129) and stays on the device.  N = 1: compact pipelined read into pinned memory.  N > 1: every rank writes
-    # its stripes straight into ONE full-frame image in pinned host memory shared by all ranks (each over its own PCIe link);
-    # if that mapping cannot be set up on every rank, the legacy path copies rank 0's assembled RGBA32F image instead.
+    def local_image():
+        ptr, _ = pt.ResultDevicePtr()
+        return torch.as_tensor(D._DeviceBuffer(ptr, (rows_local, W, 4)), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device(n=1):
+        if tiled is None:
+            pt.Render(n)
+        elif fused:
+            tiled.step_batch(n)    # one trace launch per batch; every frame still reaches rank 0 through its own slot
+        else:
+            for _ in range(n):
+                tiled.step()       # render f; finish gather f-1 (it overlapped this render); start gather f
+
+    def finish_device():
+        if tiled is not None:
+            tiled.flush()
+
+    def run_steps(steps):
+        for k in range(0, steps, BATCH):
+            step_device(min(BATCH, steps - k))
+        finish_device()
+
+    # ------------------------------------------------------------------ precision gate (outside every timed region)
+    gate = None
+    precision = args.precision
+    if precision in ("auto", "fast"):
+        n_gate = cfg["gate_frames"]
+        imgs = {}
+        for prec in (ptb200.PRECISION_EXACT, ptb200.PRECISION_FAST):
+            pt.SetPrecision(prec)
+            pt.ResetRenderer()
+            run_steps(n_gate)
+            pt.Synchronize()
+            torch.cuda.synchronize(dev)
+            imgs[prec] = local_image()[..., :3].double().clone()
+        diff = imgs[ptb200.PRECISION_EXACT] - imgs[ptb200.PRECISION_FAST]
+        stats = torch.stack([(diff ** 2).sum(dim=(0, 1)), torch.full((3,), float(diff[..., 0].numel()), device=dev, dtype=torch.float64)])
+        finite = torch.isfinite(diff).all().float()
+        if world > 1:
+            dist.all_reduce(stats)
+            dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+        mse = (stats[0] / stats[1]).tolist()
+        passed = bool(finite.item() >= 1 and max(mse) < MSE_TOLERANCE)
+        gate = {"frames": n_gate, "per_channel_mse_fast_vs_exact": mse, "tolerance": MSE_TOLERANCE, "passed": passed,
+                "note": "accumulated image after `frames` frames at SPP 1, matched seeds, this workload, all ranks' stripes"}
+        del imgs, diff
+        if precision == "auto":
+            precision = "fast" if passed else "exact"
+    headline = ptb200.PRECISION_FAST if precision == "fast" else ptb200.PRECISION_EXACT
+
+    # ------------------------------------------------------------------ device-timed region
+    def timed(steps):
+        """K steps enqueued in batches on the launching stream, one CUDA-event bracket around the whole region (the pipeline is
+        drained inside it).  No flush kernel: the estimates rotate through 2 x BATCH scratch images (> L2)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        run_steps(steps)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def measure(prec, steps, with_clocks):
+        pt.SetPrecision(prec)
+        pt.ResetRenderer()
+        run_steps(max(args.warmup, 3))
+        launches0 = pt.KernelLaunches
+        if with_clocks:
+            with ClockSampler(physical_gpu_index(local_rank)) as clocks:
+                ms = timed(steps)
+            clk = clocks.summary()
+        else:
+            ms, clk = timed(steps), None
+        launches = pt.KernelLaunches - launches0
+        # the megakernel launches themselves, in the same batched / pipelined / tiled mode (event pair around each launch)
+        barrier()
+        pt.SetKernelTiming(True)
+        run_steps(max(BATCH, min(steps, 8 * BATCH)))
+        barrier()
+        kt = pt.KernelTime()
+        pt.SetKernelTiming(False)
+        kern = torch.tensor([kt["ms"] / max(1, kt["frames"]), kt["ms"] / max(1, kt["launches"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+        return ms, launches, clk, float(kern[0].item()), float(kern[1].item()), kt["frames"] // max(1, kt["launches"])
+
+    ms_total, launches, clocks, kern_ms, kern_launch_ms, frames_per_launch = measure(headline, args.steps, True)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "note": "not a bench value"}), flush=True)
+        pt.Dispose()
+        return
+    exact = None
+    if headline != ptb200.PRECISION_EXACT:
+        n_x = max(BATCH, args.steps // 2)
+        ms_x, _, _, kern_x, _, _ = measure(ptb200.PRECISION_EXACT, n_x, False)
+        exact = {"value": samples_per_step * n_x / (ms_x * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_x / n_x, "kernel_ms": kern_x,
+                 "note": "the exact build (bit-identical to the CPU oracle and the compiled reference shaders), same mode, half the steps"}
+        pt.SetPrecision(headline)
+
+    # ------------------------------------------------------------------ end to end
     shared = None
     if world > 1 and os.environ.get("PTB_E2E", "scatter") == "scatter":
         try:
@@ -265,21 +381,8 @@ def run_ours(args, rank, world, local_rank):
     host_bufs = [torch.empty((H if rank == 0 else 1, W, 3 if world == 1 else 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     side = torch.cuda.Stream(device=dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
-    snap = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1) else None
+    snap = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1 and shared is None) else None
     state = {"i": 0}
-
-    def step_device(n=1):
-        if tiled is None:
-            pt.Render(n)
-        elif n > 1 and fused:
-            tiled.step_batch(n)    # one trace launch for n frames; every frame still reaches rank 0 through its own slot
-        else:
-            for _ in range(n):
-                tiled.step()       # render f; finish gather f-1 (it overlapped this render); start gather f
-
-    def finish_device():
-        if tiled is not None:
-            tiled.flush()
 
     def step_e2e():
         # what the C# host does every frame: camera UBO writes (host memory -> the library), Render(), and here the
@@ -294,30 +397,29 @@ def run_ours(args, rank, world, local_rank):
         elif shared is not None:
             tiled.step()           # the device-side exchange keeps running exactly as in the device-timed loop
             pt.ReadResultScatterAsync(shared.ptr(i), ptb200.FORMAT_RGB32F)
-        else:
-            if fused:
-                # rank 0 owns the slot between acquire and release: snapshot it (HBM->HBM) there, copy to the host on a side stream
-                k = i & 1
+        elif fused:
+            # rank 0 owns the slot between acquire and release: snapshot it (HBM->HBM) there, copy to the host on a side stream
+            k = i & 1
 
-                def consume(full, k=k):
-                    cur = torch.cuda.current_stream(dev)
-                    cur.wait_event(copy_done[k])             # the D2H that last read snap[k] is done
-                    snap[k].copy_(full, non_blocking=True)
-                    side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        host_bufs[k].copy_(snap[k], non_blocking=True)
-                        copy_done[k].record(side)
-                tiled.step_fused(consumer=consume if rank == 0 else None)
-            else:
-                full = tiled.step()
-                if rank == 0 and full is not None:
-                    k = i & 1
-                    cur = torch.cuda.current_stream(dev)
-                    side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        host_bufs[k].copy_(full, non_blocking=True)
-                        copy_done[k].record(side)
-                    cur.wait_event(copy_done[k])      # (cheap) keeps `full[k]` from being rewritten before its copy was issued
+            def consume(full, k=k):
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(copy_done[k])             # the D2H that last read snap[k] is done
+                snap[k].copy_(full, non_blocking=True)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    host_bufs[k].copy_(snap[k], non_blocking=True)
+                    copy_done[k].record(side)
+            tiled.step_fused(consumer=consume if rank == 0 else None)
+        else:
+            full = tiled.step()
+            if rank == 0 and full is not None:
+                k = i & 1
+                cur = torch.cuda.current_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    host_bufs[k].copy_(full, non_blocking=True)
+                    copy_done[k].record(side)
+                cur.wait_event(copy_done[k])      # (cheap) keeps `full[k]` from being rewritten before its copy was issued
 
     def finish_e2e():
         if tiled is None:
@@ -332,62 +434,6 @@ def run_ours(args, rank, world, local_rank):
             side.synchronize()
             torch.cuda.current_stream(dev).synchronize()
 
-    def samples_per_step_():
-        return W * H * SPP
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    flush_stream = torch.cuda.Stream(device=dev)
-
-    def timed(fn, steps, flush_l2, finisher=None):
-        """K steps enqueued back to back on the launching stream (the library pipelines consecutive frames), one CUDA-event
-        bracket around the whole region.  L2 flush: a 160 MiB memset (> the 126 MB L2) per step on a concurrent stream, INSIDE the timed region
-        (a serialised flush would have to drain the frame pipeline and time something the library never does)."""
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        wall0 = time.perf_counter()
-        ev0.record()
-        chunk = batch if (batch > 1 and fn is step_device) else 1
-        for k in range(0, steps, chunk):
-            m = min(chunk, steps - k)
-            if flush_l2:
-                with torch.cuda.stream(flush_stream):
-                    for _ in range(m):
-                        flush.zero_()
-            if chunk > 1:
-                fn(m)
-            else:
-                fn()
-        if finisher is not None:
-            finisher()             # drain the pipeline inside the timed region
-        ev1.record()
-        barrier()
-        wall = time.perf_counter() - wall0
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, wall
-
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step_device()
-    finish_device()
-    launches0 = pt.KernelLaunches
-    with ClockSampler(physical_gpu_index(local_rank)) as clocks:
-        ms_total, _ = timed(step_device, args.steps, True, finish_device)
-    launches = pt.KernelLaunches - launches0
-    if args.profile:
-        if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "note": "not a bench value"}), flush=True)
-        pt.Dispose()
-        return
-    # back-to-back (image stays L2-resident between frames, as in the interactive app) and the end-to-end path
-    ms_b2b, _ = timed(step_device, args.steps, False, finish_device)
     for _ in range(3):
         step_e2e()
     finish_e2e()
@@ -438,57 +484,85 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(n_alt):
                 step_alt()
             pt.Synchronize()
-            e2e_formats[name] = {"value": samples_per_step_() * n_alt / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s",
+            e2e_formats[name] = {"value": samples_per_step * n_alt / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s",
                                  "d2h_bytes_per_step": W * H * (16 if fmt == ptb200.FORMAT_RGBA32F else 4)}
 
-    # kernel-only duration for the roofline (device time of the megakernel launches alone, max over ranks)
-    pt.SetOverlap(1)                 # isolate the megakernel: one stream, no blend kernel, launches back to back
-    pt.Render(3); pt.Synchronize()
-    pt.Render(20)
-    kern_ms = pt.LastRenderMs() / 20
-    pt.SetOverlap(frames_in_flight)
-    if world > 1:
-        t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kern_ms = float(t.item())
+    # ------------------------------------------------------------------ N > 1: the exchanged frame against ONE GPU rendering alone
+    exchange_check = None
+    if tiled is not None:
+        n_chk = 8
+        pt.Synchronize()
+        pt.ResetRenderer()
+        barrier()
+        keep = {}
 
-    samples_per_step = W * H * SPP
+        def grab(full):
+            keep["img"] = full            # the slot stays valid: nothing is rendered after these frames
+        if fused:
+            tiled.step_batch(n_chk, consumer=grab if rank == 0 else None)
+        else:
+            for _ in range(n_chk):
+                tiled.step()
+            keep["img"] = tiled.flush()
+        barrier()
+        if rank == 0:
+            solo = ptb200.PathTracer(None, W, H, RAY_DEPTH, SPP, FOCAL, APERTURE, max_spheres=scene.max_spheres, max_cuboids=scene.max_cuboids, device=local_rank)
+            solo.SetPrecision(headline)
+            solo.GenerateAtmosphere(256, 50, 15, 0.5, 15.0); solo.LoadScene(scene); solo.SetCamera(cam)
+            solo.Render(n_chk); solo.Synchronize()
+            ptr, _ = solo.ResultDevicePtr()
+            want = torch.as_tensor(D._DeviceBuffer(ptr, (H, W, 4)), device=dev)
+            got = keep["img"]
+            same = bool((got.view(torch.int32) == want.view(torch.int32)).all().item())
+            exchange_check = {"exchange_equals_single_gpu": same, "frames": n_chk,
+                              "max_abs_diff": float((got - want).abs().max().item()),
+                              "note": f"{n_chk} frames from a reset through the {world}-GPU exchange vs the same frames rendered by rank 0's GPU alone (untiled), compared on the device"}
+            del want
+            solo.Dispose()
+        barrier()
+
     value = samples_per_step * args.steps / (ms_total * 1e-3) / 1e6
     peak, peak_src = measured_peaks()
-    algo_bytes = rows_local * W * 32            # 16 B load of the previous mean + 16 B store per pixel per dispatch
-    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-    ncu = ncu_summary()
+    algo_bytes = rows_local * W * 32 * frames_per_launch   # per pixel and frame: 16 B load of the previous mean + 16 B store
+    achieved = algo_bytes / (kern_launch_ms * 1e-3) / 1e9
+    ncu = ncu_summary() if (world == 1 and args.config == "c2") else {}
+    prec_name = "fast" if headline == ptb200.PRECISION_FAST else "exact"
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "flushed every step by a 160 MiB memset (> 126 MB L2) on a concurrent stream, inside the timed region",
-                   "partition": f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + ("exchange fused into the blend kernel: peer stores into rank 0's image over NVLink (CUDA IPC), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render") if world > 1 else "single GPU, no collective",
-                   "kernel": f"persistent megakernel (ptb::megakernel) + blend kernel per frame, {frames_in_flight} frames in flight (ptb_set_overlap)"
-                             + (f", {batch} frames per trace launch (PTB_BATCH)" if batch > 1 else "") + (f", grid / {grid_div} (PTB_GRID_DIV)" if grid_div > 1 else "")},
+        "config": {"workload": cfg["workload"], "name": args.config,
+                   "precision": (f"{prec_name}: " + ("MUFU rcp/rsq/sin/cos/ex2 + FMA contraction (ptb_set_precision), within the north star's per-channel MSE < 1e-6 of the exact build on this workload (see precision_gate)"
+                                                     if prec_name == "fast" else "the evaluation model of DESIGN.md §2, bit-identical to the CPU oracle and the compiled reference shaders")),
+                   "l2": f"no flush kernel in the timed region: the frame estimates rotate through 2 x {BATCH} scratch images per rank ({2 * BATCH * rows_local * W * 16 / 1e6:.0f} MB on this rank, L2 is 126 MB); inputs larger than L2",
+                   "partition": (f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + (f"exchange fused into the batch blend kernel: peer stores into rank 0's per-frame slots over NVLink (CUDA IPC, {EXCHANGE_SLOTS} slots), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render")) if world > 1 else "single GPU, no collective",
+                   "kernel": f"persistent megakernel, {BATCH} consecutive frames per launch (ptb_set_batch) + one blend kernel per batch, {frames_in_flight} batches in flight; ray-classification table for scenes of <= 64 primitives, shared-memory BVH above 96"},
+        "precision_gate": gate,
+        "exact": exact,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "ptb::megakernel<false>",
-                     "kernel_ms": kern_ms, "kernel_timing": "megakernel alone, in-place mode (ptb_set_overlap(1)), 20 launches back to back, CUDA events", "algorithmic_bytes_per_launch": algo_bytes,
-                     "note": "the pass is FP32-issue-bound, not HBM-bound: ~3.4k lane-instructions per 32 B of image traffic (DESIGN.md); see issue_*",
-                     "issue_active_pct": ncu.get("smsp_issue_active_pct"), "inst_executed_per_launch": ncu.get("inst_executed_per_launch"),
-                     "issue": issue_roofline(ncu, kern_ms, world)},
+                     "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": f"ptb{'_fast' if prec_name == 'fast' else ''}::megakernel",
+                     "kernel_ms": kern_ms, "kernel_ms_per_launch": kern_launch_ms, "frames_per_launch": frames_per_launch,
+                     "kernel_timing": "CUDA-event pair around every megakernel launch on its own stream, in the same batched / pipelined / tiled mode as `value` (ptb_set_kernel_timing), max over ranks; kernel_ms is per frame",
+                     "algorithmic_bytes_per_launch": algo_bytes,
+                     "note": "the pass is FP32-issue-bound, not HBM-bound: thousands of lane-instructions per 32 B of image traffic (DESIGN.md); `traffic` and ncu_capture come from the committed single-GPU c2 capture named in profiles/ncu_summary.json and are attached to that configuration only",
+                     "ncu_capture": ({k: ncu.get(k) for k in ("source", "kernel", "smsp_issue_active_pct", "inst_executed_per_launch", "thread_inst_per_sample", "frames_per_launch")} if ncu else None)},
         "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": (80 + 144) * world,
                 "d2h_bytes_per_step": W * H * (12 if rgb_e2e else 16), "steps": e2e_steps, "format": "RGB32F" if rgb_e2e else "RGBA32F",
                 "last_frame_on_host_equals_device_image": e2e_verified,
-                "note": ("per step: InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), the frame read back to pinned host memory as RGB32F "
+                "note": ("one Render() per step (no batching: every frame is read back): InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), the frame read back to pinned host memory as RGB32F "
                          "(colour floats bit for bit; the constant alpha 1.0 of compute.glsl:129 is not shipped) through the pipelined read-back (snapshot/pack kernel on the render stream + copy stream, "
-                         "overlapping the next Render()); one sync after the last step, inside the timed region. "
+                         "overlapping the next Render()); one sync after the last step, inside the timed region; PCIe-bound. "
                          + ("" if world == 1 else ("N > 1: ptb_read_result_scatter_async — every rank writes its stripes into their rows of one full-frame image in pinned host memory shared by all ranks, each over its own PCIe link; the device-side exchange runs as in the device-timed loop"
                                                    if shared is not None else "N > 1 fallback: rank 0 copies the assembled RGBA32F image")))},
         "e2e_other_formats": e2e_formats,
-        "back_to_back": {"value": samples_per_step * args.steps / (ms_b2b * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_b2b / args.steps,
-                         "note": "same steps without the concurrent L2 flush"},
+        "exchange_check": exchange_check,
         "gpu_launches": launches,
-        "clocks": clocks.summary(),
+        "clocks": clocks,
     }
     if rank == 0 and world == 1:
-        line["cpu_baseline"] = cpu_baseline(pt)
-        line["gl_proxy"] = gl_proxy()
+        line["cpu_baseline"] = cpu_baseline(pt, cfg, scene)
+        if args.config == "c2":
+            line["gl_proxy"] = gl_proxy()
     if tiled is not None and fused:
         tiled.exchange_ok()
     if shared is not None:
@@ -499,27 +573,30 @@ def run_ours(args, rank, world, local_rank):
     pt.Dispose()
 
 
-def cpu_baseline(pt):
+def cpu_baseline(pt, cfg, scene):
     """The compiled reference shader (else the oracle port) on this box's host cores, a bounded sample of the same
     workload (rank 0, N = 1 only)."""
     import ptb200
-    from oracle import oracle as O_
-    O, kind, _ = cpu_reference()
+    O, kind, _ = cpu_reference(scene.max_spheres)
     sc = ptb200.scene
+    W, H = cfg["W"], cfg["H"]
     env = pt.ReadEnvironment()
-    scene, cam = sc.load_default_scene(), sc.default_camera()
+    cam = sc.default_camera()
     basic, ubo = sc.basic_data_bytes(cam, W, H), scene.ubo_bytes()
     img = np.zeros((H, W, 4), np.float32)
     threads = host_threads()
-    kw = dict(spp=SPP, ray_depth=RAY_DEPTH, focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=48, n_cuboids=7, n_threads=threads)
-    O.render(img, basic, ubo, env, frame=0, **kw)                 # warm-up / thread pool start
+    kw = dict(spp=SPP, ray_depth=cfg["ray_depth"], focal_length=FOCAL, aperture_diameter=APERTURE, n_spheres=len(scene.spheres),
+              n_cuboids=len(scene.cuboids), max_spheres=scene.max_spheres, n_threads=threads)
+    y_step = 1 if cfg["scene"] == "default" and W <= 1920 else 8      # the large configs take a bounded sample: every 8th row
+    O.render(img, basic, ubo, env, frame=0, y_step=max(y_step, 4), **kw)                 # warm-up / thread pool start
     frames, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < 10.0 and frames < 64:
         frames += 1
-        O.render(img, basic, ubo, env, frame=frames, **kw)
+        O.render(img, basic, ubo, env, frame=frames, y_step=y_step, **kw)
     dt = time.perf_counter() - t0
-    return {"value": W * H * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
-            "sample": f"{frames} full 1920x1080 frames at SPP 1 ({dt:.1f} s), OpenMP over rows"}
+    rows = len(range(0, H, y_step))
+    return {"value": W * rows * SPP * frames / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+            "sample": f"{frames} passes over " + ("the full frame" if y_step == 1 else f"every {y_step}-th row of the frame") + f" ({W}x{rows} pixels each) at SPP 1 ({dt:.1f} s), OpenMP over rows"}
 
 
 def gl_proxy():
@@ -544,9 +621,11 @@ def gl_proxy():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=320)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="auto", choices=["auto", "fast", "exact"])
     ap.add_argument("--profile", action="store_true", help="profiling aid: only warm-up + timed steps (for runs under ncu); prints no bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

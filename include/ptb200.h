@@ -157,12 +157,14 @@ int ptb_set_overlap(ptb_ctx* ctx, int n);
  * than one CTA per SM), so that with n >= d frames in flight d frames are co-resident and one frame's drain runs beside
  * another's bulk instead of beside an empty machine.  Results do not depend on it. */
 int ptb_set_grid_divisor(ptb_ctx* ctx, int d);
-/* Frame batching (default 1 = off).  With frames >= 2, ptb_render_frames(n) traces up to `frames` consecutive frames per
+/* Frame batching (default 16; 1 = off).  ptb_render_frames(n) with n >= 2 traces up to `frames` consecutive frames per
  * megakernel launch: the work counter runs over all their pixels, frame-major, each frame's estimate goes to its own scratch
- * image and the per-frame blends follow in frame order — the same arithmetic in the same order as n single-frame calls, so
- * the image is bit-identical — but lanes move from the last pixels of one frame straight into the next and only the last
- * frame of a batch pays the drain of the longest paths.  Applies to the megakernel with overlap >= 2, width <= 4096, statistics off;
- * with the fused exchange a batch is capped at the number of exchange slots. */
+ * image, and ONE blend kernel folds the batch into the accumulation image frame by frame in registers — the same arithmetic
+ * in the same order as n single-frame calls, so the image is bit-identical — but lanes move from the last pixels of one
+ * frame straight into the next and only the last frame of a batch pays the drain of the longest paths (an 8-GPU share of a
+ * 1080p frame: 67 -> 47 us/frame).  A plain ptb_render() is never batched.  Applies to the megakernel with overlap >= 2,
+ * width <= 4096, statistics off; with the fused exchange every frame of a batch still lands in its own slot on rank 0, so a
+ * batch is capped at the number of exchange slots.  Scratch memory: 2 x frames x image size, allocated at the first batch. */
 int ptb_set_batch(ptb_ctx* ctx, int frames);
 /* Arithmetic of the megakernel (protocols P1 / P2).
  *   PTB_PRECISION_EXACT (default): the evaluation model of DESIGN.md §2 — IEEE fp32, no contraction, correctly rounded 1/x and
@@ -185,6 +187,11 @@ int ptb_set_ray_classification(ptb_ctx* ctx, int mode, int cells, int buckets);
 /* Scenes with at least this many primitives are traced through the shared-memory BVH, smaller ones by the brute-force fold
  * (default 96).  Results do not depend on it (the hierarchy only removes primitives that fail the exact test). */
 int ptb_set_bvh_threshold(ptb_ctx* ctx, int primitives);
+/* Device time of the megakernel launches themselves, in whatever mode is running (pipelined, batched, tiled): with timing
+ * enabled every megakernel launch is bracketed by a CUDA-event pair on the stream it runs on; ptb_kernel_time() waits for the
+ * outstanding pairs, returns the summed duration, the frames and the launches they covered, and restarts the count. */
+int ptb_set_kernel_timing(ptb_ctx* ctx, int enabled);
+int ptb_kernel_time(ptb_ctx* ctx, double* ms_total, long long* frames, long long* launches);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */
 /* Introspection of the packed scene / launch shape (syncs the scene first): what the last LoadScene turned into. */
 #define PTB_INFO_BVH_NODES 0      /* nodes of the shared-memory BVH (0: brute-force fold) */

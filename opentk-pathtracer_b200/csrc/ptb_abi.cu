@@ -125,7 +125,7 @@ struct ptb_ctx {
     // frame batching (ptb_set_batch): up to `batch` consecutive frames of one ptb_render_frames call are traced by ONE
     // megakernel launch into a set of per-frame scratch images; two sets alternate so that the blends of batch k run beside
     // the trace of batch k+1
-    int batch = 1;
+    int batch = 16;
     float4* d_batch_scratch[2] = {nullptr, nullptr};
     size_t batch_scratch_frames = 0, batch_scratch_stride = 0;     // frames per set / float4 elements per frame
     unsigned int* d_batch_counters[2] = {nullptr, nullptr};
@@ -134,6 +134,14 @@ struct ptb_ctx {
     unsigned long long batch_seq = 0;
     bool mega_ring = true;
     int mega_fold_set = -1;
+    // ptb_set_kernel_timing: an event pair around every megakernel launch, on the stream it runs on
+    bool kt_on = false;
+    cudaEvent_t kt_a[8] = {}, kt_b[8] = {};
+    int kt_frames[8] = {};
+    bool kt_used[8] = {};
+    unsigned kt_next = 0;
+    double kt_ms = 0.0;
+    long long kt_frames_total = 0, kt_launches = 0;
     int precision = PTB_PRECISION_EXACT, mega_precision_set = -1;   // ptb_set_precision: which translation unit's megakernel runs
 };
 
@@ -476,8 +484,8 @@ void layout_block(ptb_ctx* c)
     const int nS = c->n_spheres, nC = c->n_cuboids;
     c->off_aux = (nS + 3) & ~3;                 // the sphere array is padded to a multiple of four (never-hit dummies)
     c->off_cmin = c->off_aux + (nS + 3) / 4;
-    c->off_cmax = c->off_cmin + nC;
-    c->off_nodes = c->off_cmax + nC;
+    c->off_cmax = c->off_cmin + 1;                // slab bounds interleaved: lo0, hi0, lo1, hi1, ...
+    c->off_nodes = c->off_cmin + 2 * nC;
     c->off_pidx = c->off_nodes + 2 * c->n_nodes;
     c->off_mat = c->off_pidx + ((int)c->bvh_pidx.size() + 3) / 4;
     c->block_bytes = (c->off_mat + (nS + nC) * 4) * 16;
@@ -555,6 +563,8 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     for (int k = 0; k < 3; ++k) { P.rct_lo[k] = c->rct_lo[k]; P.rct_inv[k] = c->rct_inv[k]; P.rct_n[k] = c->rct_n[k]; }
     P.rct_G = c->rct_G; P.rct_halfG = 0.5f * (float)c->rct_G;
     P.rct_sm0 = c->rct_sm0; P.rct_sm1 = c->rct_sm1;
+    for (int k = 0; k < 3; ++k) P.rct_nf[k] = (float)c->rct_n[k];
+    { const int n = c->n_spheres + c->n_cuboids; P.rct_valid = n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
 }
 
 int fold_of(const ptb_ctx* c) { return (c->n_nodes > 0 || c->n_unbounded > 0) ? 1 : (c->rct_on ? 2 : 0); }
@@ -691,16 +701,38 @@ int with_mega_batch(ptb_ctx* c, F&& launch)
     }
 }
 
+int kt_collect(ptb_ctx* c, int slot)
+{
+    if (!c->kt_used[slot]) return PTB_OK;
+    CU(cudaEventSynchronize(c->kt_b[slot]));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, c->kt_a[slot], c->kt_b[slot]));
+    c->kt_ms += ms; c->kt_frames_total += c->kt_frames[slot]; c->kt_launches++;
+    c->kt_used[slot] = false;
+    return PTB_OK;
+}
+
 int launch_mega(ptb_ctx* c, const RenderParams& P, bool batch, int smem, cudaStream_t stream)
 {
+    int slot = -1;
+    if (c->kt_on) {
+        slot = (int)(c->kt_next++ % 8u);
+        { const int rc = kt_collect(c, slot); if (rc != PTB_OK) return rc; }
+        CU(cudaEventRecord(c->kt_a[slot], stream));
+    }
     if (c->precision == PTB_PRECISION_FAST) {
         CU(ptb_fast_api::launch(&P, fold_of(c), c->mega_ring, batch, c->mega_grid, smem, stream));
-        return PTB_OK;
+    } else {
+        const int rc = batch ? with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; })
+                             : with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; });
+        if (rc != PTB_OK) return rc;
+        CU(cudaGetLastError());
     }
-    const int rc = batch ? with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; })
-                         : with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; });
-    if (rc != PTB_OK) return rc;
-    CU(cudaGetLastError());
+    if (slot >= 0) {
+        CU(cudaEventRecord(c->kt_b[slot], stream));
+        c->kt_frames[slot] = batch ? P.batch : 1;
+        c->kt_used[slot] = true;
+    }
     return PTB_OK;
 }
 
@@ -765,25 +797,29 @@ int launch_batch(ptb_ctx* c, int frames)
     CU(cudaStreamWaitEvent(bs, c->ev_batch_trace[s], 0));
     const size_t n = (size_t)c->local_rows * c->width;
     c->launches++;
-    for (int j = 0; j < frames; ++j) {
-        const int frame = c->frame + j;
-        const float blend = 1.0f * (1.0f / (float)(frame + 1));          // as fill_params: 1.0 / (thisRendererFrame + 1)
-        const float4* estimate = c->d_batch_scratch[s] + (size_t)j * c->batch_scratch_stride;
-        if (c->xch_on) {
-            const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
-            const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
-            if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
-            blend_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(
-                c->d_image, estimate, c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, frame, blend,
-                reinterpret_cast<float4*>(c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes), reinterpret_cast<ExchangeFlags*>(c->xch_block),
-                slot, c->d_xch_blocks);
-            c->xch_seq++;
-        } else {
-            blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, estimate, n, frame, blend);
+    // one blend kernel for the whole batch: the running mean is folded frame by frame in registers (same operations, same order)
+    BatchBlend B = {};
+    B.frame0 = c->frame; B.frames = frames; B.stride = (unsigned long long)c->batch_scratch_stride;
+    for (int j = 0; j < frames; ++j) B.blend[j] = 1.0f * (1.0f / (float)(c->frame + j + 1));     // as fill_params: 1.0 / (thisRendererFrame + 1)
+    if (c->xch_on) {
+        BatchScatter X = {};
+        for (int j = 0; j < frames; ++j) {
+            X.slot[j] = (int)((c->xch_seq + j) % (unsigned long long)c->xch_slots);
+            X.full[j] = reinterpret_cast<float4*>(c->xch_block + 4096 + (size_t)X.slot[j] * c->xch_image_bytes);
         }
-        CU(cudaGetLastError());
-        c->launches++;
+        // the batch's last frame needs the release of frame (seq_last - slots); `consumed` is monotonic, so that covers the others
+        const unsigned long long last = c->xch_seq + frames - 1;
+        const unsigned need = last >= (unsigned long long)c->xch_slots ? (unsigned)(last - c->xch_slots + 1) : 0u;
+        if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
+        blend_scatter_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_batch_scratch[s], c->width, c->local_rows, c->height, c->rank,
+                                                                                c->world, c->stripe_rows, B, X, reinterpret_cast<ExchangeFlags*>(c->xch_block),
+                                                                                c->d_xch_blocks);
+        c->xch_seq += frames;
+    } else {
+        blend_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_batch_scratch[s], n, B);
     }
+    CU(cudaGetLastError());
+    c->launches++;
     CU(cudaEventRecord(c->ev_batch_blend[s], bs));
     c->batch_blend_recorded[s] = true;
     CU(cudaStreamWaitEvent(c->stream, c->ev_batch_blend[s], 0));       // whatever the host enqueues next sees these frames
@@ -863,6 +899,7 @@ void ptb_destroy(ptb_ctx* c)
     cudaFree(c->d_image); cudaFree(c->d_counters); cudaFree(c->d_stats);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_stage[i]); if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    for (int i = 0; i < 8; ++i) { if (c->kt_a[i]) cudaEventDestroy(c->kt_a[i]); if (c->kt_b[i]) cudaEventDestroy(c->kt_b[i]); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1225,7 +1262,7 @@ static int exchange_close(ptb_ctx* c)
 int ptb_exchange_init(ptb_ctx* c, int slots)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
-    if (slots < 1 || slots > 8) return fail(PTB_E_INVALID, "slots %d outside [1,8]", slots);
+    if (slots < 1 || slots > 16) return fail(PTB_E_INVALID, "slots %d outside [1,16]", slots);
     if (c->overlap < 2) return fail(PTB_E_STATE, "the fused exchange needs the pipelined mode (ptb_set_overlap >= 2)");
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     exchange_close(c);
@@ -1322,7 +1359,7 @@ int ptb_set_overlap(ptb_ctx* c, int n)
 int ptb_set_batch(ptb_ctx* c, int frames)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
-    if (frames < 1 || frames > 16) return fail(PTB_E_INVALID, "batch %d outside [1,16]", frames);
+    if (frames < 1 || frames > kMaxBatch) return fail(PTB_E_INVALID, "batch %d outside [1,%d]", frames, kMaxBatch);
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     c->batch = frames;
     return PTB_OK;
@@ -1334,6 +1371,26 @@ int ptb_set_grid_divisor(ptb_ctx* c, int d)
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     c->grid_divisor = d;
     c->mega_smem_set = -1;           // recompute the grid at the next launch
+    return PTB_OK;
+}
+int ptb_set_kernel_timing(ptb_ctx* c, int enabled)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
+    for (int i = 0; i < 8; ++i) {
+        if (enabled && !c->kt_a[i]) { CU(cudaEventCreate(&c->kt_a[i])); CU(cudaEventCreate(&c->kt_b[i])); }
+        c->kt_used[i] = false;
+    }
+    c->kt_on = enabled != 0;
+    c->kt_ms = 0.0; c->kt_frames_total = 0; c->kt_launches = 0; c->kt_next = 0;
+    return PTB_OK;
+}
+int ptb_kernel_time(ptb_ctx* c, double* ms_total, long long* frames, long long* launches)
+{
+    if (!c || !ms_total || !frames || !launches) return fail(PTB_E_INVALID, "null argument");
+    for (int i = 0; i < 8; ++i) { const int rc = kt_collect(c, i); if (rc != PTB_OK) return rc; }
+    *ms_total = c->kt_ms; *frames = c->kt_frames_total; *launches = c->kt_launches;
+    c->kt_ms = 0.0; c->kt_frames_total = 0; c->kt_launches = 0;
     return PTB_OK;
 }
 int ptb_set_precision(ptb_ctx* c, int precision)

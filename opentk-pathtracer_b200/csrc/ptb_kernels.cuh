@@ -82,6 +82,8 @@ struct RenderParams {
     int rct_n[3], rct_G;                            // cells per axis, direction buckets per cube-face axis
     float rct_halfG;
     unsigned rct_sm0, rct_sm1;                      // which bits of the mask's low / high word are spheres
+    float rct_nf[3];                                // cells per axis as floats (range test of the cell coordinates)
+    unsigned long long rct_valid;                   // the mask of every existing primitive: what an unclassifiable ray tests
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -96,8 +98,9 @@ struct PackedScene {           // SoA block in shared memory
     int nS, nC, off_aux, off_cmin, off_cmax, off_mat;
     __device__ __forceinline__ float4 sphere(int i) const { return base[i]; }                 // (c, r*r)
     __device__ __forceinline__ float sphere_rcp_r(int i) const { return reinterpret_cast<const float*>(base + off_aux)[i]; }
-    __device__ __forceinline__ float4 cmin(int i) const { return base[off_cmin + i]; }
-    __device__ __forceinline__ float4 cmax(int i) const { return base[off_cmax + i]; }
+    // slab bounds are interleaved (lo0, hi0, lo1, hi1, ...; off_cmax == off_cmin + 1): one address computation per cuboid
+    __device__ __forceinline__ float4 cmin(int i) const { return base[off_cmin + 2 * i]; }
+    __device__ __forceinline__ float4 cmax(int i) const { return base[off_cmax + 2 * i]; }
     __device__ __forceinline__ float4 mat(int prim, int k) const { return mats[off_mat + prim * 4 + k]; }
 };
 struct RawScene {              // the std140 bytes exactly as the host uploaded them (naive proxy)
@@ -181,34 +184,73 @@ __device__ __forceinline__ void trace(const Scene& sc, V3 o, V3 d, float& T, int
     }
 }
 
-// The fold over the shared-memory block: spheres four at a time (the array is padded to a multiple of four with spheres of
-// r^2 = -inf that nothing can hit), one max + branch for the four discriminants — a NaN or negative discriminant never hits,
-// so dropping those through the NaN-ignoring max is exact — then the cuboids as in trace().
-__device__ __forceinline__ void accept_sphere(float b, float disc, int i, float& T, int& prim, bool& inside)
+// ---- the fold's arithmetic, written once for every variant of the fold (plain, table, cooperative, BVH) -----------------
+// State of the fold: (T, prim, t2w) with t2w = the winner's exit distance; HitInfo.FromInside (pt:237,250) is T == t2w.
+// In the fast build the multiply-adds are contracted by hand, identically everywhere, so that a ray gets the same distances
+// whichever variant of the fold happens to trace it (the frame's tail switches to the cooperative fold).
+struct RayInv { V3 inv, noi; };       // 1 / d and (fast build) -o / d
+__device__ __forceinline__ RayInv ray_inverse(V3 o, V3 d)
 {
-    if (!(disc < 0.0f)) {
-        const float sq = fsqrt(disc);
-        const float t1 = -b - sq;
-        const float t2 = -b + sq;
-        if (t1 <= t2 && t2 > 0.0f && t1 < T) {
-            T = t1 < 0.0f ? t2 : t1;
-            inside = (T == t2);
-            prim = i;
-        }
-    }
+    RayInv r;
+#ifdef PTB_FAST
+    // a zero component would give inf * 0 = NaN in lo * inv - o * inv: 1e-18 keeps it a huge finite slope (and changes nothing
+    // for |d| >= 1e-10, where it is below half an ulp)
+    r.inv = mk(rcp(d.x + copysignf(1e-18f, d.x)), rcp(d.y + copysignf(1e-18f, d.y)), rcp(d.z + copysignf(1e-18f, d.z)));
+    r.noi = mk(-o.x * r.inv.x, -o.y * r.inv.y, -o.z * r.inv.z);
+#else
+    r.inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
+    r.noi = mk(0.0f, 0.0f, 0.0f);
+#endif
+    return r;
 }
-__device__ __forceinline__ void sphere_terms(const float4 s, V3 o, V3 d, float& b, float& disc)
+__device__ __forceinline__ void sphere_terms(const float4 s, V3 o, V3 d, float& b, float& disc)       // pt:263-266
 {
     const V3 v = mk(o.x - s.x, o.y - s.y, o.z - s.z);
+#ifdef PTB_FAST
+    b = __fmaf_rn(d.z, v.z, __fmaf_rn(d.y, v.y, d.x * v.x));
+    const float c = __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmaf_rn(v.x, v.x, -s.w)));
+    disc = __fmaf_rn(b, b, -c);
+#else
     b = dot(d, v);
     const float c = dot(v, v) - s.w;
     disc = b * b - c;
+#endif
 }
+__device__ __forceinline__ void slab_terms(const float4 lo, const float4 hi, V3 o, const RayInv& ri, float& t1, float& t2)   // pt:282-291
+{
+#ifdef PTB_FAST
+    const float ax = __fmaf_rn(lo.x, ri.inv.x, ri.noi.x), ay = __fmaf_rn(lo.y, ri.inv.y, ri.noi.y), az = __fmaf_rn(lo.z, ri.inv.z, ri.noi.z);
+    const float bx = __fmaf_rn(hi.x, ri.inv.x, ri.noi.x), by = __fmaf_rn(hi.y, ri.inv.y, ri.noi.y), bz = __fmaf_rn(hi.z, ri.inv.z, ri.noi.z);
+#else
+    const float ax = (lo.x - o.x) * ri.inv.x, ay = (lo.y - o.y) * ri.inv.y, az = (lo.z - o.z) * ri.inv.z;
+    const float bx = (hi.x - o.x) * ri.inv.x, by = (hi.y - o.y) * ri.inv.y, bz = (hi.z - o.z) * ri.inv.z;
+#endif
+    t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
+    t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
+}
+__device__ __forceinline__ void accept(float t1, float t2, int i, float& T, int& prim, float& t2w)      // pt:234-240, 247-253
+{
+    if (t1 <= t2 && t2 > 0.0f && t1 < T) {
+        T = t1 < 0.0f ? t2 : t1;
+        t2w = t2;
+        prim = i;
+    }
+}
+__device__ __forceinline__ void accept_sphere(float b, float disc, int i, float& T, int& prim, float& t2w)
+{
+    if (!(disc < 0.0f)) {
+        const float sq = fsqrt(disc);
+        accept(-b - sq, -b + sq, i, T, prim, t2w);
+    }
+}
+// The fold over the shared-memory block: spheres four at a time (the array is padded to a multiple of four with spheres of
+// r^2 = -inf that nothing can hit), one max + branch for the four discriminants — a NaN or negative discriminant never hits,
+// so dropping those through the NaN-ignoring max is exact — then the cuboids.
 __device__ __forceinline__ void trace_any(const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
 {
     T = kFloatMax;
     prim = -1;
-    inside = false;
+    float t2w = 0.0f;
     const int n4 = (sc.nS + 3) & ~3;
     for (int i = 0; i < n4; i += 4) {
         float b0, b1, b2, b3, d0, d1, d2, d3;
@@ -217,26 +259,21 @@ __device__ __forceinline__ void trace_any(const PackedScene& sc, V3 o, V3 d, flo
         sphere_terms(sc.base[i + 2], o, d, b2, d2);
         sphere_terms(sc.base[i + 3], o, d, b3, d3);
         if (fmax_(fmax_(d0, d1), fmax_(d2, d3)) >= 0.0f) {
-            accept_sphere(b0, d0, i, T, prim, inside);
-            accept_sphere(b1, d1, i + 1, T, prim, inside);
-            accept_sphere(b2, d2, i + 2, T, prim, inside);
-            accept_sphere(b3, d3, i + 3, T, prim, inside);
+            accept_sphere(b0, d0, i, T, prim, t2w);
+            accept_sphere(b1, d1, i + 1, T, prim, t2w);
+            accept_sphere(b2, d2, i + 2, T, prim, t2w);
+            accept_sphere(b3, d3, i + 3, T, prim, t2w);
         }
     }
-    const float ix = rcp(d.x), iy = rcp(d.y), iz = rcp(d.z);
+    const RayInv ri = ray_inverse(o, d);
+    const float4* cub = sc.base + sc.off_cmin;
 #pragma unroll 2
     for (int i = 0; i < sc.nC; ++i) {
-        const float4 lo = sc.cmin(i), hi = sc.cmax(i);
-        const float ax = (lo.x - o.x) * ix, ay = (lo.y - o.y) * iy, az = (lo.z - o.z) * iz;
-        const float bx = (hi.x - o.x) * ix, by = (hi.y - o.y) * iy, bz = (hi.z - o.z) * iz;
-        const float t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
-        const float t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
-        if (t1 <= t2 && t2 > 0.0f && t1 < T) {
-            T = t1 < 0.0f ? t2 : t1;
-            inside = (T == t2);
-            prim = sc.nS + i;
-        }
+        float t1, t2;
+        slab_terms(cub[2 * i], cub[2 * i + 1], o, ri, t1, t2);
+        accept(t1, t2, sc.nS + i, T, prim, t2w);
     }
+    inside = (T == t2w);
 }
 __device__ __forceinline__ void trace_any(const RawScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside) { trace(sc, o, d, T, prim, inside); }
 
@@ -435,25 +472,18 @@ __device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, P
 //   K  = the largest index whose primitive contains the origin (t1 < 0 < t2): it always overwrites what came before;
 //   the winner is the smallest entry distance t1 among later, non-containing hits if that beats t2_K (strictly),
 //   else K; ties go to the lower index; with no K it is the plain first-wins argmin of t1 (t1 < FLOAT_MAX).
-__device__ __forceinline__ bool coop_test(const PackedScene& sc, int i, V3 o, V3 d, V3 inv, float& t1, float& t2)
+__device__ __forceinline__ bool coop_test(const PackedScene& sc, int i, V3 o, V3 d, const RayInv& ri, float& t1, float& t2)
 {
     if (i < sc.nS) {
-        const float4 s = sc.sphere(i);
-        const V3 v = mk(o.x - s.x, o.y - s.y, o.z - s.z);
-        const float b = dot(d, v);
-        const float c = dot(v, v) - s.w;
-        const float disc = b * b - c;
+        float b, disc;
+        sphere_terms(sc.sphere(i), o, d, b, disc);
         if (disc < 0.0f) return false;
         const float sq = fsqrt(disc);
         t1 = -b - sq;
         t2 = -b + sq;
         return t1 <= t2;
     }
-    const float4 lo = sc.cmin(i - sc.nS), hi = sc.cmax(i - sc.nS);
-    const float ax = (lo.x - o.x) * inv.x, ay = (lo.y - o.y) * inv.y, az = (lo.z - o.z) * inv.z;
-    const float bx = (hi.x - o.x) * inv.x, by = (hi.y - o.y) * inv.y, bz = (hi.z - o.z) * inv.z;
-    t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
-    t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
+    slab_terms(sc.cmin(i - sc.nS), sc.cmax(i - sc.nS), o, ri, t1, t2);
     return t1 <= t2;
 }
 // All 32 lanes call this.  The n_live live rays of the warp (bits of `live`) are served by groups of g = 32 / next_pow2(n_live)
@@ -469,7 +499,7 @@ __device__ __forceinline__ void trace_group(const PackedScene& sc, unsigned lane
     const int src = (grp < n_live) ? (int)src_bit : (int)(__ffs(live) - 1);   // spare groups shadow the first ray (result unused)
     const V3 o = mk(__shfl_sync(0xffffffffu, o_.x, src), __shfl_sync(0xffffffffu, o_.y, src), __shfl_sync(0xffffffffu, o_.z, src));
     const V3 d = mk(__shfl_sync(0xffffffffu, d_.x, src), __shfl_sync(0xffffffffu, d_.y, src), __shfl_sync(0xffffffffu, d_.z, src));
-    const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
+    const RayInv inv = ray_inverse(o, d);
     const int n = sc.nS + sc.nC;
 
     uint32_t key; int idx, k_idx; float t1, t2, k_t2;
@@ -526,7 +556,7 @@ __device__ __forceinline__ void trace_group(const PackedScene& sc, unsigned lane
 // exact formulas.  Because candidates arrive out of index order, the order-dependent fold is rebuilt from its closed form
 // (see trace_group): pass 0 finds K, the largest index containing the origin, and the first-index argmin of the entry distance;
 // if K exists a second pass looks only at later primitives that beat t2_K.
-__device__ __forceinline__ void bvh_consider(const PackedScene& sc, int i, V3 o, V3 d, V3 inv, int after, float limit,
+__device__ __forceinline__ void bvh_consider(const PackedScene& sc, int i, V3 o, V3 d, const RayInv& inv, int after, float limit,
                                              uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2, float& best)
 {
     float a1, a2;
@@ -546,7 +576,7 @@ __device__ __forceinline__ bool bvh_box(const float4 lo, const float4 hi, V3 o, 
     const float tf = fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz)));
     return tn <= tf && tf >= -tau && tn <= best + tau;
 }
-__device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, V3 inv, int after, float limit, float best,
+__device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, const RayInv& inv, int after, float limit, float best,
                                          uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2, int* visits = nullptr)
 {
     key = 0xffffffffu; idx = 0x7fffffff; t1b = kFloatMax; t2b = 0.0f; k_idx = -1; k_t2 = 0.0f;
@@ -562,8 +592,8 @@ __device__ __forceinline__ void bvh_pass(const PackedScene& sc, V3 o, V3 d, V3 i
             for (int j = 0; j < count; ++j) bvh_consider(sc, sc.pidx[first + j], o, d, inv, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
         } else {
             float tl, tr;
-            const bool hl = bvh_box(sc.nodes[2 * first], sc.nodes[2 * first + 1], o, inv, sc.tau, best, tl);
-            const bool hr = bvh_box(sc.nodes[2 * first + 2], sc.nodes[2 * first + 3], o, inv, sc.tau, best, tr);
+            const bool hl = bvh_box(sc.nodes[2 * first], sc.nodes[2 * first + 1], o, inv.inv, sc.tau, best, tl);
+            const bool hr = bvh_box(sc.nodes[2 * first + 2], sc.nodes[2 * first + 3], o, inv.inv, sc.tau, best, tr);
             if (hl && hr) {
                 const bool left_first = tl <= tr;
                 if (sp < 32) stack[sp++] = left_first ? first + 1 : first;
@@ -581,7 +611,7 @@ __device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, flo
     // non-finite rays (normalize(0) after total internal reflection, ...) take the plain fold: nothing to cull by
     const float fin = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
     if (!(fin <= kFloatMax)) { trace(sc, o, d, T, prim, inside); return; }
-    const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
+    const RayInv inv = ray_inverse(o, d);
     uint32_t key; int idx, k_idx; float t1, t2, k_t2;
     bvh_pass(sc, o, d, inv, -1, kFloatMax, kFloatMax, key, idx, t1, t2, k_idx, k_t2, visits);
     if (k_idx < 0) {
@@ -609,32 +639,32 @@ __device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, flo
 // loop runs for the lane with the most candidates of its warp (~12 spheres + ~4 cuboids).
 __device__ __forceinline__ unsigned long long rct_lookup(const RenderParams& P, V3 o, V3 d, V3 inv)
 {
-    const float fin = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
-    const int cx = __float2int_rd((o.x - P.rct_lo[0]) * P.rct_inv[0]);
-    const int cy = __float2int_rd((o.y - P.rct_lo[1]) * P.rct_inv[1]);
-    const int cz = __float2int_rd((o.z - P.rct_lo[2]) * P.rct_inv[2]);
+    // every comparison below is false for a NaN operand, so non-finite origins and directions fall through to the full mask
+    const float fx = (o.x - P.rct_lo[0]) * P.rct_inv[0], fy = (o.y - P.rct_lo[1]) * P.rct_inv[1], fz = (o.z - P.rct_lo[2]) * P.rct_inv[2];
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    int f;
-    float im, ua, ub;
-    if (ax >= ay && ax >= az) { f = d.x < 0.0f ? 1 : 0; im = fabsf(inv.x); ua = d.y; ub = d.z; }
-    else if (ay >= az) { f = d.y < 0.0f ? 3 : 2; im = fabsf(inv.y); ua = d.x; ub = d.z; }
-    else { f = d.z < 0.0f ? 5 : 4; im = fabsf(inv.z); ua = d.x; ub = d.y; }
-    const bool ok = fin <= kFloatMax && im <= 2.0f && (unsigned)cx < (unsigned)P.rct_n[0] && (unsigned)cy < (unsigned)P.rct_n[1] &&
-                    (unsigned)cz < (unsigned)P.rct_n[2];       // im <= 2: the major component of a unit vector is >= 0.577
-    if (!ok) return ~0ull;
-    const int G = P.rct_G;
-    const int gu = min(G - 1, max(0, __float2int_rd((ua * im + 1.0f) * P.rct_halfG)));
-    const int gv = min(G - 1, max(0, __float2int_rd((ub * im + 1.0f) * P.rct_halfG)));
-    const size_t cell = ((size_t)cz * P.rct_n[1] + cy) * P.rct_n[0] + cx;
-    return __ldg(P.rct + (cell * 6 + f) * (size_t)(G * G) + gv * G + gu);
+    const bool mx = ax >= ay && ax >= az, my = !mx && ay >= az;
+    const float dm = mx ? d.x : (my ? d.y : d.z);
+    const float im = fabsf(mx ? inv.x : (my ? inv.y : inv.z));
+    const float u = (mx ? d.y : d.x) * im, v = ((mx || my) ? d.z : d.y) * im;
+    // 0.5 <= im <= 2: the major component of a unit vector lies in [0.577, 1]; anything else (zero, huge, inf) is not classified
+    const bool ok = fx >= 0.0f && fx < P.rct_nf[0] && fy >= 0.0f && fy < P.rct_nf[1] && fz >= 0.0f && fz < P.rct_nf[2] &&
+                    im >= 0.5f && im <= 2.0f && fabsf(u) <= 1.0001f && fabsf(v) <= 1.0001f;
+    if (!ok) return P.rct_valid;
+    const unsigned G = (unsigned)P.rct_G, Gm = G - 1u;
+    const unsigned gu = min(Gm, (unsigned)max(0, __float2int_rd(__fmaf_rn(u, P.rct_halfG, P.rct_halfG))));
+    const unsigned gv = min(Gm, (unsigned)max(0, __float2int_rd(__fmaf_rn(v, P.rct_halfG, P.rct_halfG))));
+    const unsigned f = (mx ? 0u : (my ? 2u : 4u)) + (dm < 0.0f ? 1u : 0u);
+    const unsigned cell = ((unsigned)__float2int_rd(fz) * (unsigned)P.rct_n[1] + (unsigned)__float2int_rd(fy)) * (unsigned)P.rct_n[0] + (unsigned)__float2int_rd(fx);
+    const unsigned entry = ((cell * 6u + f) * G + gv) * G + gu;          // < 2^23: the table is capped at 64 MiB
+    return __ldg(P.rct + entry);
 }
 __device__ __forceinline__ void trace_rct(const RenderParams& P, const PackedScene& sc, V3 o, V3 d, float& T, int& prim, bool& inside)
 {
     T = kFloatMax;
     prim = -1;
-    inside = false;
-    const V3 inv = mk(rcp(d.x), rcp(d.y), rcp(d.z));
-    const unsigned long long mask = rct_lookup(P, o, d, inv);
+    float t2w = 0.0f;
+    const RayInv ri = ray_inverse(o, d);
+    const unsigned long long mask = rct_lookup(P, o, d, ri.inv);
     const unsigned w0 = (unsigned)mask, w1 = (unsigned)(mask >> 32);
 #pragma unroll 1
     for (int w = 0; w < 2; ++w) {                       // spheres 0..31, then 32..63
@@ -645,29 +675,22 @@ __device__ __forceinline__ void trace_rct(const RenderParams& P, const PackedSce
             bits &= bits - 1u;
             float b, disc;
             sphere_terms(base[j], o, d, b, disc);
-            accept_sphere(b, disc, 32 * w + j, T, prim, inside);
+            accept_sphere(b, disc, 32 * w + j, T, prim, t2w);
         }
     }
 #pragma unroll 1
     for (int w = 0; w < 2; ++w) {                       // cuboids, bits nS..nS+nC-1
         unsigned bits = w ? (w1 & ~P.rct_sm1) : (w0 & ~P.rct_sm0);
-        const int first = 32 * w - sc.nS;
+        const float4* cub = sc.base + sc.off_cmin + 2 * (32 * w - sc.nS);
         while (bits) {
-            const int i = first + __ffs(bits) - 1;
+            const int j = __ffs(bits) - 1;
             bits &= bits - 1u;
-            if (i >= sc.nC) break;                      // bits beyond the last primitive (full mask of the fallback)
-            const float4 lo = sc.cmin(i), hi = sc.cmax(i);
-            const float ax = (lo.x - o.x) * inv.x, ay = (lo.y - o.y) * inv.y, az = (lo.z - o.z) * inv.z;
-            const float bx = (hi.x - o.x) * inv.x, by = (hi.y - o.y) * inv.y, bz = (hi.z - o.z) * inv.z;
-            const float t1 = fmax_(kFloatMin, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
-            const float t2 = fmin_(kFloatMax, fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz))));
-            if (t1 <= t2 && t2 > 0.0f && t1 < T) {
-                T = t1 < 0.0f ? t2 : t1;
-                inside = (T == t2);
-                prim = sc.nS + i;
-            }
+            float t1, t2;
+            slab_terms(cub[2 * j], cub[2 * j + 1], o, ri, t1, t2);
+            accept(t1, t2, 32 * w + j, T, prim, t2w);
         }
     }
+    inside = (T == t2w);
 }
 
 #ifndef PTB_MEGA_ONLY      // (the fast-arithmetic translation unit compiles the megakernel only)
@@ -769,6 +792,30 @@ __global__ void blend_kernel(float4* __restrict__ image, const float4* __restric
     image[i] = make_float4(out.x, out.y, out.z, 1.0f);
 }
 
+// The same for a batch of consecutive frames traced by one launch (ptb_set_batch): the running mean is folded frame by frame in
+// registers — mix(mix(mix(prev, e0, b0), e1, b1), ...), exactly the operations of `frames` blend_kernel launches in the same
+// order — with one read and one write of the accumulation image instead of `frames` of each.
+constexpr int kMaxBatch = 16;
+struct BatchBlend {
+    float blend[kMaxBatch];        // 1 / (frame + 1) of each frame, host-rounded like RenderParams::blend
+    int frame0, frames;
+    unsigned long long stride;     // float4 elements between consecutive frames' estimates
+};
+__global__ void blend_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, size_t n, const __grid_constant__ BatchBlend B)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 acc = mk(0.0f, 0.0f, 0.0f);
+    if (B.frame0 > 0) {
+        const float4 l = image[i];
+        acc = mk(l.x, l.y, l.z);
+    }
+    for (int j = 0; j < B.frames; ++j) {
+        const float4 e = estimates[(size_t)j * B.stride + i];
+        acc = mix(acc, mk(e.x, e.y, e.z), B.blend[j]);
+    }
+    image[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+}
 #endif  // PTB_MEGA_ONLY
 
 // local row -> global y for the stripe partition
@@ -1033,8 +1080,8 @@ __global__ void pack_scene_kernel(const unsigned char* __restrict__ ubo, int max
     } else if (i < nS + nC) {
         const int c = i - nS;
         const float4* s = reinterpret_cast<const float4*>(ubo + (size_t)max_spheres * kSphereStride + (size_t)c * kCuboidStride);
-        block[off_cmin + c] = s[0];
-        block[off_cmax + c] = s[1];
+        block[off_cmin + 2 * c] = s[0];
+        block[off_cmax + 2 * c] = s[1];
         for (int k = 0; k < 4; ++k) block[off_mat + i * 4 + k] = s[2 + k];
     }
 }
@@ -1201,8 +1248,7 @@ __global__ void atmosphere_kernel(const __grid_constant__ AtmosParams A, float4*
 // next to the images on rank 0 (system-scope atomics): `consumed` = frames the consumer has released, `arrived[slot]` = ranks
 // that have finished writing that slot.  Every wait is bounded by a timeout that raises `error` instead of hanging the GPU.
 struct ExchangeFlags {
-    unsigned arrived[8];     // per slot, monotonic: += 1 per rank per use
-    unsigned pad0[8];
+    unsigned arrived[16];    // per slot, monotonic: += 1 per rank per use
     unsigned consumed;       // frames released by rank 0's consumer
     unsigned pad1[15];
     unsigned error;          // != 0: a wait timed out
@@ -1261,6 +1307,43 @@ __global__ void blend_scatter_kernel(float4* __restrict__ image, const float4* _
             *block_count = 0u;
             __threadfence_system();
             atomicAdd_system(&flags->arrived[slot], 1u);
+        }
+    }
+}
+// The fused exchange for a batch: frame j's blended pixels go to rank 0's slot `slot[j]`; every slot gets its own arrival.
+struct BatchScatter {
+    float4* full[kMaxBatch];       // rank 0's row-major image of each frame's slot (peer mapping)
+    int slot[kMaxBatch];
+};
+__global__ void blend_scatter_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, int width, int local_rows, int height,
+                                           int rank, int world, int stripe_rows, const __grid_constant__ BatchBlend B,
+                                           const __grid_constant__ BatchScatter X, ExchangeFlags* flags, unsigned* block_count)
+{
+    const size_t n = (size_t)local_rows * width;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int lrow = (int)(i / (size_t)width), x = (int)(i - (size_t)lrow * width);
+        const int ls = lrow / stripe_rows;
+        const int y = (ls * world + rank) * stripe_rows + (lrow - ls * stripe_rows);
+        V3 acc = mk(0.0f, 0.0f, 0.0f);
+        if (B.frame0 > 0) {
+            const float4 l = image[i];
+            acc = mk(l.x, l.y, l.z);
+        }
+        for (int j = 0; j < B.frames; ++j) {
+            const float4 e = estimates[(size_t)j * B.stride + i];
+            acc = mix(acc, mk(e.x, e.y, e.z), B.blend[j]);
+            if (y < height) X.full[j][(size_t)y * width + x] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        }
+        image[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(block_count, 1u) == gridDim.x - 1) {       // last block of this rank: everything above is visible system-wide
+            *block_count = 0u;
+            __threadfence_system();
+            for (int j = 0; j < B.frames; ++j) atomicAdd_system(&flags->arrived[X.slot[j]], 1u);
         }
     }
 }
@@ -1428,7 +1511,7 @@ __global__ void dbg_trace_kernel(const __grid_constant__ RenderParams P, const f
             // q[3]: candidates the table left for this ray (65 = the ray took the full mask: outside the grid / non-finite)
             trace_rct(P, sc, o, d, T, prim, inside);
             const unsigned long long mk64 = rct_lookup(P, o, d, mk(rcp(d.x), rcp(d.y), rcp(d.z)));
-            visits = mk64 == ~0ull ? 65 : __popcll(mk64);
+            visits = mk64 == P.rct_valid ? 65 : __popcll(mk64);
         }
         float* q = out + 12 * i;
         const bool hit = T != kFloatMax;

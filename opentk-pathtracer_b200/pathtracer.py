@@ -309,6 +309,15 @@ class PathTracer:
     def KernelLaunches(self) -> int:
         return _lib.check(self._L.ptb_kernel_launches(self._ctx))
 
+    def SetKernelTiming(self, enabled: bool) -> None:
+        _lib.check(self._L.ptb_set_kernel_timing(self._ctx, int(enabled)))
+
+    def KernelTime(self) -> dict:
+        """Summed device time of the megakernel launches since the last call (ptb_kernel_time): ms, frames, launches."""
+        ms, fr, ln = C.c_double(), C.c_longlong(), C.c_longlong()
+        _lib.check(self._L.ptb_kernel_time(self._ctx, C.byref(ms), C.byref(fr), C.byref(ln)))
+        return dict(ms=ms.value, frames=fr.value, launches=ln.value)
+
     def SetPrecision(self, precision: int) -> None:
         """PRECISION_EXACT (default; bit-identical to the oracle) or PRECISION_FAST (MUFU + FMA build of the same kernel)."""
         _lib.check(self._L.ptb_set_precision(self._ctx, int(precision)))
