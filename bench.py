@@ -21,8 +21,8 @@ accumulated image must be below the north star's 1e-6 — and uses it when it pa
 CPU oracle and the compiled reference shaders) is timed beside it and reported under `exact`.
 
 Prints ONE JSON line (rank 0).  `value`: CUDA events on the launching stream around K steps, inputs resident in HBM.
-L2: no flush kernel runs inside the timed region — the frame estimates rotate through 2 x 16 scratch images per rank
-(>= 0.5 GB at 1080p on one GPU), far more than the 126 MB L2, so no step finds its inputs or outputs cached.
+L2: no flush kernel runs inside the timed region — the frame estimates rotate through 3 x 16 scratch images per rank
+(1.6 GB at 1080p on one GPU, 200 MB on an eighth of the frame), far more than the 126 MB L2, so no step finds its inputs or outputs cached.
 `e2e`: the same metric through the public API with host buffers, one Render() per step: the per-frame camera UBO upload
 the C# host does (MainWindow.cs:131-132) and a read-back of every frame into pinned host memory as RGB32F.
 `--impl reference` times the reference's own compute shader on the host CPUs (oracle/_ref: compute.glsl compiled by g++ from
@@ -51,7 +51,7 @@ CONFIGS = {
 }
 STRIPE_ROWS = 8
 BATCH = max(1, min(16, int(os.environ.get("PTB_BATCH", "16"))))
-EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "16"))      # full-image buffers on rank 0 (>= the batch: every frame of a batch has its own)
+EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "32"))      # full-image buffers on rank 0 (>= the batch: every frame of a batch has its own)
 MSE_TOLERANCE = 1e-6                                         # north star: per-channel MSE at matched seed
 
 
@@ -243,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
         if fused:
             # CUDA IPC needs peer access between the ranks' devices; if any rank cannot set it up, everybody uses NCCL
             try:
-                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True, slots=EXCHANGE_SLOTS)
+                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True, slots=EXCHANGE_SLOTS, rgb=True)
                 ok = torch.ones(1, device=dev)
             except Exception as exc:      # noqa: BLE001
                 print(f"rank {rank}: fused exchange unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr, flush=True)
@@ -316,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ device-timed region
     def timed(steps):
         """K steps enqueued in batches on the launching stream, one CUDA-event bracket around the whole region (the pipeline is
-        drained inside it).  No flush kernel: the estimates rotate through 2 x BATCH scratch images (> L2)."""
+        drained inside it).  No flush kernel: the estimates rotate through 3 x BATCH scratch images (> L2)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
@@ -342,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             ms, clk = timed(steps), None
         launches = pt.KernelLaunches - launches0
-        # the megakernel launches themselves, in the same batched / pipelined / tiled mode (event pair around each launch)
+        # the megakernel launches themselves, in the same batched / pipelined / tiled mode (device-side bracket of each launch)
         barrier()
         pt.SetKernelTiming(True)
         run_steps(max(BATCH, min(steps, 8 * BATCH)))
@@ -378,10 +378,10 @@ def run_ours(args, rank, world, local_rank):
                 print(f"shared host frame unavailable ({exc}); e2e falls back to rank 0's copy of the assembled image", file=sys.stderr, flush=True)
             shared = None
     rgb_e2e = world == 1 or shared is not None
-    host_bufs = [torch.empty((H if rank == 0 else 1, W, 3 if world == 1 else 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_bufs = [torch.empty((H if rank == 0 else 1, W, 3 if tiled is None else tiled.channels), dtype=torch.float32).pin_memory() for _ in range(2)]
     side = torch.cuda.Stream(device=dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
-    snap = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1 and shared is None) else None
+    snap = [torch.empty((H, W, tiled.channels), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1 and shared is None) else None
     state = {"i": 0}
 
     def step_e2e():
@@ -513,7 +513,8 @@ def run_ours(args, rank, world, local_rank):
             ptr, _ = solo.ResultDevicePtr()
             want = torch.as_tensor(D._DeviceBuffer(ptr, (H, W, 4)), device=dev)
             got = keep["img"]
-            same = bool((got.view(torch.int32) == want.view(torch.int32)).all().item())
+            want = want[..., :got.shape[-1]]         # RGB32F slots carry the three colour floats; alpha is the constant 1.0
+            same = bool((got.view(torch.int32) == want.contiguous().view(torch.int32)).all().item())
             exchange_check = {"exchange_equals_single_gpu": same, "frames": n_chk,
                               "max_abs_diff": float((got - want).abs().max().item()),
                               "note": f"{n_chk} frames from a reset through the {world}-GPU exchange vs the same frames rendered by rank 0's GPU alone (untiled), compared on the device"}
@@ -534,20 +535,21 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": cfg["workload"], "name": args.config,
                    "precision": (f"{prec_name}: " + ("MUFU rcp/rsq/sin/cos/ex2 + FMA contraction (ptb_set_precision), within the north star's per-channel MSE < 1e-6 of the exact build on this workload (see precision_gate)"
                                                      if prec_name == "fast" else "the evaluation model of DESIGN.md §2, bit-identical to the CPU oracle and the compiled reference shaders")),
-                   "l2": f"no flush kernel in the timed region: the frame estimates rotate through 2 x {BATCH} scratch images per rank ({2 * BATCH * rows_local * W * 16 / 1e6:.0f} MB on this rank, L2 is 126 MB); inputs larger than L2",
-                   "partition": (f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + (f"exchange fused into the batch blend kernel: peer stores into rank 0's per-frame slots over NVLink (CUDA IPC, {EXCHANGE_SLOTS} slots), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render")) if world > 1 else "single GPU, no collective",
+                   "l2": f"no flush kernel in the timed region: the frame estimates rotate through 3 x {BATCH} scratch images per rank ({3 * BATCH * rows_local * W * 16 / 1e6:.0f} MB on this rank, L2 is 126 MB); inputs larger than L2",
+                   "partition": (f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + (f"exchange fused into the batch blend kernel: peer stores into rank 0's per-frame slots over NVLink (CUDA IPC, {EXCHANGE_SLOTS} RGB32F slots: colour floats bit for bit, the constant alpha is not shipped), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render")) if world > 1 else "single GPU, no collective",
                    "kernel": f"persistent megakernel, {BATCH} consecutive frames per launch (ptb_set_batch) + one blend kernel per batch, {frames_in_flight} batches in flight; ray-classification table for scenes of <= 64 primitives, shared-memory BVH above 96"},
         "precision_gate": gate,
         "exact": exact,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": f"ptb{'_fast' if prec_name == 'fast' else ''}::megakernel",
                      "kernel_ms": kern_ms, "kernel_ms_per_launch": kern_launch_ms, "frames_per_launch": frames_per_launch,
-                     "kernel_timing": "CUDA-event pair around every megakernel launch on its own stream, in the same batched / pipelined / tiled mode as `value` (ptb_set_kernel_timing), max over ranks; kernel_ms is per frame",
+                     "kernel_timing": "device-side bracket of every megakernel launch (first CTA start -> last CTA end, %globaltimer) in the same batched / pipelined / tiled mode as `value` (ptb_set_kernel_timing), max over ranks; kernel_ms is per frame; consecutive launches overlap in the drain of the previous grid, so kernel_ms can exceed ms_per_step by that overlap",
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "note": "the pass is FP32-issue-bound, not HBM-bound: thousands of lane-instructions per 32 B of image traffic (DESIGN.md); `traffic` and ncu_capture come from the committed single-GPU c2 capture named in profiles/ncu_summary.json and are attached to that configuration only",
                      "ncu_capture": ({k: ncu.get(k) for k in ("source", "kernel", "smsp_issue_active_pct", "inst_executed_per_launch", "thread_inst_per_sample", "frames_per_launch")} if ncu else None)},
         "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": (80 + 144) * world,
-                "d2h_bytes_per_step": W * H * (12 if rgb_e2e else 16), "steps": e2e_steps, "format": "RGB32F" if rgb_e2e else "RGBA32F",
+                "d2h_bytes_per_step": W * H * (12 if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else 16), "steps": e2e_steps,
+                "format": "RGB32F" if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else "RGBA32F",
                 "last_frame_on_host_equals_device_image": e2e_verified,
                 "note": ("one Render() per step (no batching: every frame is read back): InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), the frame read back to pinned host memory as RGB32F "
                          "(colour floats bit for bit; the constant alpha 1.0 of compute.glsl:129 is not shipped) through the pipelined read-back (snapshot/pack kernel on the render stream + copy stream, "

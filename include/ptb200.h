@@ -141,6 +141,10 @@ int ptb_max_local_rows(ptb_ctx* ctx);
  * ptb_render on every rank, and on rank 0 ptb_exchange_acquire (stream-ordered wait for all ranks, returns the frame's
  * device buffer), consumer work on the context stream, ptb_exchange_release.  Waits time out after 4 s (ptb_exchange_status). */
 int ptb_exchange_init(ptb_ctx* ctx, int slots);
+/* The same with the pixel format of the slots: PTB_FORMAT_RGBA32F (what ptb_exchange_init uses) or PTB_FORMAT_RGB32F — packed
+ * colour floats, bit for bit; the constant alpha 1.0 (compute.glsl:129) is not shipped, which takes a quarter off rank 0's
+ * NVLink ingress, the resource that bounds the exchange once the frame is split over many GPUs. */
+int ptb_exchange_init_format(ptb_ctx* ctx, int slots, int format);
 int ptb_exchange_handle(ptb_ctx* ctx, void* handle64);
 int ptb_exchange_attach(ptb_ctx* ctx, const void* handle64);
 int ptb_exchange_acquire(ptb_ctx* ctx, void** full_device);
@@ -188,8 +192,10 @@ int ptb_set_ray_classification(ptb_ctx* ctx, int mode, int cells, int buckets);
  * (default 96).  Results do not depend on it (the hierarchy only removes primitives that fail the exact test). */
 int ptb_set_bvh_threshold(ptb_ctx* ctx, int primitives);
 /* Device time of the megakernel launches themselves, in whatever mode is running (pipelined, batched, tiled): with timing
- * enabled every megakernel launch is bracketed by a CUDA-event pair on the stream it runs on; ptb_kernel_time() waits for the
- * outstanding pairs, returns the summed duration, the frames and the launches they covered, and restarts the count. */
+ * enabled every launch records when its first CTA starts and when its last CTA ends (%globaltimer, two atomics per CTA);
+ * ptb_kernel_time() waits for the outstanding launches, returns the summed duration in ms, the frames and the launches they
+ * covered, and restarts the count.  Consecutive launches of a pipelined render overlap (the next grid's CTAs move in as the
+ * previous grid's longest paths drain), so the sum can exceed the wall time of the region by that overlap. */
 int ptb_set_kernel_timing(ptb_ctx* ctx, int enabled);
 int ptb_kernel_time(ptb_ctx* ctx, double* ms_total, long long* frames, long long* launches);
 int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this context so far */

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -37,6 +38,10 @@ int fail(int code, const char* fmt, ...)
 constexpr int kBasicBytes = 144;   // MainWindow.cs:196
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kMaxOverlap = 4;
+// Scratch sets of the batched path.  Three, not two: with two, the trace of batch k+2 would wait for the blend of batch k, which
+// itself can only start once batch k+1's persistent grid lets go of its CTA slots — trace and blend would take turns instead of
+// overlapping.  With three, batch k+2 only needs the blend of batch k-1.
+constexpr int kBatchSets = 3;
 
 } // namespace
 
@@ -110,7 +115,7 @@ struct ptb_ctx {
     size_t scratch_bytes = 0;
     unsigned long long launch_seq = 0;
     // fused multi-GPU exchange (ptb_exchange_*): rank 0 owns [flags | slots x full image]; other ranks map it through CUDA IPC
-    bool xch_on = false, xch_mapped = false;
+    bool xch_on = false, xch_mapped = false, xch_rgb = false;
     int xch_slots = 0;
     unsigned char* xch_block = nullptr;
     size_t xch_image_bytes = 0;
@@ -125,17 +130,21 @@ struct ptb_ctx {
     // frame batching (ptb_set_batch): up to `batch` consecutive frames of one ptb_render_frames call are traced by ONE
     // megakernel launch into a set of per-frame scratch images; two sets alternate so that the blends of batch k run beside
     // the trace of batch k+1
+    unsigned* d_done = nullptr;      // [kBatchSets] "batch traced" flags (written by the trace's last CTA) + [kBatchSets] a sticky error word
+    int blend_ctas = 64;             // grid of the batch blend kernels (a background kernel beside the next batch's trace)
     int batch = 16;
-    float4* d_batch_scratch[2] = {nullptr, nullptr};
+    float4* d_batch_scratch[kBatchSets] = {};
     size_t batch_scratch_frames = 0, batch_scratch_stride = 0;     // frames per set / float4 elements per frame
-    unsigned int* d_batch_counters[2] = {nullptr, nullptr};
-    cudaEvent_t ev_batch_trace[2] = {nullptr, nullptr}, ev_batch_blend[2] = {nullptr, nullptr};
-    bool batch_blend_recorded[2] = {false, false};
+    unsigned int* d_batch_counters[kBatchSets] = {};
+    cudaEvent_t ev_batch_trace[kBatchSets] = {}, ev_batch_blend[kBatchSets] = {};
+    bool batch_blend_recorded[kBatchSets] = {};
     unsigned long long batch_seq = 0;
     bool mega_ring = true;
     int mega_fold_set = -1;
     // ptb_set_kernel_timing: an event pair around every megakernel launch, on the stream it runs on
     bool kt_on = false;
+    unsigned long long* d_kt = nullptr;        // 8 x {min CTA start, max CTA end}
+    unsigned long long* h_kt = nullptr;        // pinned: [0..15] results, [16..17] the initial pair {~0, 0}
     cudaEvent_t kt_a[8] = {}, kt_b[8] = {};
     int kt_frames[8] = {};
     bool kt_used[8] = {};
@@ -559,6 +568,8 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.tiles_magic = (P.tiles_x > 1 && (unsigned long long)P.tiles_total * P.tiles_x < (1ull << 32)) ? (unsigned)(((1ull << 32) + P.tiles_x - 1) / P.tiles_x) : 0u;
     P.batch = 1;
     P.scratch_stride = 0ull;
+    P.ktime = nullptr;
+    P.done_flag = nullptr; P.done_value = 0u;
     P.rct = c->rct_on ? c->d_rct : nullptr;
     for (int k = 0; k < 3; ++k) { P.rct_lo[k] = c->rct_lo[k]; P.rct_inv[k] = c->rct_inv[k]; P.rct_n[k] = c->rct_n[k]; }
     P.rct_G = c->rct_G; P.rct_halfG = 0.5f * (float)c->rct_G;
@@ -658,11 +669,15 @@ int launch_frame(ptb_ctx* c)
             if (c->xch_on) {
                 const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
                 const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
-                if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
-                blend_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(
-                    c->d_image, c->d_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->frame, P.blend,
-                    reinterpret_cast<float4*>(c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes), reinterpret_cast<ExchangeFlags*>(c->xch_block),
-                    slot, c->d_xch_blocks);
+                BatchBlend B = {};
+                B.frame0 = c->frame; B.frames = 1; B.stride = 0ull; B.blend[0] = P.blend;
+                BatchScatter X = {};
+                X.slot[0] = slot;
+                X.full[0] = c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes;
+                const BatchWait none = {nullptr, 0u, nullptr};      // ordered by the stream event above
+                blend_scatter_batch_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 4), 256, 0, bs>>>(
+                    c->d_image, c->d_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->xch_rgb ? 1 : 0, B, X,
+                    reinterpret_cast<ExchangeFlags*>(c->xch_block), need, c->d_xch_blocks, none);
                 c->xch_seq++;
             } else {
                 blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_scratch[s], n, c->frame, P.blend);
@@ -705,9 +720,11 @@ int kt_collect(ptb_ctx* c, int slot)
 {
     if (!c->kt_used[slot]) return PTB_OK;
     CU(cudaEventSynchronize(c->kt_b[slot]));
-    float ms = 0.0f;
-    CU(cudaEventElapsedTime(&ms, c->kt_a[slot], c->kt_b[slot]));
-    c->kt_ms += ms; c->kt_frames_total += c->kt_frames[slot]; c->kt_launches++;
+    // device-side bracket: first CTA start -> last CTA end (an event pair on the stream would also count the time a launch
+    // waits for SM slots behind the previous, still resident, persistent grid)
+    const unsigned long long t0 = c->h_kt[2 * slot], t1 = c->h_kt[2 * slot + 1];
+    if (t1 > t0) c->kt_ms += (double)(t1 - t0) * 1e-6;
+    c->kt_frames_total += c->kt_frames[slot]; c->kt_launches++;
     c->kt_used[slot] = false;
     return PTB_OK;
 }
@@ -718,17 +735,20 @@ int launch_mega(ptb_ctx* c, const RenderParams& P, bool batch, int smem, cudaStr
     if (c->kt_on) {
         slot = (int)(c->kt_next++ % 8u);
         { const int rc = kt_collect(c, slot); if (rc != PTB_OK) return rc; }
-        CU(cudaEventRecord(c->kt_a[slot], stream));
+        CU(cudaMemcpyAsync(c->d_kt + 2 * slot, c->h_kt + 16, 16, cudaMemcpyHostToDevice, stream));
     }
+    RenderParams Pt = P;
+    Pt.ktime = slot >= 0 ? c->d_kt + 2 * slot : nullptr;
     if (c->precision == PTB_PRECISION_FAST) {
-        CU(ptb_fast_api::launch(&P, fold_of(c), c->mega_ring, batch, c->mega_grid, smem, stream));
+        CU(ptb_fast_api::launch(&Pt, fold_of(c), c->mega_ring, batch, c->mega_grid, smem, stream));
     } else {
-        const int rc = batch ? with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; })
-                             : with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(P); return PTB_OK; });
+        const int rc = batch ? with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(Pt); return PTB_OK; })
+                             : with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(Pt); return PTB_OK; });
         if (rc != PTB_OK) return rc;
         CU(cudaGetLastError());
     }
     if (slot >= 0) {
+        CU(cudaMemcpyAsync(c->h_kt + 2 * slot, c->d_kt + 2 * slot, 16, cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(c->kt_b[slot], stream));
         c->kt_frames[slot] = batch ? P.batch : 1;
         c->kt_used[slot] = true;
@@ -748,7 +768,7 @@ int ensure_batch(ptb_ctx* c, int frames)
     const size_t stride = c->image_bytes / sizeof(float4);
     if (c->batch_scratch_frames < (size_t)frames || c->batch_scratch_stride != stride) {
         { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kBatchSets; ++s) {
             if (c->d_batch_scratch[s]) { CU(cudaFree(c->d_batch_scratch[s])); c->d_batch_scratch[s] = nullptr; }
             CU(cudaMalloc(&c->d_batch_scratch[s], (size_t)frames * c->image_bytes));
             c->batch_blend_recorded[s] = false;
@@ -756,7 +776,12 @@ int ensure_batch(ptb_ctx* c, int frames)
         c->batch_scratch_frames = (size_t)frames;
         c->batch_scratch_stride = stride;
     }
-    for (int s = 0; s < 2; ++s) {
+    if (!c->d_done) {
+        CU(cudaMalloc(&c->d_done, (kBatchSets + 1) * sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->d_done, 0, (kBatchSets + 1) * sizeof(unsigned), c->stream));
+        { const int rc = mark_inputs(c); if (rc != PTB_OK) return rc; }
+    }
+    for (int s = 0; s < kBatchSets; ++s) {
         if (!c->d_batch_counters[s]) {
             CU(cudaMalloc(&c->d_batch_counters[s], 2 * sizeof(unsigned int)));
             CU(cudaMemsetAsync(c->d_batch_counters[s], 0, 2 * sizeof(unsigned int), c->stream));
@@ -781,42 +806,51 @@ int launch_batch(ptb_ctx* c, int frames)
         if (rc != PTB_OK) return rc;
         return frames > 1 ? (frames - 1 >= 2 ? launch_batch(c, frames - 1) : launch_frame(c)) : PTB_OK;
     }
-    const int s = (int)(c->batch_seq & 1ull);
-    cudaStream_t ts = c->trace_stream[s];
-    if (c->seen_version[s] != c->inputs_version) { CU(cudaStreamWaitEvent(ts, c->ev_inputs, 0)); c->seen_version[s] = c->inputs_version; }
+    const int s = (int)(c->batch_seq % (unsigned long long)kBatchSets);      // scratch set
+    const int t = (int)(c->batch_seq & 1ull);                                // trace stream
+    cudaStream_t ts = c->trace_stream[t];
+    if (c->seen_version[t] != c->inputs_version) { CU(cudaStreamWaitEvent(ts, c->ev_inputs, 0)); c->seen_version[t] = c->inputs_version; }
     if (c->batch_blend_recorded[s]) CU(cudaStreamWaitEvent(ts, c->ev_batch_blend[s], 0));      // this scratch set has been consumed
     P.scratch = c->d_batch_scratch[s];
     P.counters = c->d_batch_counters[s];
     P.batch = frames;
     P.scratch_stride = (unsigned long long)c->batch_scratch_stride;
+    // the blend kernel of this batch does not wait for a stream event: it is launched right behind the trace, takes CTA slots
+    // as soon as the previous grid frees some, and spins on this flag (see wait_for_trace)
+    P.done_flag = c->d_done + s;
+    P.done_value = (unsigned)(c->batch_seq + 1ull);
     const int rc = launch_mega(c, P, true, smem, ts);
     if (rc != PTB_OK) return rc;
     CU(cudaEventRecord(c->ev_batch_trace[s], ts));
     cudaStream_t bs = c->blend_stream;
     if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
-    CU(cudaStreamWaitEvent(bs, c->ev_batch_trace[s], 0));
     const size_t n = (size_t)c->local_rows * c->width;
     c->launches++;
+    BatchWait Wt = {c->d_done + s, (unsigned)(c->batch_seq + 1ull), c->d_done + kBatchSets};
     // one blend kernel for the whole batch: the running mean is folded frame by frame in registers (same operations, same order)
     BatchBlend B = {};
     B.frame0 = c->frame; B.frames = frames; B.stride = (unsigned long long)c->batch_scratch_stride;
     for (int j = 0; j < frames; ++j) B.blend[j] = 1.0f * (1.0f / (float)(c->frame + j + 1));     // as fill_params: 1.0 / (thisRendererFrame + 1)
+    // a batch blend is a background kernel: it has a whole batch time to move a few hundred MB, so it gets a small grid and
+    // leaves the CTA slots to the next batch's persistent grid (PTB_BLEND_CTAS overrides the default for experiments)
+    static const int blend_ctas_env = getenv("PTB_BLEND_CTAS") ? atoi(getenv("PTB_BLEND_CTAS")) : 0;
+    const size_t blend_cap = blend_ctas_env > 0 ? (size_t)blend_ctas_env : (size_t)c->blend_ctas;
+    const unsigned blend_grid = (unsigned)std::min<size_t>((n + 255) / 256, blend_cap);
     if (c->xch_on) {
         BatchScatter X = {};
         for (int j = 0; j < frames; ++j) {
             X.slot[j] = (int)((c->xch_seq + j) % (unsigned long long)c->xch_slots);
-            X.full[j] = reinterpret_cast<float4*>(c->xch_block + 4096 + (size_t)X.slot[j] * c->xch_image_bytes);
+            X.full[j] = c->xch_block + 4096 + (size_t)X.slot[j] * c->xch_image_bytes;
         }
         // the batch's last frame needs the release of frame (seq_last - slots); `consumed` is monotonic, so that covers the others
         const unsigned long long last = c->xch_seq + frames - 1;
         const unsigned need = last >= (unsigned long long)c->xch_slots ? (unsigned)(last - c->xch_slots + 1) : 0u;
-        if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
-        blend_scatter_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_batch_scratch[s], c->width, c->local_rows, c->height, c->rank,
-                                                                                c->world, c->stripe_rows, B, X, reinterpret_cast<ExchangeFlags*>(c->xch_block),
-                                                                                c->d_xch_blocks);
+        blend_scatter_batch_kernel<<<blend_grid, 256, 0, bs>>>(
+            c->d_image, c->d_batch_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->xch_rgb ? 1 : 0, B, X,
+            reinterpret_cast<ExchangeFlags*>(c->xch_block), need, c->d_xch_blocks, Wt);
         c->xch_seq += frames;
     } else {
-        blend_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_batch_scratch[s], n, B);
+        blend_batch_kernel<<<blend_grid, 256, 0, bs>>>(c->d_image, c->d_batch_scratch[s], n, B, Wt);
     }
     CU(cudaGetLastError());
     c->launches++;
@@ -885,7 +919,7 @@ void ptb_destroy(ptb_ctx* c)
         if (c->ev_blend_done[i]) cudaEventDestroy(c->ev_blend_done[i]);
         if (c->trace_stream[i]) cudaStreamDestroy(c->trace_stream[i]);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kBatchSets; ++i) {
         cudaFree(c->d_batch_scratch[i]); cudaFree(c->d_batch_counters[i]);
         if (c->ev_batch_trace[i]) cudaEventDestroy(c->ev_batch_trace[i]);
         if (c->ev_batch_blend[i]) cudaEventDestroy(c->ev_batch_blend[i]);
@@ -900,6 +934,8 @@ void ptb_destroy(ptb_ctx* c)
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_stage[i]); if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (int i = 0; i < 8; ++i) { if (c->kt_a[i]) cudaEventDestroy(c->kt_a[i]); if (c->kt_b[i]) cudaEventDestroy(c->kt_b[i]); }
+    cudaFree(c->d_kt); if (c->h_kt) cudaFreeHost(c->h_kt);
+    cudaFree(c->d_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1247,6 +1283,31 @@ int ptb_deinterleave_device(ptb_ctx* c, const void* gathered, void* full)
     return PTB_OK;
 }
 
+// Stream memory operations of the driver API (no libcuda link dependency: resolved through the runtime).  With them rank 0's
+// acquire / release are commands of the stream's front end, not kernels — a one-thread kernel would have to wait for a CTA
+// slot, and a persistent grid frees none until it drains.
+typedef int (*StreamWaitValue32)(cudaStream_t, unsigned long long, unsigned, unsigned);
+typedef int (*StreamWriteValue32)(cudaStream_t, unsigned long long, unsigned, unsigned);
+static StreamWaitValue32 g_wait32 = nullptr;
+static StreamWriteValue32 g_write32 = nullptr;
+static bool g_memops_probed = false;
+static bool stream_memops()
+{
+    if (!g_memops_probed) {
+        g_memops_probed = true;
+        if (getenv("PTB_NO_MEMOPS")) return false;
+        void *w = nullptr, *r = nullptr;
+        cudaDriverEntryPointQueryResult q1, q2;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWriteValue32", &r, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess) {
+            g_wait32 = (StreamWaitValue32)w;
+            g_write32 = (StreamWriteValue32)r;
+        }
+        cudaGetLastError();
+    }
+    return g_wait32 && g_write32;
+}
+
 static int exchange_close(ptb_ctx* c)
 {
     if (c->xch_block) {
@@ -1259,15 +1320,18 @@ static int exchange_close(ptb_ctx* c)
     return PTB_OK;
 }
 
-int ptb_exchange_init(ptb_ctx* c, int slots)
+int ptb_exchange_init(ptb_ctx* c, int slots) { return ptb_exchange_init_format(c, slots, PTB_FORMAT_RGBA32F); }
+int ptb_exchange_init_format(ptb_ctx* c, int slots, int format)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
-    if (slots < 1 || slots > 16) return fail(PTB_E_INVALID, "slots %d outside [1,16]", slots);
+    if (format != PTB_FORMAT_RGBA32F && format != PTB_FORMAT_RGB32F) return fail(PTB_E_INVALID, "the exchange ships RGBA32F or RGB32F, not format %d", format);
+    if (slots < 1 || slots > kMaxSlots) return fail(PTB_E_INVALID, "slots %d outside [1,%d]", slots, kMaxSlots);
     if (c->overlap < 2) return fail(PTB_E_STATE, "the fused exchange needs the pipelined mode (ptb_set_overlap >= 2)");
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     exchange_close(c);
     c->xch_slots = slots;
-    c->xch_image_bytes = (((size_t)c->width * c->height * sizeof(float4)) + 255) & ~(size_t)255;
+    c->xch_rgb = format == PTB_FORMAT_RGB32F;
+    c->xch_image_bytes = (((size_t)c->width * c->height * (c->xch_rgb ? 12 : 16)) + 255) & ~(size_t)255;
     c->xch_seq = c->xch_acquired = c->xch_released = 0;
     if (!c->d_xch_blocks) { CU(cudaMalloc(&c->d_xch_blocks, sizeof(unsigned int))); }
     CU(cudaMemset(c->d_xch_blocks, 0, sizeof(unsigned int)));
@@ -1312,9 +1376,14 @@ int ptb_exchange_acquire(ptb_ctx* c, void** full_device)
     if (c->xch_acquired >= c->xch_seq) return fail(PTB_E_STATE, "no rendered frame left to acquire");
     const int slot = (int)(c->xch_acquired % (unsigned long long)c->xch_slots);
     const unsigned target = (unsigned)((c->xch_acquired / (unsigned long long)c->xch_slots + 1) * (unsigned long long)c->world);
-    exchange_acquire_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), slot, target);
-    CU(cudaGetLastError());
-    c->launches++;
+    ExchangeFlags* fl = reinterpret_cast<ExchangeFlags*>(c->xch_block);
+    if (stream_memops() && g_wait32(c->stream, (unsigned long long)(uintptr_t)&fl->arrived[slot], target, 0x1 /* CU_STREAM_WAIT_VALUE_GEQ */) == 0) {
+        // the stream's front end polls the arrival counter: no kernel, no CTA slot needed
+    } else {
+        exchange_acquire_kernel<<<1, 1, 0, c->stream>>>(fl, slot, target);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
     c->xch_acquired++;
     *full_device = c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes;
     return PTB_OK;
@@ -1325,9 +1394,13 @@ int ptb_exchange_release(ptb_ctx* c)
     if (!c->xch_on || c->rank != 0) return fail(PTB_E_STATE, "release is rank 0's side of an initialised exchange");
     if (c->xch_released >= c->xch_acquired) return fail(PTB_E_STATE, "nothing acquired");
     c->xch_released++;
-    exchange_release_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), (unsigned)c->xch_released);
-    CU(cudaGetLastError());
-    c->launches++;
+    ExchangeFlags* fl = reinterpret_cast<ExchangeFlags*>(c->xch_block);
+    if (stream_memops() && g_write32(c->stream, (unsigned long long)(uintptr_t)&fl->consumed, (unsigned)c->xch_released, 0x0 /* default: ordered after prior work */) == 0) {
+    } else {
+        exchange_release_kernel<<<1, 1, 0, c->stream>>>(fl, (unsigned)c->xch_released);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
     return PTB_OK;
 }
 int ptb_exchange_status(ptb_ctx* c)
@@ -1379,6 +1452,11 @@ int ptb_set_kernel_timing(ptb_ctx* c, int enabled)
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     for (int i = 0; i < 8; ++i) {
         if (enabled && !c->kt_a[i]) { CU(cudaEventCreate(&c->kt_a[i])); CU(cudaEventCreate(&c->kt_b[i])); }
+        if (enabled && !c->d_kt) {
+            CU(cudaMalloc(&c->d_kt, 16 * sizeof(unsigned long long)));
+            CU(cudaMallocHost(&c->h_kt, 18 * sizeof(unsigned long long)));
+            c->h_kt[16] = ~0ull; c->h_kt[17] = 0ull;
+        }
         c->kt_used[i] = false;
     }
     c->kt_on = enabled != 0;

@@ -40,6 +40,24 @@ constexpr int kCuboidStride = 96;   // Cuboid.cs:8
 #ifndef PTB_COOP_MAX
 #define PTB_COOP_MAX 8        // tail: at most this many live paths in a starved warp -> group-cooperative fold (0 disables)
 #endif
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 constexpr int kMegaThreads = PTB_THREADS;
 constexpr int kQueue = 64;          // primary-ray ring entries per warp (two tiles)
 
@@ -82,6 +100,9 @@ struct RenderParams {
     int rct_n[3], rct_G;                            // cells per axis, direction buckets per cube-face axis
     float rct_halfG;
     unsigned rct_sm0, rct_sm1;                      // which bits of the mask's low / high word are spheres
+    unsigned long long* ktime;                      // optional {min CTA start, max CTA end} in globaltimer ns (ptb_set_kernel_timing)
+    unsigned* done_flag;                            // optional: the last CTA out stores done_value here (release): the batch's blend
+    unsigned done_value;                            //   kernel, already resident, spins on it instead of waiting for a stream event
     float rct_nf[3];                                // cells per axis as floats (range test of the cell coordinates)
     unsigned long long rct_valid;                   // the mask of every existing primitive: what an unclassifiable ray tests
 };
@@ -801,20 +822,52 @@ struct BatchBlend {
     int frame0, frames;
     unsigned long long stride;     // float4 elements between consecutive frames' estimates
 };
-__global__ void blend_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, size_t n, const __grid_constant__ BatchBlend B)
+// Device-side dependency of a batch's blend kernel on the batch's trace.  A persistent grid leaves no CTA slot (and no
+// register) free while it runs, so a kernel that waited for the trace through a stream event could only start one batch late,
+// when the NEXT grid drains.  Instead the blend kernel is launched right behind the trace without a stream dependency: its few
+// CTAs (high-priority stream) take the first slots the previous grid frees, sit beside the trace, and start the moment the
+// trace's last CTA publishes `value` in `flag`.  The grid is small (<= 64 CTAs), so the trace always has CTA slots to finish.
+struct BatchWait {
+    const unsigned* flag;          // nullptr: nothing to wait for (the caller ordered the kernel by a stream event)
+    unsigned value;
+    unsigned* error;               // sticky: a wait that timed out
+};
+__device__ __forceinline__ void wait_for_trace(const BatchWait& Wt)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    V3 acc = mk(0.0f, 0.0f, 0.0f);
-    if (B.frame0 > 0) {
-        const float4 l = image[i];
-        acc = mk(l.x, l.y, l.z);
+    if (Wt.flag && threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        while ((int)(ld_acquire_gpu(Wt.flag) - Wt.value) < 0) {
+            __nanosleep(500);
+            if (global_ns() - t0 > 20000000000ull) { atomicExch(Wt.error, 1u); break; }
+        }
     }
-    for (int j = 0; j < B.frames; ++j) {
-        const float4 e = estimates[(size_t)j * B.stride + i];
-        acc = mix(acc, mk(e.x, e.y, e.z), B.blend[j]);
+    __syncthreads();
+}
+// Eight of a pixel's estimates are requested before the first one is used (eight independent 128-bit loads in flight per
+// thread, <= 64 registers), so a few dozen CTAs already move a batch at several hundred GB/s: a background job beside the next
+// batch's persistent grid, not a whole-machine pass.
+constexpr int kBlendChunk = 8;
+__global__ void __launch_bounds__(256, 4) blend_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, size_t n,
+                                                             const __grid_constant__ BatchBlend B, const __grid_constant__ BatchWait Wt)
+{
+    wait_for_trace(Wt);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        V3 acc = mk(0.0f, 0.0f, 0.0f);
+        if (B.frame0 > 0) {
+            const float4 l = image[i];
+            acc = mk(l.x, l.y, l.z);
+        }
+        for (int j0 = 0; j0 < B.frames; j0 += kBlendChunk) {
+            float4 e[kBlendChunk];
+#pragma unroll
+            for (int j = 0; j < kBlendChunk; ++j)
+                if (j0 + j < B.frames) e[j] = estimates[(size_t)(j0 + j) * B.stride + i];
+#pragma unroll
+            for (int j = 0; j < kBlendChunk; ++j)
+                if (j0 + j < B.frames) acc = mix(acc, mk(e[j].x, e[j].y, e[j].z), B.blend[j0 + j]);
+        }
+        image[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
     }
-    image[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
 }
 #endif  // PTB_MEGA_ONLY
 
@@ -877,6 +930,7 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
     __shared__ uint32_t s_ring[kRing ? (kMegaThreads / 32) * 8 * kQueue : 1];
     float4* sblock = reinterpret_cast<float4*>(smem_raw);
 
+    if (P.ktime && threadIdx.x == 0) atomicMin(P.ktime, global_ns());      // launch timing: when the first CTA starts
     // ---- stage the packed scene: one elected thread arms the barrier and issues the bulk copies
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
@@ -1034,8 +1088,13 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
     // ---- last CTA out re-arms the counters for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (P.ktime) atomicMax(P.ktime + 1, global_ns());                   // ... and when the last one ends
         __threadfence();
-        if (atomicAdd(P.counters + 1, 1u) == gridDim.x - 1) { P.counters[0] = 0u; P.counters[1] = 0u; __threadfence(); }
+        if (atomicAdd(P.counters + 1, 1u) == gridDim.x - 1) {
+            P.counters[0] = 0u; P.counters[1] = 0u;
+            __threadfence();
+            if (P.done_flag) st_release_gpu(P.done_flag, P.done_value);     // every CTA fenced before its increment: all estimates are visible
+        }
     }
 }
 
@@ -1247,8 +1306,9 @@ __global__ void atmosphere_kernel(const __grid_constant__ AtmosParams A, float4*
 // so the frame needs no staging copy, no NCCL gather and no de-interleave pass.  Flow control lives in a small flag block
 // next to the images on rank 0 (system-scope atomics): `consumed` = frames the consumer has released, `arrived[slot]` = ranks
 // that have finished writing that slot.  Every wait is bounded by a timeout that raises `error` instead of hanging the GPU.
+constexpr int kMaxSlots = 32;
 struct ExchangeFlags {
-    unsigned arrived[16];    // per slot, monotonic: += 1 per rank per use
+    unsigned arrived[kMaxSlots];   // per slot, monotonic: += 1 per rank per use
     unsigned consumed;       // frames released by rank 0's consumer
     unsigned pad1[15];
     unsigned error;          // != 0: a wait timed out
@@ -1261,12 +1321,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 __device__ __forceinline__ void wait_at_least(const unsigned* flag, unsigned target, unsigned* error)
 {
     const unsigned long long t0 = global_ns();
@@ -1277,67 +1331,69 @@ __device__ __forceinline__ void wait_at_least(const unsigned* flag, unsigned tar
     }
 }
 
-__global__ void blend_scatter_kernel(float4* __restrict__ image, const float4* __restrict__ estimate, int width, int local_rows, int height,
-                                     int rank, int world, int stripe_rows, int frame, float blend,
-                                     float4* __restrict__ full, ExchangeFlags* flags, int slot, unsigned* block_count)
-{
-    // (the wait for the slot to be free is a separate one-thread kernel ahead of this one on the same stream: if every block
-    //  of this grid spun on the flag they could fill all SM slots and starve the very kernel that releases the slot)
-    const size_t n = (size_t)local_rows * width;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int lrow = (int)(i / (size_t)width), x = (int)(i - (size_t)lrow * width);
-        const int ls = lrow / stripe_rows;
-        const int y = (ls * world + rank) * stripe_rows + (lrow - ls * stripe_rows);
-        const float4 e = estimate[i];
-        V3 last = mk(0.0f, 0.0f, 0.0f);
-        if (frame > 0) {
-            const float4 l = image[i];
-            last = mk(l.x, l.y, l.z);
-        }
-        const V3 out = mix(last, mk(e.x, e.y, e.z), blend);
-        const float4 o4 = make_float4(out.x, out.y, out.z, 1.0f);
-        image[i] = o4;
-        if (y < height) full[(size_t)y * width + x] = o4;
-        __threadfence_system();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(block_count, 1u) == gridDim.x - 1) {       // last block of this rank: everything above is visible system-wide
-            *block_count = 0u;
-            __threadfence_system();
-            atomicAdd_system(&flags->arrived[slot], 1u);
-        }
-    }
-}
-// The fused exchange for a batch: frame j's blended pixels go to rank 0's slot `slot[j]`; every slot gets its own arrival.
+// Blend + scatter for 1..16 consecutive frames (ptb_render: one frame from its scratch image; batches: all of them).  One
+// thread per pixel, all its estimates requested up front (see blend_batch_kernel); frame j's blended pixel goes to rank 0's
+// slot `slot[j]` (a CUDA-IPC peer mapping: the stores travel over NVLink) as RGBA32F or — `rgb` — as packed RGB32F: the alpha
+// the shader stores is the constant 1.0 (pt:129), and rank 0's NVLink ingress (7/8 of every frame at N = 8) is what bounds the
+// exchange, so it is not shipped.  Four neighbouring lanes then pass their colours one lane down and three of them store a
+// 128-bit piece of the quad's 48 bytes.  Every slot gets its own arrival from the kernel's last block.
 struct BatchScatter {
-    float4* full[kMaxBatch];       // rank 0's row-major image of each frame's slot (peer mapping)
+    void* full[kMaxBatch];         // rank 0's row-major image of each frame's slot (peer mapping)
     int slot[kMaxBatch];
 };
-__global__ void blend_scatter_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, int width, int local_rows, int height,
-                                           int rank, int world, int stripe_rows, const __grid_constant__ BatchBlend B,
-                                           const __grid_constant__ BatchScatter X, ExchangeFlags* flags, unsigned* block_count)
+__global__ void __launch_bounds__(256, 4) blend_scatter_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, int width,
+                                                                     int local_rows, int height, int rank, int world, int stripe_rows, int rgb,
+                                                                     const __grid_constant__ BatchBlend B, const __grid_constant__ BatchScatter X,
+                                                                     ExchangeFlags* flags, unsigned need_consumed, unsigned* block_count,
+                                                                     const __grid_constant__ BatchWait Wt)
 {
+    // the slots of this batch are free once the consumer has released frame (last - slots): wait here, not in a kernel of its own
+    if (need_consumed > 0u && threadIdx.x == 0) wait_at_least(&flags->consumed, need_consumed, &flags->error);
+    wait_for_trace(Wt);
     const size_t n = (size_t)local_rows * width;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int lrow = (int)(i / (size_t)width), x = (int)(i - (size_t)lrow * width);
+    const size_t n32 = (n + 31) & ~(size_t)31;                  // whole warps stay in the loop together (the shuffles below)
+    const bool quads = rgb && (width & 3) == 0;                 // then lanes 4q..4q+3 are one aligned quad of one row
+    const unsigned lane = threadIdx.x & 31u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (size_t)gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        const size_t ii = live ? i : n - 1;
+        const int lrow = (int)(ii / (size_t)width), x = (int)(ii - (size_t)lrow * width);
         const int ls = lrow / stripe_rows;
         const int y = (ls * world + rank) * stripe_rows + (lrow - ls * stripe_rows);
+        const size_t g = (size_t)y * width + x;                 // this pixel in the full image
         V3 acc = mk(0.0f, 0.0f, 0.0f);
         if (B.frame0 > 0) {
-            const float4 l = image[i];
+            const float4 l = image[ii];
             acc = mk(l.x, l.y, l.z);
         }
-        for (int j = 0; j < B.frames; ++j) {
-            const float4 e = estimates[(size_t)j * B.stride + i];
-            acc = mix(acc, mk(e.x, e.y, e.z), B.blend[j]);
-            if (y < height) X.full[j][(size_t)y * width + x] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        const bool whole = __all_sync(0xffffffffu, live);
+        for (int j0 = 0; j0 < B.frames; j0 += kBlendChunk) {
+            float4 e[kBlendChunk];
+#pragma unroll
+            for (int j = 0; j < kBlendChunk; ++j)
+                if (j0 + j < B.frames) e[j] = estimates[(size_t)(j0 + j) * B.stride + ii];
+#pragma unroll
+            for (int j = 0; j < kBlendChunk; ++j)
+                if (j0 + j < B.frames) {
+                    acc = mix(acc, mk(e[j].x, e[j].y, e[j].z), B.blend[j0 + j]);
+                    void* full = X.full[j0 + j];
+                    if (!rgb) {
+                        if (live && y < height) static_cast<float4*>(full)[g] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+                    } else if (quads && whole) {
+                        const float nr = __shfl_down_sync(0xffffffffu, acc.x, 1), ng = __shfl_down_sync(0xffffffffu, acc.y, 1),
+                                    nb = __shfl_down_sync(0xffffffffu, acc.z, 1);
+                        const unsigned p = lane & 3u;
+                        const float4 piece = p == 0u ? make_float4(acc.x, acc.y, acc.z, nr) : (p == 1u ? make_float4(acc.y, acc.z, nr, ng) : make_float4(acc.z, nr, ng, nb));
+                        if (p < 3u && y < height) reinterpret_cast<float4*>(static_cast<float*>(full) + (g - p) * 3)[p] = piece;
+                    } else if (live && y < height) {
+                        float* dst = static_cast<float*>(full) + g * 3;
+                        dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z;
+                    }
+                }
         }
-        image[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
-        __threadfence_system();
+        if (live) image[ii] = make_float4(acc.x, acc.y, acc.z, 1.0f);
     }
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         if (atomicAdd(block_count, 1u) == gridDim.x - 1) {       // last block of this rank: everything above is visible system-wide

@@ -99,7 +99,7 @@ class TiledPathTracer:
     """
 
     def __init__(self, tracer, rank: int, world: int, stripe_rows: int = DEFAULT_STRIPE_ROWS, device=None, fused: bool = False,
-                 slots: int = 2):
+                 slots: int = 2, rgb: bool = False):
         import torch
 
         self.tracer, self.rank, self.world, self.stripe_rows = tracer, rank, world, stripe_rows
@@ -124,6 +124,7 @@ class TiledPathTracer:
         self._pending = None       # (buffer index, work)
         self._last_full = None
         self._slot_tensors = {}
+        self.channels = 3 if (rgb and self.fused) else 4       # fused exchange: RGB32F slots ship 12 instead of 16 bytes per pixel
         if self.fused:
             self._init_fused(slots)
 
@@ -140,7 +141,7 @@ class TiledPathTracer:
 
         L, ctx = self.tracer._L, self.tracer._ctx
         self.slots = int(slots)
-        _lib.check(L.ptb_exchange_init(ctx, slots))
+        _lib.check(L.ptb_exchange_init_format(ctx, slots, 1 if self.channels == 3 else 0))
         handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
         if self.rank == 0:
             raw = C.create_string_buffer(64)
@@ -170,7 +171,7 @@ class TiledPathTracer:
         _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
         full = self._slot_tensors.get(ptr.value)
         if full is None:           # wrapping a raw pointer costs tens of microseconds: once per slot, not once per frame
-            full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+            full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, self.channels)), device=self.device)
             self._slot_tensors[ptr.value] = full
         if consumer is not None:
             consumer(full)
@@ -205,7 +206,7 @@ class TiledPathTracer:
                 _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
                 full = self._slot_tensors.get(ptr.value)
                 if full is None:
-                    full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, 4)), device=self.device)
+                    full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, self.channels)), device=self.device)
                     self._slot_tensors[ptr.value] = full
                 if consumer is not None:
                     consumer(full)

@@ -44,16 +44,20 @@ if True:
     single.Dispose()
 
 ok = True
-for fused in (False, True):
+for fused, rgb, batched in ((False, False, False), (True, False, False), (True, True, True)):
     pt = make()
-    tp = D.TiledPathTracer(pt, rank, world, 8, device=dev, fused=fused, slots=int(os.environ.get('SLOTS', '2')))
-    snap = torch.empty((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+    tp = D.TiledPathTracer(pt, rank, world, 8, device=dev, fused=fused, slots=int(os.environ.get('SLOTS', '2')), rgb=rgb)
+    snap = torch.empty((H, W, tp.channels), dtype=torch.float32, device=dev) if rank == 0 else None
     full = None
-    for f in range(FRAMES):
-        if fused:      # the slot is only ours between acquire and release: copy it out inside the consumer callback
-            tp.step_fused(consumer=(lambda t: snap.copy_(t)) if rank == 0 else None)
-        else:
-            tp.step()
+    if batched:        # frames traced by batched launches (slot ring = 2: chunks of two), every frame delivered in RGB32F
+        pt.SetBatch(4)
+        tp.step_batch(FRAMES, consumer=(lambda t: snap.copy_(t)) if rank == 0 else None)
+    else:
+        for f in range(FRAMES):
+            if fused:      # the slot is only ours between acquire and release: copy it out inside the consumer callback
+                tp.step_fused(consumer=(lambda t: snap.copy_(t)) if rank == 0 else None)
+            else:
+                tp.step()
     full = snap if fused else tp.flush()
     torch.cuda.synchronize(dev)
     mine = D.local_rows_of(rank, world, 8, H)
@@ -63,11 +67,15 @@ for fused in (False, True):
         tp.exchange_ok()
     if rank == 0:
         got = full.cpu().numpy()
+        if got.shape[2] == 3:          # RGB32F slots: the colour floats, bit for bit
+            got = np.concatenate([got, np.ones_like(got[..., :1])], axis=2)
         same = bool((got.view(np.uint32) == ref.view(np.uint32)).all())
         ok &= same
         if not same:
             time.sleep(1.0)
             got2 = full.cpu().numpy()
+            if got2.shape[2] == 3:
+                got2 = np.concatenate([got2, np.ones_like(got2[..., :1])], axis=2)
             print('   after 1 s the image is correct:', bool((got2.view(np.uint32) == ref.view(np.uint32)).all()), flush=True)
             bad = (got.view(np.uint32) != ref.view(np.uint32)).any(axis=2)
             rows = np.nonzero(bad.any(axis=1))[0]
@@ -76,7 +84,7 @@ for fused in (False, True):
             yy, xx = np.argwhere(bad)[len(np.argwhere(bad)) // 2]
             print('   sample bad pixel', int(yy), int(xx), 'got', got[yy, xx], 'refs per frame count:', [rf[yy, xx, 0] for rf in refs], flush=True)
             print('   mismatching rows:', rows[:24].tolist(), '... count', rows.size, 'of', H, '; bad px', int(bad.sum()), '; got', got[rows[0], 0], 'ref', ref[rows[0], 0], flush=True)
-        print(f"[{'fused' if fused else 'nccl '}] {world} GPUs {W}x{H}: exchanged image == single-GPU render: {same}", flush=True)
+        print(f"[{'fused' if fused else 'nccl '}{' rgb batched' if batched else ''}] {world} GPUs {W}x{H}: exchanged image == single-GPU render: {same}", flush=True)
     dist.barrier()
     # timing: K pipelined steps
     for _ in range(10):
@@ -85,8 +93,11 @@ for fused in (False, True):
     K = 300
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        tp.step()
+    if batched:
+        tp.step_batch(K)
+    else:
+        for _ in range(K):
+            tp.step()
     tp.flush()
     e1.record()
     dist.barrier(); torch.cuda.synchronize(dev)
