@@ -258,6 +258,12 @@ def run_ours(args, rank, world, local_rank):
     rows_local = pt.Result.shape[0]
     samples_per_step = W * H * SPP
 
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if os.environ.get("PTB_BENCH_LOG"):
+            print(f"[bench rank {rank} +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     def local_image():
         ptr, _ = pt.ResultDevicePtr()
         return torch.as_tensor(D._DeviceBuffer(ptr, (rows_local, W, 4)), device=dev)
@@ -292,6 +298,7 @@ def run_ours(args, rank, world, local_rank):
         n_gate = cfg["gate_frames"]
         imgs = {}
         for prec in (ptb200.PRECISION_EXACT, ptb200.PRECISION_FAST):
+            log(f"gate: precision {prec}, {n_gate} frames")
             pt.SetPrecision(prec)
             pt.ResetRenderer()
             run_steps(n_gate)
@@ -354,7 +361,9 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(kern, op=dist.ReduceOp.MAX)
         return ms, launches, clk, float(kern[0].item()), float(kern[1].item()), kt["frames"] // max(1, kt["launches"])
 
+    log("timed region (headline precision)")
     ms_total, launches, clocks, kern_ms, kern_launch_ms, frames_per_launch = measure(headline, args.steps, True)
+    log(f"timed region done: {ms_total / args.steps:.4f} ms/step")
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "note": "not a bench value"}), flush=True)
@@ -434,9 +443,11 @@ def run_ours(args, rank, world, local_rank):
             side.synchronize()
             torch.cuda.current_stream(dev).synchronize()
 
+    log("e2e warm-up")
     for _ in range(3):
         step_e2e()
     finish_e2e()
+    log("e2e timed")
     e2e_steps = max(5, min(args.steps, 200))
     barrier()
     t0 = time.perf_counter()
@@ -489,6 +500,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ------------------------------------------------------------------ N > 1: the exchanged frame against ONE GPU rendering alone
     exchange_check = None
+    log("e2e done; exchange check")
     if tiled is not None:
         n_chk = 8
         pt.Synchronize()
@@ -522,6 +534,7 @@ def run_ours(args, rank, world, local_rank):
             solo.Dispose()
         barrier()
 
+    log("exchange check done")
     value = samples_per_step * args.steps / (ms_total * 1e-3) / 1e6
     peak, peak_src = measured_peaks()
     algo_bytes = rows_local * W * 32 * frames_per_launch   # per pixel and frame: 16 B load of the previous mean + 16 B store

@@ -669,6 +669,9 @@ int launch_frame(ptb_ctx* c)
             if (c->xch_on) {
                 const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
                 const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
+                // a one-thread kernel waits for the slot: this blend grid is as large as the image, and a grid that large spinning
+                // on `consumed` would hold every CTA slot the consumer's own kernels (read-back snapshot, ...) need before it can release
+                if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
                 BatchBlend B = {};
                 B.frame0 = c->frame; B.frames = 1; B.stride = 0ull; B.blend[0] = P.blend;
                 BatchScatter X = {};
@@ -677,7 +680,7 @@ int launch_frame(ptb_ctx* c)
                 const BatchWait none = {nullptr, 0u, nullptr};      // ordered by the stream event above
                 blend_scatter_batch_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 4), 256, 0, bs>>>(
                     c->d_image, c->d_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->xch_rgb ? 1 : 0, B, X,
-                    reinterpret_cast<ExchangeFlags*>(c->xch_block), need, c->d_xch_blocks, none);
+                    reinterpret_cast<ExchangeFlags*>(c->xch_block), 0u, c->d_xch_blocks, none);
                 c->xch_seq++;
             } else {
                 blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_scratch[s], n, c->frame, P.blend);
