@@ -51,7 +51,9 @@ CONFIGS = {
 }
 STRIPE_ROWS = 8
 BATCH = max(1, min(16, int(os.environ.get("PTB_BATCH", "16"))))
-EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "32"))      # full-image buffers on rank 0 (>= the batch: every frame of a batch has its own)
+
+ROTATE_ROOTS = os.environ.get("PTB_ROOTS", "rotate") != "rank0"   # frame q is assembled on rank q % N (one gather per frame; no single GPU's NVLink ingress carries them all)
+EXCHANGE_SLOTS = int(os.environ.get("PTB_SLOTS", "8" if ROTATE_ROOTS else "32"))   # full-image buffers per root (>= 2 batches of frames in flight over all roots)
 MSE_TOLERANCE = 1e-6                                         # north star: per-channel MSE at matched seed
 
 
@@ -243,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
         if fused:
             # CUDA IPC needs peer access between the ranks' devices; if any rank cannot set it up, everybody uses NCCL
             try:
-                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True, slots=EXCHANGE_SLOTS, rgb=True)
+                tiled = D.TiledPathTracer(pt, rank, world, STRIPE_ROWS, device=dev, fused=True, slots=EXCHANGE_SLOTS, rgb=True, rotate=ROTATE_ROOTS)
                 ok = torch.ones(1, device=dev)
             except Exception as exc:      # noqa: BLE001
                 print(f"rank {rank}: fused exchange unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr, flush=True)
@@ -387,10 +389,11 @@ def run_ours(args, rank, world, local_rank):
                 print(f"shared host frame unavailable ({exc}); e2e falls back to rank 0's copy of the assembled image", file=sys.stderr, flush=True)
             shared = None
     rgb_e2e = world == 1 or shared is not None
-    host_bufs = [torch.empty((H if rank == 0 else 1, W, 3 if tiled is None else tiled.channels), dtype=torch.float32).pin_memory() for _ in range(2)]
+    every_rank_roots = tiled is not None and fused and tiled.rotate
+    host_bufs = [torch.empty((H if (rank == 0 or (every_rank_roots and shared is None)) else 1, W, 3 if tiled is None else tiled.channels), dtype=torch.float32).pin_memory() for _ in range(2)]
     side = torch.cuda.Stream(device=dev)
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
-    snap = [torch.empty((H, W, tiled.channels), dtype=torch.float32, device=dev) for _ in range(2)] if (rank == 0 and world > 1 and shared is None) else None
+    snap = [torch.empty((H, W, tiled.channels), dtype=torch.float32, device=dev) for _ in range(2)] if ((rank == 0 or every_rank_roots) and world > 1 and shared is None) else None
     state = {"i": 0}
 
     def step_e2e():
@@ -418,7 +421,7 @@ def run_ours(args, rank, world, local_rank):
                 with torch.cuda.stream(side):
                     host_bufs[k].copy_(snap[k], non_blocking=True)
                     copy_done[k].record(side)
-            tiled.step_fused(consumer=consume if rank == 0 else None)
+            tiled.step_fused(consumer=consume if snap is not None else None)
         else:
             full = tiled.step()
             if rank == 0 and full is not None:
@@ -511,12 +514,18 @@ def run_ours(args, rank, world, local_rank):
         def grab(full):
             keep["img"] = full            # the slot stays valid: nothing is rendered after these frames
         if fused:
-            tiled.step_batch(n_chk, consumer=grab if rank == 0 else None)
+            tiled.step_batch(n_chk, consumer=grab)
+            root = tiled.last_root()      # the rank the last frame was assembled on
         else:
             for _ in range(n_chk):
                 tiled.step()
             keep["img"] = tiled.flush()
+            root = 0
         barrier()
+        got = torch.empty((H, W, tiled.channels), dtype=torch.float32, device=dev)
+        if rank == root:
+            got.copy_(keep["img"])
+        dist.broadcast(got, src=root)     # to rank 0 for the comparison (outside every timed region)
         if rank == 0:
             solo = ptb200.PathTracer(None, W, H, RAY_DEPTH, SPP, FOCAL, APERTURE, max_spheres=scene.max_spheres, max_cuboids=scene.max_cuboids, device=local_rank)
             solo.SetPrecision(headline)
@@ -524,10 +533,9 @@ def run_ours(args, rank, world, local_rank):
             solo.Render(n_chk); solo.Synchronize()
             ptr, _ = solo.ResultDevicePtr()
             want = torch.as_tensor(D._DeviceBuffer(ptr, (H, W, 4)), device=dev)
-            got = keep["img"]
             want = want[..., :got.shape[-1]]         # RGB32F slots carry the three colour floats; alpha is the constant 1.0
             same = bool((got.view(torch.int32) == want.contiguous().view(torch.int32)).all().item())
-            exchange_check = {"exchange_equals_single_gpu": same, "frames": n_chk,
+            exchange_check = {"exchange_equals_single_gpu": same, "frames": n_chk, "assembled_on_rank": root,
                               "max_abs_diff": float((got - want).abs().max().item()),
                               "note": f"{n_chk} frames from a reset through the {world}-GPU exchange vs the same frames rendered by rank 0's GPU alone (untiled), compared on the device"}
             del want
@@ -549,7 +557,7 @@ def run_ours(args, rank, world, local_rank):
                    "precision": (f"{prec_name}: " + ("MUFU rcp/rsq/sin/cos/ex2 + FMA contraction (ptb_set_precision), within the north star's per-channel MSE < 1e-6 of the exact build on this workload (see precision_gate)"
                                                      if prec_name == "fast" else "the evaluation model of DESIGN.md §2, bit-identical to the CPU oracle and the compiled reference shaders")),
                    "l2": f"no flush kernel in the timed region: the frame estimates rotate through 3 x {BATCH} scratch images per rank ({3 * BATCH * rows_local * W * 16 / 1e6:.0f} MB on this rank, L2 is 126 MB); inputs larger than L2",
-                   "partition": (f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + (f"exchange fused into the batch blend kernel: peer stores into rank 0's per-frame slots over NVLink (CUDA IPC, {EXCHANGE_SLOTS} RGB32F slots: colour floats bit for bit, the constant alpha is not shipped), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render")) if world > 1 else "single GPU, no collective",
+                   "partition": (f"interleaved {STRIPE_ROWS}-row stripes over {world} GPU(s); " + (f"exchange fused into the batch blend kernel: peer stores into the frame's root over NVLink (CUDA IPC; " + ("rotating roots: frame q is assembled on rank q % N" if ROTATE_ROOTS else "every frame on rank 0") + f"; {EXCHANGE_SLOTS} RGB32F slots per root: colour floats bit for bit, the constant alpha is not shipped), no NCCL on the data path" if fused else "one NCCL gather to rank 0 per frame + de-interleave, overlapped with the next frame's render")) if world > 1 else "single GPU, no collective",
                    "kernel": f"persistent megakernel, {BATCH} consecutive frames per launch (ptb_set_batch) + one blend kernel per batch, {frames_in_flight} batches in flight; ray-classification table for scenes of <= 64 primitives, shared-memory BVH above 96"},
         "precision_gate": gate,
         "exact": exact,

@@ -145,6 +145,16 @@ int ptb_exchange_init(ptb_ctx* ctx, int slots);
  * colour floats, bit for bit; the constant alpha 1.0 (compute.glsl:129) is not shipped, which takes a quarter off rank 0's
  * NVLink ingress, the resource that bounds the exchange once the frame is split over many GPUs. */
 int ptb_exchange_init_format(ptb_ctx* ctx, int slots, int format);
+/* Rotating roots (rotate != 0): frame number q of the exchange is assembled on rank q % world instead of always on rank 0 —
+ * one gather per frame as before, but no single GPU's NVLink ingress carries every frame (at 8 GPUs rank 0 would take in 7/8
+ * of each frame: 22 MB per 1080p frame, the bound of the whole exchange once a frame takes ~25 us).  Every rank then owns a
+ * block of `slots` images and maps all the others': ptb_exchange_init_roots on every rank, ptb_exchange_handle on every rank,
+ * all-gather the handles, ptb_exchange_attach_peer(rank, handle) for each; every rank acquires / releases the frames it is
+ * the root of (ptb_exchange_root tells which rank holds a given frame). */
+int ptb_exchange_init_roots(ptb_ctx* ctx, int slots, int format, int rotate);
+int ptb_exchange_attach_peer(ptb_ctx* ctx, int peer_rank, const void* handle64);
+int ptb_exchange_root(ptb_ctx* ctx, long long frame_seq);   /* frame_seq < 0: the last frame rendered */
+int ptb_exchange_pending(ptb_ctx* ctx);                      /* frames rendered that this rank is the root of and has not acquired yet */
 int ptb_exchange_handle(ptb_ctx* ctx, void* handle64);
 int ptb_exchange_attach(ptb_ctx* ctx, const void* handle64);
 int ptb_exchange_acquire(ptb_ctx* ctx, void** full_device);

@@ -57,6 +57,10 @@ SIGNATURES = {
     "ptb_deinterleave_device": (C.c_int, [_P, C.c_void_p, C.c_void_p]),
     "ptb_exchange_init": (C.c_int, [_P, C.c_int]),
     "ptb_exchange_init_format": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ptb_exchange_init_roots": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "ptb_exchange_attach_peer": (C.c_int, [_P, C.c_int, C.c_void_p]),
+    "ptb_exchange_root": (C.c_int, [_P, C.c_longlong]),
+    "ptb_exchange_pending": (C.c_int, [_P]),
     "ptb_exchange_handle": (C.c_int, [_P, C.c_void_p]),
     "ptb_exchange_attach": (C.c_int, [_P, C.c_void_p]),
     "ptb_exchange_acquire": (C.c_int, [_P, C.POINTER(C.c_void_p)]),

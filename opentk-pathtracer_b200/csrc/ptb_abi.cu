@@ -115,9 +115,13 @@ struct ptb_ctx {
     size_t scratch_bytes = 0;
     unsigned long long launch_seq = 0;
     // fused multi-GPU exchange (ptb_exchange_*): rank 0 owns [flags | slots x full image]; other ranks map it through CUDA IPC
+    // Roots: 1 = every frame is assembled on rank 0 (xch_block = rank 0's block, mapped by the others); world = rotating roots,
+    // frame q is assembled on rank q % world (every rank owns a block and maps all the others': xch_peer[]).
     bool xch_on = false, xch_mapped = false, xch_rgb = false;
-    int xch_slots = 0;
-    unsigned char* xch_block = nullptr;
+    int xch_slots = 0, xch_roots = 1;
+    unsigned char* xch_block = nullptr;          // this rank's own block (roots == world, or rank 0), or rank 0's mapping (roots == 1)
+    unsigned char* xch_peer[16] = {};            // rotating roots: the block of every rank (own block for self)
+    bool xch_peer_mapped[16] = {};
     size_t xch_image_bytes = 0;
     unsigned long long xch_seq = 0, xch_acquired = 0, xch_released = 0;
     unsigned int* d_xch_blocks = nullptr;
@@ -578,6 +582,26 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     { const int n = c->n_spheres + c->n_cuboids; P.rct_valid = n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
 }
 
+// Where frame number q of the exchange goes: the root's block, the slot in it and how many frames that root's consumer must
+// have released before the slot may be written again.
+struct XchTarget { unsigned char* block; int slot; unsigned need; };
+XchTarget xch_target(const ptb_ctx* c, unsigned long long q)
+{
+    const bool rot = c->xch_roots > 1;
+    const unsigned long long li = rot ? q / (unsigned long long)c->world : q;          // index among the root's own frames
+    XchTarget t;
+    t.block = rot ? c->xch_peer[q % (unsigned long long)c->world] : c->xch_block;
+    t.slot = (int)(li % (unsigned long long)c->xch_slots);
+    t.need = li >= (unsigned long long)c->xch_slots ? (unsigned)(li - c->xch_slots + 1) : 0u;
+    return t;
+}
+// frames with number < seq that this rank is the root of
+unsigned long long xch_own_frames(const ptb_ctx* c, unsigned long long seq)
+{
+    if (c->xch_roots <= 1) return c->rank == 0 ? seq : 0ull;
+    return (seq + (unsigned long long)(c->world - 1 - c->rank)) / (unsigned long long)c->world;
+}
+
 int fold_of(const ptb_ctx* c) { return (c->n_nodes > 0 || c->n_unbounded > 0) ? 1 : (c->rct_on ? 2 : 0); }
 
 template <int kFold, class F>
@@ -667,20 +691,20 @@ int launch_frame(ptb_ctx* c)
             CU(cudaStreamWaitEvent(bs, c->ev_trace_done[s], 0));
             const size_t n = (size_t)c->local_rows * c->width;
             if (c->xch_on) {
-                const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
-                const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
+                const XchTarget tg = xch_target(c, c->xch_seq);
+                ExchangeFlags* fl = reinterpret_cast<ExchangeFlags*>(tg.block);
                 // a one-thread kernel waits for the slot: this blend grid is as large as the image, and a grid that large spinning
                 // on `consumed` would hold every CTA slot the consumer's own kernels (read-back snapshot, ...) need before it can release
-                if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
+                if (tg.need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(fl, tg.need); c->launches++; }
                 BatchBlend B = {};
                 B.frame0 = c->frame; B.frames = 1; B.stride = 0ull; B.blend[0] = P.blend;
                 BatchScatter X = {};
-                X.slot[0] = slot;
-                X.full[0] = c->xch_block + 4096 + (size_t)slot * c->xch_image_bytes;
+                X.slot[0] = tg.slot; X.flags[0] = fl; X.need[0] = 0u;
+                X.full[0] = tg.block + 4096 + (size_t)tg.slot * c->xch_image_bytes;
                 const BatchWait none = {nullptr, 0u, nullptr};      // ordered by the stream event above
                 blend_scatter_batch_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 4), 256, 0, bs>>>(
                     c->d_image, c->d_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->xch_rgb ? 1 : 0, B, X,
-                    reinterpret_cast<ExchangeFlags*>(c->xch_block), 0u, c->d_xch_blocks, none);
+                    c->d_xch_blocks, none);
                 c->xch_seq++;
             } else {
                 blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, bs>>>(c->d_image, c->d_scratch[s], n, c->frame, P.blend);
@@ -696,10 +720,10 @@ int launch_frame(ptb_ctx* c)
         // no rows on this rank (more ranks than stripes): it still has to arrive at the frame's slot, or rank 0 would wait for ever
         { const int rc = ensure_pipeline(c); if (rc != PTB_OK) return rc; }
         cudaStream_t bs = c->blend_stream;
-        const int slot = (int)(c->xch_seq % (unsigned long long)c->xch_slots);
-        const unsigned need = c->xch_seq >= (unsigned long long)c->xch_slots ? (unsigned)(c->xch_seq - c->xch_slots + 1) : 0u;
-        if (need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), need); c->launches++; }
-        exchange_arrive_kernel<<<1, 1, 0, bs>>>(reinterpret_cast<ExchangeFlags*>(c->xch_block), slot);
+        const XchTarget tg = xch_target(c, c->xch_seq);
+        ExchangeFlags* fl = reinterpret_cast<ExchangeFlags*>(tg.block);
+        if (tg.need > 0u) { exchange_wait_free_kernel<<<1, 1, 0, bs>>>(fl, tg.need); c->launches++; }
+        exchange_arrive_kernel<<<1, 1, 0, bs>>>(fl, tg.slot);
         CU(cudaGetLastError());
         c->launches++;
         c->xch_seq++;
@@ -842,15 +866,14 @@ int launch_batch(ptb_ctx* c, int frames)
     if (c->xch_on) {
         BatchScatter X = {};
         for (int j = 0; j < frames; ++j) {
-            X.slot[j] = (int)((c->xch_seq + j) % (unsigned long long)c->xch_slots);
-            X.full[j] = c->xch_block + 4096 + (size_t)X.slot[j] * c->xch_image_bytes;
+            const XchTarget tg = xch_target(c, c->xch_seq + j);
+            X.slot[j] = tg.slot; X.need[j] = tg.need;
+            X.flags[j] = reinterpret_cast<ExchangeFlags*>(tg.block);
+            X.full[j] = tg.block + 4096 + (size_t)tg.slot * c->xch_image_bytes;
         }
-        // the batch's last frame needs the release of frame (seq_last - slots); `consumed` is monotonic, so that covers the others
-        const unsigned long long last = c->xch_seq + frames - 1;
-        const unsigned need = last >= (unsigned long long)c->xch_slots ? (unsigned)(last - c->xch_slots + 1) : 0u;
         blend_scatter_batch_kernel<<<blend_grid, 256, 0, bs>>>(
             c->d_image, c->d_batch_scratch[s], c->width, c->local_rows, c->height, c->rank, c->world, c->stripe_rows, c->xch_rgb ? 1 : 0, B, X,
-            reinterpret_cast<ExchangeFlags*>(c->xch_block), need, c->d_xch_blocks, Wt);
+            c->d_xch_blocks, Wt);
         c->xch_seq += frames;
     } else {
         blend_batch_kernel<<<blend_grid, 256, 0, bs>>>(c->d_image, c->d_batch_scratch[s], n, B, Wt);
@@ -1098,17 +1121,17 @@ int ptb_render_frames(ptb_ctx* c, int n)
     // fused exchange: the blend of frame k waits until frame k - slots was released, and rank 0's releases can only be enqueued
     // after this call has returned (its stream waits for every blend): more un-released frames than slots would wait on itself
     if (c->xch_on && c->local_rows > 0) {
-        const unsigned long long in_flight = c->rank == 0 ? c->xch_seq - c->xch_released : 0ull;
-        if (in_flight + (unsigned long long)n > (unsigned long long)c->xch_slots)
-            return fail(PTB_E_STATE, "fused exchange: %d frame(s) requested with %llu not yet released and %d slot(s); acquire/release between calls "
-                                     "(TiledPathTracer.render does) or raise ptb_exchange_init's slot count", n, in_flight, c->xch_slots);
+        const unsigned long long mine = xch_own_frames(c, c->xch_seq + (unsigned long long)n) - c->xch_released;     // frames this rank would be holding
+        if (mine > (unsigned long long)c->xch_slots)
+            return fail(PTB_E_STATE, "fused exchange: %d frame(s) requested would leave %llu un-released frames on this root with %d slot(s); acquire/release "
+                                     "between calls (TiledPathTracer.render does) or raise the slot count", n, mine, c->xch_slots);
     }
     CU(cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < n;) {
         // fused exchange: blend j of a batch waits for the release of frame (seq_j - slots), and rank 0 enqueues this batch's
         // acquires / releases only after the whole batch (its stream waits for the batch's last blend) — so a batch may not be
         // longer than the slot ring, or its own later blends would wait for its own earlier releases
-        const int bmax = c->xch_on ? std::min(c->batch, c->xch_slots) : c->batch;
+        const int bmax = c->xch_on ? std::min(c->batch, c->xch_slots * c->xch_roots) : c->batch;
         const int b = batch_eligible(c) ? std::min(n - i, bmax) : 1;
         rc = b >= 2 ? launch_batch(c, b) : launch_frame(c);
         if (rc != PTB_OK) return rc;
@@ -1313,6 +1336,10 @@ static bool stream_memops()
 
 static int exchange_close(ptb_ctx* c)
 {
+    for (int r = 0; r < 16; ++r) {
+        if (c->xch_peer[r] && c->xch_peer_mapped[r]) cudaIpcCloseMemHandle(c->xch_peer[r]);
+        c->xch_peer[r] = nullptr; c->xch_peer_mapped[r] = false;
+    }
     if (c->xch_block) {
         if (c->xch_mapped) cudaIpcCloseMemHandle(c->xch_block);
         else cudaFree(c->xch_block);
@@ -1320,38 +1347,43 @@ static int exchange_close(ptb_ctx* c)
     c->xch_block = nullptr;
     c->xch_on = false;
     c->xch_mapped = false;
+    c->xch_roots = 1;
     return PTB_OK;
 }
 
-int ptb_exchange_init(ptb_ctx* c, int slots) { return ptb_exchange_init_format(c, slots, PTB_FORMAT_RGBA32F); }
-int ptb_exchange_init_format(ptb_ctx* c, int slots, int format)
+int ptb_exchange_init(ptb_ctx* c, int slots) { return ptb_exchange_init_roots(c, slots, PTB_FORMAT_RGBA32F, 0); }
+int ptb_exchange_init_format(ptb_ctx* c, int slots, int format) { return ptb_exchange_init_roots(c, slots, format, 0); }
+int ptb_exchange_init_roots(ptb_ctx* c, int slots, int format, int rotate)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     if (format != PTB_FORMAT_RGBA32F && format != PTB_FORMAT_RGB32F) return fail(PTB_E_INVALID, "the exchange ships RGBA32F or RGB32F, not format %d", format);
     if (slots < 1 || slots > kMaxSlots) return fail(PTB_E_INVALID, "slots %d outside [1,%d]", slots, kMaxSlots);
+    if (rotate && c->world > 16) return fail(PTB_E_INVALID, "rotating roots support up to 16 ranks");
     if (c->overlap < 2) return fail(PTB_E_STATE, "the fused exchange needs the pipelined mode (ptb_set_overlap >= 2)");
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     exchange_close(c);
     c->xch_slots = slots;
+    c->xch_roots = (rotate && c->world > 1) ? c->world : 1;
     c->xch_rgb = format == PTB_FORMAT_RGB32F;
     c->xch_image_bytes = (((size_t)c->width * c->height * (c->xch_rgb ? 12 : 16)) + 255) & ~(size_t)255;
     c->xch_seq = c->xch_acquired = c->xch_released = 0;
     if (!c->d_xch_blocks) { CU(cudaMalloc(&c->d_xch_blocks, sizeof(unsigned int))); }
     CU(cudaMemset(c->d_xch_blocks, 0, sizeof(unsigned int)));
     CU(cudaDeviceSynchronize());
-    if (c->rank == 0) {
+    if (c->rank == 0 || c->xch_roots > 1) {
         const size_t bytes = 4096 + (size_t)slots * c->xch_image_bytes;
         CU(cudaMalloc(&c->xch_block, bytes));
         CU(cudaMemset(c->xch_block, 0, bytes));
         CU(cudaDeviceSynchronize());      // cudaMemset on device memory may return before it ran; peers must never see it land late
-        c->xch_on = true;
+        if (c->xch_roots > 1) c->xch_peer[c->rank] = c->xch_block;
+        c->xch_on = c->xch_roots == 1;    // rotating roots: on once every peer's block is attached
     }
     return PTB_OK;
 }
 int ptb_exchange_handle(ptb_ctx* c, void* handle64)
 {
     if (!c || !handle64) return fail(PTB_E_INVALID, "null argument");
-    if (c->rank != 0 || !c->xch_block) return fail(PTB_E_STATE, "only rank 0 exports the exchange block, after ptb_exchange_init");
+    if (!c->xch_block || c->xch_mapped) return fail(PTB_E_STATE, "only a root exports its exchange block (rank 0, or every rank with rotating roots), after ptb_exchange_init");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, c->xch_block));
@@ -1361,6 +1393,7 @@ int ptb_exchange_handle(ptb_ctx* c, void* handle64)
 int ptb_exchange_attach(ptb_ctx* c, const void* handle64)
 {
     if (!c || !handle64) return fail(PTB_E_INVALID, "null argument");
+    if (c->xch_roots > 1) return fail(PTB_E_STATE, "rotating roots: attach every peer with ptb_exchange_attach_peer");
     if (c->rank == 0) return fail(PTB_E_STATE, "rank 0 owns the exchange block");
     if (c->xch_slots < 1) return fail(PTB_E_STATE, "call ptb_exchange_init first");
     cudaIpcMemHandle_t h;
@@ -1372,11 +1405,41 @@ int ptb_exchange_attach(ptb_ctx* c, const void* handle64)
     c->xch_on = true;
     return PTB_OK;
 }
+int ptb_exchange_attach_peer(ptb_ctx* c, int peer_rank, const void* handle64)
+{
+    if (!c || !handle64) return fail(PTB_E_INVALID, "null argument");
+    if (c->xch_roots <= 1) return fail(PTB_E_STATE, "ptb_exchange_attach_peer belongs to rotating roots (ptb_exchange_init_roots(..., 1))");
+    if (peer_rank < 0 || peer_rank >= c->world) return fail(PTB_E_INVALID, "peer rank %d outside [0,%d)", peer_rank, c->world);
+    if (peer_rank != c->rank && !c->xch_peer[peer_rank]) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->xch_peer[peer_rank] = (unsigned char*)p;
+        c->xch_peer_mapped[peer_rank] = true;
+    }
+    bool all = true;
+    for (int r = 0; r < c->world; ++r) all = all && c->xch_peer[r] != nullptr;
+    c->xch_on = all;
+    return PTB_OK;
+}
+int ptb_exchange_root(ptb_ctx* c, long long frame_seq)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    const unsigned long long q = frame_seq < 0 ? (c->xch_seq ? c->xch_seq - 1 : 0ull) : (unsigned long long)frame_seq;
+    return c->xch_roots > 1 ? (int)(q % (unsigned long long)c->world) : 0;
+}
+int ptb_exchange_pending(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (!c->xch_on || !c->xch_block || c->xch_mapped) return 0;
+    return (int)(xch_own_frames(c, c->xch_seq) - c->xch_acquired);
+}
 int ptb_exchange_acquire(ptb_ctx* c, void** full_device)
 {
     if (!c || !full_device) return fail(PTB_E_INVALID, "null argument");
-    if (!c->xch_on || c->rank != 0) return fail(PTB_E_STATE, "acquire is rank 0's side of an initialised exchange");
-    if (c->xch_acquired >= c->xch_seq) return fail(PTB_E_STATE, "no rendered frame left to acquire");
+    if (!c->xch_on || !c->xch_block || c->xch_mapped) return fail(PTB_E_STATE, "acquire is a root's side of an initialised exchange");
+    if (c->xch_acquired >= xch_own_frames(c, c->xch_seq)) return fail(PTB_E_STATE, "no rendered frame left to acquire on this root");
     const int slot = (int)(c->xch_acquired % (unsigned long long)c->xch_slots);
     const unsigned target = (unsigned)((c->xch_acquired / (unsigned long long)c->xch_slots + 1) * (unsigned long long)c->world);
     ExchangeFlags* fl = reinterpret_cast<ExchangeFlags*>(c->xch_block);
@@ -1394,7 +1457,7 @@ int ptb_exchange_acquire(ptb_ctx* c, void** full_device)
 int ptb_exchange_release(ptb_ctx* c)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
-    if (!c->xch_on || c->rank != 0) return fail(PTB_E_STATE, "release is rank 0's side of an initialised exchange");
+    if (!c->xch_on || !c->xch_block || c->xch_mapped) return fail(PTB_E_STATE, "release is a root's side of an initialised exchange");
     if (c->xch_released >= c->xch_acquired) return fail(PTB_E_STATE, "nothing acquired");
     c->xch_released++;
     ExchangeFlags* fl = reinterpret_cast<ExchangeFlags*>(c->xch_block);
@@ -1411,7 +1474,7 @@ int ptb_exchange_status(ptb_ctx* c)
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     if (!c->xch_on) return PTB_OK;
     unsigned err = 0;
-    CU(cudaMemcpy(&err, c->xch_block + offsetof(ExchangeFlags, error), sizeof err, cudaMemcpyDeviceToHost));
+    if (c->xch_block) CU(cudaMemcpy(&err, c->xch_block + offsetof(ExchangeFlags, error), sizeof err, cudaMemcpyDeviceToHost));
     return err ? fail(PTB_E_STATE, "a fused-exchange wait timed out (a rank stalled or the consumer never released a slot)") : PTB_OK;
 }
 

@@ -1338,17 +1338,21 @@ __device__ __forceinline__ void wait_at_least(const unsigned* flag, unsigned tar
 // exchange, so it is not shipped.  Four neighbouring lanes then pass their colours one lane down and three of them store a
 // 128-bit piece of the quad's 48 bytes.  Every slot gets its own arrival from the kernel's last block.
 struct BatchScatter {
-    void* full[kMaxBatch];         // rank 0's row-major image of each frame's slot (peer mapping)
+    void* full[kMaxBatch];           // the root's row-major image of each frame's slot (peer mapping, or local on the root itself)
+    ExchangeFlags* flags[kMaxBatch]; // the flag block of each frame's root (rank 0, or rank q % world with rotating roots)
     int slot[kMaxBatch];
+    unsigned need[kMaxBatch];        // frames the root's consumer must have released before the slot may be rewritten (0: none)
 };
 __global__ void __launch_bounds__(256, 4) blend_scatter_batch_kernel(float4* __restrict__ image, const float4* __restrict__ estimates, int width,
                                                                      int local_rows, int height, int rank, int world, int stripe_rows, int rgb,
                                                                      const __grid_constant__ BatchBlend B, const __grid_constant__ BatchScatter X,
-                                                                     ExchangeFlags* flags, unsigned need_consumed, unsigned* block_count,
-                                                                     const __grid_constant__ BatchWait Wt)
+                                                                     unsigned* block_count, const __grid_constant__ BatchWait Wt)
 {
-    // the slots of this batch are free once the consumer has released frame (last - slots): wait here, not in a kernel of its own
-    if (need_consumed > 0u && threadIdx.x == 0) wait_at_least(&flags->consumed, need_consumed, &flags->error);
+    // a slot is free once its root's consumer has released the frame that used it last: wait here (small grids only — the
+    // single-frame path, whose grid is as large as the image, sends a one-thread kernel ahead instead and passes need = 0)
+    if (threadIdx.x == 0)
+        for (int j = 0; j < B.frames; ++j)
+            if (X.need[j] > 0u) wait_at_least(&X.flags[j]->consumed, X.need[j], &X.flags[j]->error);
     wait_for_trace(Wt);
     const size_t n = (size_t)local_rows * width;
     const size_t n32 = (n + 31) & ~(size_t)31;                  // whole warps stay in the loop together (the shuffles below)
@@ -1399,7 +1403,7 @@ __global__ void __launch_bounds__(256, 4) blend_scatter_batch_kernel(float4* __r
         if (atomicAdd(block_count, 1u) == gridDim.x - 1) {       // last block of this rank: everything above is visible system-wide
             *block_count = 0u;
             __threadfence_system();
-            for (int j = 0; j < B.frames; ++j) atomicAdd_system(&flags->arrived[X.slot[j]], 1u);
+            for (int j = 0; j < B.frames; ++j) atomicAdd_system(&X.flags[j]->arrived[X.slot[j]], 1u);
         }
     }
 }

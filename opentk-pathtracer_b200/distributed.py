@@ -99,7 +99,7 @@ class TiledPathTracer:
     """
 
     def __init__(self, tracer, rank: int, world: int, stripe_rows: int = DEFAULT_STRIPE_ROWS, device=None, fused: bool = False,
-                 slots: int = 2, rgb: bool = False):
+                 slots: int = 2, rgb: bool = False, rotate: bool = False):
         import torch
 
         self.tracer, self.rank, self.world, self.stripe_rows = tracer, rank, world, stripe_rows
@@ -125,13 +125,15 @@ class TiledPathTracer:
         self._last_full = None
         self._slot_tensors = {}
         self.channels = 3 if (rgb and self.fused) else 4       # fused exchange: RGB32F slots ship 12 instead of 16 bytes per pixel
+        self.rotate = bool(rotate) and self.fused             # frame q is assembled on rank q % world instead of always on rank 0
         if self.fused:
             self._init_fused(slots)
 
     # ------------------------------------------------------------------ fused exchange (peer stores instead of NCCL)
     def _init_fused(self, slots: int) -> None:
-        """ptb_exchange_*: rank 0 allocates [flags | slots x full image]; its CUDA-IPC handle (64 bytes) is broadcast with
-        torch.distributed and mapped by every other rank, whose blend kernels then store straight into rank 0's image."""
+        """ptb_exchange_*: a root allocates [flags | slots x full image]; its CUDA-IPC handle (64 bytes) travels through
+        torch.distributed and is mapped by the other ranks, whose blend kernels then store straight into the root's image.
+        One root (rank 0) by default; with `rotate` every rank is the root of every world-th frame and maps all the others."""
         import ctypes as C
 
         import torch
@@ -141,79 +143,82 @@ class TiledPathTracer:
 
         L, ctx = self.tracer._L, self.tracer._ctx
         self.slots = int(slots)
-        _lib.check(L.ptb_exchange_init_format(ctx, slots, 1 if self.channels == 3 else 0))
-        handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
-        if self.rank == 0:
+        fmt = 1 if self.channels == 3 else 0
+        if self.rotate:
+            _lib.check(L.ptb_exchange_init_roots(ctx, slots, fmt, 1))
             raw = C.create_string_buffer(64)
             _lib.check(L.ptb_exchange_handle(ctx, raw))
-            handle.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-        dist.broadcast(handle, src=0)
-        if self.rank != 0:
-            raw = C.create_string_buffer(bytes(handle.cpu().numpy().tobytes()), 64)
-            _lib.check(L.ptb_exchange_attach(ctx, raw))
+            mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).to(self.device)
+            handles = [torch.zeros(64, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+            dist.all_gather(handles, mine)
+            for r in range(self.world):
+                peer = C.create_string_buffer(bytes(handles[r].cpu().numpy().tobytes()), 64)
+                _lib.check(L.ptb_exchange_attach_peer(ctx, r, peer))
+        else:
+            _lib.check(L.ptb_exchange_init_format(ctx, slots, fmt))
+            handle = torch.zeros(64, dtype=torch.uint8, device=self.device)
+            if self.rank == 0:
+                raw = C.create_string_buffer(64)
+                _lib.check(L.ptb_exchange_handle(ctx, raw))
+                handle.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+            dist.broadcast(handle, src=0)
+            if self.rank != 0:
+                raw = C.create_string_buffer(bytes(handle.cpu().numpy().tobytes()), 64)
+                _lib.check(L.ptb_exchange_attach(ctx, raw))
         dist.barrier()
 
-    def step_fused(self, consumer=None):
-        """One frame through the fused path: every rank renders (trace + blend-and-scatter kernels); rank 0 then waits, in
-        stream order, until all ranks' pixels have landed, lets `consumer(full_image_tensor)` enqueue its work on the current
-        stream, and releases the slot.  Returns the full-image tensor on rank 0 (valid until `slots` frames later)."""
+    def _consume_pending(self, consumer=None):
+        """Acquire, hand to `consumer`, and release every rendered frame this rank is the root of.  Returns the last one."""
         import ctypes as C
 
         import torch
 
         from . import _lib
 
-        self.tracer.Render()
-        if self.rank != 0:
-            return None
         L, ctx = self.tracer._L, self.tracer._ctx
-        ptr = C.c_void_p()
-        _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
-        full = self._slot_tensors.get(ptr.value)
-        if full is None:           # wrapping a raw pointer costs tens of microseconds: once per slot, not once per frame
-            full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, self.channels)), device=self.device)
-            self._slot_tensors[ptr.value] = full
-        if consumer is not None:
-            consumer(full)
-        _lib.check(L.ptb_exchange_release(ctx))
-        self._last_full = full
+        full = None
+        for _ in range(_lib.check(L.ptb_exchange_pending(ctx))):
+            ptr = C.c_void_p()
+            _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
+            full = self._slot_tensors.get(ptr.value)
+            if full is None:           # wrapping a raw pointer costs tens of microseconds: once per slot, not once per frame
+                full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, self.channels)), device=self.device)
+                self._slot_tensors[ptr.value] = full
+            if consumer is not None:
+                consumer(full)
+            _lib.check(L.ptb_exchange_release(ctx))
+        if full is not None:
+            self._last_full = full
         return full
+
+    def last_root(self) -> int:
+        """The rank that holds the assembled image of the frame rendered last."""
+        from . import _lib
+        return _lib.check(self.tracer._L.ptb_exchange_root(self.tracer._ctx, -1)) if self.fused else 0
+
+    def step_fused(self, consumer=None):
+        """One frame through the fused path: every rank renders (trace + blend-and-scatter kernels); the frame's root then
+        waits, in stream order, until all ranks' pixels have landed, lets `consumer(full_image_tensor)` enqueue its work on the
+        current stream, and releases the slot.  Returns the full-image tensor on the root (valid until `slots` frames later)."""
+        self.tracer.Render()
+        return self._consume_pending(consumer)
 
     def step_batch(self, frames: int, consumer=None):
         """`frames` frames through the fused path with frame batching (PathTracer.SetBatch): every rank traces them with one
-        megakernel launch; the per-frame blend-and-scatter kernels still deliver every frame's pixels to rank 0 in order, so
-        rank 0 acquires / consumes / releases one slot per frame exactly as step_fused does."""
-        import ctypes as C
-
-        import torch
-
-        from . import _lib
-
+        megakernel launch per batch; one blend-and-scatter kernel per batch still delivers every frame's pixels to its root, so
+        a root acquires / consumes / releases one slot per frame exactly as step_fused does."""
         if not self.fused:
             raise RuntimeError("step_batch needs the fused exchange (per-frame NCCL gathers cannot be batched)")
-        L, ctx = self.tracer._L, self.tracer._ctx
         full = None
         left = int(frames)
+        roots = self.world if self.rotate else 1
         while left > 0:
-            # a chunk never exceeds the slot ring: its blends may only wait for releases that are already enqueued
-            chunk = min(left, self.slots)
+            # a chunk never exceeds the slot ring(s): its blends may only wait for releases that are already enqueued
+            chunk = min(left, self.slots * roots)
             left -= chunk
             self.tracer.Render(chunk)
-            if self.rank != 0:
-                continue
-            for _ in range(chunk):
-                ptr = C.c_void_p()
-                _lib.check(L.ptb_exchange_acquire(ctx, C.byref(ptr)))
-                full = self._slot_tensors.get(ptr.value)
-                if full is None:
-                    full = torch.as_tensor(_DeviceBuffer(ptr.value, (self.height, self.width, self.channels)), device=self.device)
-                    self._slot_tensors[ptr.value] = full
-                if consumer is not None:
-                    consumer(full)
-                _lib.check(L.ptb_exchange_release(ctx))
-        if self.rank != 0:
-            return None
-        self._last_full = full
+            got = self._consume_pending(consumer)
+            full = got if got is not None else full
         return full
 
     def exchange_ok(self) -> None:

@@ -30,4 +30,4 @@ def test_two_gpu_exchange_matches_single_gpu(size):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTIGPU_OK" in res.stdout, res.stdout[-3000:]
-    assert res.stdout.count("exchanged image == single-GPU render: True") == 3     # NCCL gather, fused RGBA, fused RGB batched
+    assert res.stdout.count("exchanged image == single-GPU render: True") == 4     # NCCL gather, fused RGBA, fused RGB batched, the same with rotating roots

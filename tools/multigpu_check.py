@@ -44,22 +44,24 @@ if True:
     single.Dispose()
 
 ok = True
-for fused, rgb, batched in ((False, False, False), (True, False, False), (True, True, True)):
+for fused, rgb, batched, rotate in ((False, False, False, False), (True, False, False, False), (True, True, True, False), (True, True, True, True)):
     pt = make()
-    tp = D.TiledPathTracer(pt, rank, world, 8, device=dev, fused=fused, slots=int(os.environ.get('SLOTS', '2')), rgb=rgb)
-    snap = torch.empty((H, W, tp.channels), dtype=torch.float32, device=dev) if rank == 0 else None
+    tp = D.TiledPathTracer(pt, rank, world, 8, device=dev, fused=fused, slots=int(os.environ.get('SLOTS', '2')), rgb=rgb, rotate=rotate)
+    snap = torch.empty((H, W, tp.channels), dtype=torch.float32, device=dev)
     full = None
     if batched:        # frames traced by batched launches (slot ring = 2: chunks of two), every frame delivered in RGB32F
         pt.SetBatch(4)
-        tp.step_batch(FRAMES, consumer=(lambda t: snap.copy_(t)) if rank == 0 else None)
+        tp.step_batch(FRAMES, consumer=lambda t: snap.copy_(t))       # runs on the root of each frame
     else:
         for f in range(FRAMES):
             if fused:      # the slot is only ours between acquire and release: copy it out inside the consumer callback
-                tp.step_fused(consumer=(lambda t: snap.copy_(t)) if rank == 0 else None)
+                tp.step_fused(consumer=lambda t: snap.copy_(t))
             else:
                 tp.step()
     full = snap if fused else tp.flush()
     torch.cuda.synchronize(dev)
+    if fused and tp.rotate:       # rotating roots: the last frame was assembled on rank last_root(); bring it to rank 0 for the comparison
+        dist.broadcast(snap, src=tp.last_root())
     mine = D.local_rows_of(rank, world, 8, H)
     loc = pt.Result
     print(f'rank {rank} fused={fused}: LOCAL stripes == single-GPU rows: {bool((loc.view(np.uint32) == ref[mine].view(np.uint32)).all())}', flush=True)
@@ -84,7 +86,7 @@ for fused, rgb, batched in ((False, False, False), (True, False, False), (True, 
             yy, xx = np.argwhere(bad)[len(np.argwhere(bad)) // 2]
             print('   sample bad pixel', int(yy), int(xx), 'got', got[yy, xx], 'refs per frame count:', [rf[yy, xx, 0] for rf in refs], flush=True)
             print('   mismatching rows:', rows[:24].tolist(), '... count', rows.size, 'of', H, '; bad px', int(bad.sum()), '; got', got[rows[0], 0], 'ref', ref[rows[0], 0], flush=True)
-        print(f"[{'fused' if fused else 'nccl '}{' rgb batched' if batched else ''}] {world} GPUs {W}x{H}: exchanged image == single-GPU render: {same}", flush=True)
+        print(f"[{'fused' if fused else 'nccl '}{' rgb batched' if batched else ''}{' rotating roots' if rotate else ''}] {world} GPUs {W}x{H}: exchanged image == single-GPU render: {same}", flush=True)
     dist.barrier()
     # timing: K pipelined steps
     for _ in range(10):

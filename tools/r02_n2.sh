@@ -2,9 +2,9 @@
 # 2-GPU validation: multi-GPU tests + a short bench (gate, exchange check, scatter e2e)
 mkdir -p gpurun_out
 {
-echo "== multi-GPU tests"; timeout 600 python -m pytest tests/test_multigpu_gpu.py -q -x 2>&1 | tail -n 8
+echo "== multi-GPU tests"; timeout 200 python -m pytest tests/test_multigpu_gpu.py -q -x 2>&1 | tail -n 8
 echo "== bench c2 N=2"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 160 --warmup 16 > gpurun_out/r02_bench_c2_n2_a.json 2> gpurun_out/r02_bench_c2_n2_a.err
+PTB_BENCH_LOG=1 timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 160 --warmup 16 > gpurun_out/r02_bench_c2_n2_a.json 2> gpurun_out/r02_bench_c2_n2_a.err
 tail -c 1500 gpurun_out/r02_bench_c2_n2_a.err
 python - <<'PY'
 import json

@@ -4,7 +4,7 @@ N=${1:-8}
 mkdir -p gpurun_out
 run() {  # name, args...
   local name=$1; shift
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
+  timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
       bench.py --gpus $N "$@" > gpurun_out/r02_bench_${name}_n${N}.json 2> gpurun_out/r02_bench_${name}_n${N}.err
   python - gpurun_out/r02_bench_${name}_n${N}.json <<'PY'
 import json, sys
