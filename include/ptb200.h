@@ -118,6 +118,15 @@ int ptb_tonemap_rgba8(ptb_ctx* ctx, unsigned char* rgba8);
 int ptb_tonemap_device(ptb_ctx* ctx, void* rgba8_device);
 int ptb_synchronize(ptb_ctx* ctx);
 
+/* PathTracer.Result as the GL texture it is in the reference (PathTracer.cs:86,97-99: Rgba32f TEXTURE_2D, sampled by
+ * ScreenEffect.Render, MainWindow.cs:51) through CUDA-GL interop: register the texture once (and again after SetSize
+ * re-allocates it) from the thread that owns the GL context; ptb_present_gl copies the accumulation image into the texture on
+ * the device, stream-ordered after the frames rendered so far — no host round trip.  Without a current GL context on the
+ * context's GPU registration fails with PTB_E_STATE. */
+int ptb_register_gl_texture(ptb_ctx* ctx, unsigned int gl_texture);
+int ptb_present_gl(ptb_ctx* ctx);
+int ptb_unregister_gl_texture(ptb_ctx* ctx);
+
 /* Device-side access for hosts that own CUDA memory / streams (PyTorch, CUDA-GL interop). */
 int ptb_result_device_ptr(ptb_ctx* ctx, void** device_ptr, size_t* bytes);
 int ptb_set_stream(ptb_ctx* ctx, void* cuda_stream);

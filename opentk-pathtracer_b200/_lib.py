@@ -46,6 +46,9 @@ SIGNATURES = {
     "ptb_read_result_format_async": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ptb_read_result_scatter_async": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "ptb_write_result": (C.c_int, [_P, C.c_void_p]),
+    "ptb_register_gl_texture": (C.c_int, [_P, C.c_uint]),
+    "ptb_present_gl": (C.c_int, [_P]),
+    "ptb_unregister_gl_texture": (C.c_int, [_P]),
     "ptb_synchronize": (C.c_int, [_P]),
     "ptb_result_device_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ptb_set_stream": (C.c_int, [_P, C.c_void_p]),

@@ -16,6 +16,10 @@
 
 using namespace ptb;
 
+// CUDA-GL interop of the runtime (cuda_gl_interop.h:204).  Declared here because that header includes <GL/gl.h>, which a
+// headless build box does not have; GLuint / GLenum are unsigned int, GL_TEXTURE_2D is 0x0DE1.
+extern "C" cudaError_t CUDARTAPI cudaGraphicsGLRegisterImage(struct cudaGraphicsResource** resource, unsigned int image, unsigned int target, unsigned int flags);
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -134,6 +138,7 @@ struct ptb_ctx {
     // frame batching (ptb_set_batch): up to `batch` consecutive frames of one ptb_render_frames call are traced by ONE
     // megakernel launch into a set of per-frame scratch images; two sets alternate so that the blends of batch k run beside
     // the trace of batch k+1
+    cudaGraphicsResource* gl_result = nullptr;   // PathTracer.Result registered through CUDA-GL interop (ptb_register_gl_texture)
     unsigned* d_done = nullptr;      // [kBatchSets] "batch traced" flags (written by the trace's last CTA) + [kBatchSets] a sticky error word
     int blend_ctas = 64;             // grid of the batch blend kernels (a background kernel beside the next batch's trace)
     int batch = 16;
@@ -951,6 +956,7 @@ void ptb_destroy(ptb_ctx* c)
         if (c->ev_batch_blend[i]) cudaEventDestroy(c->ev_batch_blend[i]);
     }
     exchange_close(c);
+    if (c->gl_result) cudaGraphicsUnregisterResource(c->gl_result);
     cudaFree(c->d_xch_blocks);
     if (c->blend_stream) cudaStreamDestroy(c->blend_stream);
     if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
@@ -974,6 +980,7 @@ int ptb_set_size(ptb_ctx* c, int width, int height)
     if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(PTB_E_INVALID, "bad size %dx%d (1..65535)", width, height);
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     exchange_close(c);                               // the slots were sized for the old image: a fresh ptb_exchange_init is required
+    if (c->gl_result) { cudaGraphicsUnregisterResource(c->gl_result); c->gl_result = nullptr; }     // the host re-allocates Result (PathTracer.cs:134) and registers it again
     c->width = width; c->height = height;
     c->frame = 0;                                    // PathTracer.cs:133
     return alloc_image(c);
@@ -1256,6 +1263,48 @@ int ptb_tonemap_rgba8(ptb_ctx* c, unsigned char* rgba8)
     if (rc == PTB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(PTB_E_CUDA, "tone-map kernel failed");
     cudaFree(d);
     return rc;
+}
+
+// ---- PathTracer.Result as a GL texture (PathTracer.cs:86,97-99: an Rgba32f TEXTURE_2D that ScreenEffect.Render samples,
+//      MainWindow.cs:51).  The host registers that texture once; ptb_present_gl copies the accumulation image into it on the
+//      device (HBM -> the texture's array, no PCIe traffic), stream-ordered after the frames rendered so far.
+int ptb_register_gl_texture(ptb_ctx* c, unsigned int texture)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (c->world != 1) return fail(PTB_E_STATE, "a tile context (ptb_set_tile) holds only its stripes; register the texture on a full-frame context");
+    CU(cudaSetDevice(c->device));
+    if (c->gl_result) { cudaGraphicsUnregisterResource(c->gl_result); c->gl_result = nullptr; }
+    const cudaError_t e = cudaGraphicsGLRegisterImage(&c->gl_result, texture, 0x0DE1u /* GL_TEXTURE_2D */, cudaGraphicsRegisterFlagsWriteDiscard);
+    if (e != cudaSuccess) {
+        c->gl_result = nullptr;
+        cudaGetLastError();
+        return fail(PTB_E_STATE, "cudaGraphicsGLRegisterImage(texture %u) failed: %s — the calling thread needs a current OpenGL context on this GPU "
+                                 "and an Rgba32f TEXTURE_2D of the render size", texture, cudaGetErrorString(e));
+    }
+    return PTB_OK;
+}
+int ptb_present_gl(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (!c->gl_result) return fail(PTB_E_STATE, "no GL texture registered (ptb_register_gl_texture)");
+    CU(cudaSetDevice(c->device));
+    CU(cudaGraphicsMapResources(1, &c->gl_result, c->stream));
+    cudaArray_t arr = nullptr;
+    cudaError_t e = cudaGraphicsSubResourceGetMappedArray(&arr, c->gl_result, 0, 0);
+    if (e == cudaSuccess) {
+        const size_t row = (size_t)c->width * sizeof(float4);
+        e = cudaMemcpy2DToArrayAsync(arr, 0, 0, c->d_image, row, row, (size_t)c->height, cudaMemcpyDeviceToDevice, c->stream);
+    }
+    const cudaError_t u = cudaGraphicsUnmapResources(1, &c->gl_result, c->stream);      // GL may sample the texture after this, in stream order
+    if (e != cudaSuccess) return fail(PTB_E_CUDA, "copy into the GL texture failed: %s (is it %dx%d Rgba32f?)", cudaGetErrorString(e), c->width, c->height);
+    if (u != cudaSuccess) return fail(PTB_E_CUDA, "cudaGraphicsUnmapResources failed: %s", cudaGetErrorString(u));
+    return PTB_OK;
+}
+int ptb_unregister_gl_texture(ptb_ctx* c)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (c->gl_result) { CU(cudaGraphicsUnregisterResource(c->gl_result)); c->gl_result = nullptr; }
+    return PTB_OK;
 }
 
 int ptb_synchronize(ptb_ctx* c)

@@ -299,6 +299,13 @@ class PathTracer:
         usually shared mapping), over this GPU's own PCIe link (ptb_read_result_scatter_async)."""
         _lib.check(self._L.ptb_read_result_scatter_async(self._ctx, int(format), C.c_void_p(pinned_full_frame_ptr)))
 
+    def RegisterGLTexture(self, texture: int) -> None:
+        """CUDA-GL interop: `texture` is the Rgba32f TEXTURE_2D the host samples as PathTracer.Result (needs a current GL context)."""
+        _lib.check(self._L.ptb_register_gl_texture(self._ctx, int(texture)))
+
+    def PresentGL(self) -> None:
+        _lib.check(self._L.ptb_present_gl(self._ctx))
+
     def Synchronize(self) -> None:
         _lib.check(self._L.ptb_synchronize(self._ctx))
 

@@ -144,6 +144,33 @@ def test_library_exports_every_declared_symbol(ptb):
     assert L.ptb_version() == 100
 
 
+def test_csharp_shim_binds_the_declared_abi():
+    """csharp/PtbNative.cs (the P/Invoke half of the drop-in for src/Render/PathTracer.cs) cannot be compiled here (no .NET):
+    every [DllImport] must at least name an entry point of include/ptb200.h with the same number of arguments, and the shim
+    class must keep the reference class's public members (PathTracer.cs:11-140)."""
+    hdr = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_args = {}
+    for m in re.finditer(r"\b(?:int|void|float|const char\*)\s+(ptb_[a-z0-9_]+)\(([^)]*)\);", hdr):
+        args = m.group(2).strip()
+        c_args[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    cs = open(os.path.join(ROOT, "csharp", "PtbNative.cs")).read()
+    imports = re.findall(r"\[DllImport\(Lib\)\]\s*public static extern (?:unsafe )?\w+ (ptb_[a-z0-9_]+)\(([^)]*)\);", cs)
+    assert len(imports) >= 25
+    for name, args in imports:
+        assert name in c_args, f"{name} is not declared in ptb200.h"
+        n = 0 if not args.strip() else len(args.split(","))
+        assert n == c_args[name], f"{name}: {n} arguments in C#, {c_args[name]} in C"
+    shim = open(os.path.join(ROOT, "csharp", "PathTracer.cs")).read()
+    for member in ("NumSpheres", "NumCuboids", "RayDepth", "SPP", "FocalLength", "ApertureDiameter", "EnvironmentMap", "Result", "Samples",
+                   "void Render()", "void SetSize(int width, int height)", "void ResetRenderer()"):
+        assert member in shim, member
+    used = set(re.findall(r"Ptb\.(ptb_[a-z0-9_]+)", shim))
+    assert used <= {n for n, _ in imports}, used - {n for n, _ in imports}
+    assert {"ptb_register_gl_texture", "ptb_present_gl", "ptb_render"} <= used      # Result goes to GL on the device, no host round trip
+    assert "ptb_read_result" not in used
+
+
 def test_library_has_sm100a_code_only(ptb):
     from importlib import import_module
     _lib = import_module("opentk-pathtracer_b200._lib")

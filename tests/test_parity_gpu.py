@@ -775,6 +775,20 @@ def test_error_codes(ptb, env256):
     huge.Dispose()
 
 
+def test_gl_interop_entry_points_without_a_gl_context(ptb, env256, default_scene, camera):
+    """PathTracer.Result is a GL texture in the reference (PathTracer.cs:86,97-99); ptb_register_gl_texture / ptb_present_gl hand
+    it over through CUDA-GL interop.  A headless box has no GL context: registration must fail cleanly with PTB_E_STATE (-3),
+    leave the context usable, and presenting without a registered texture is a call-order error."""
+    pt = make_tracer(ptb, env256, 64, 48, default_scene, camera)
+    with pytest.raises(ptb.PtbError, match="error -3"):
+        pt.RegisterGLTexture(1)
+    with pytest.raises(ptb.PtbError, match="error -3"):
+        pt.PresentGL()
+    pt.Render(2)
+    assert np.isfinite(pt.Result).all()
+    pt.Dispose()
+
+
 def test_four_thousand_spheres(ptb, oracle, env256, camera):
     """4096 spheres + 64 cuboids: 327 KB as a packed block, but with the BVH only geometry + hierarchy (~190 KB) are staged and
     the materials stay in HBM."""
