@@ -207,6 +207,10 @@ int ptb_precision(ptb_ctx* ctx);
  * cells = grid cells along the longest scene axis (default 13), buckets = direction buckets per cube-face axis (default 12).
  * The table is rebuilt on the GPU when geometry changes (not on material edits).  Results do not depend on it. */
 int ptb_set_ray_classification(ptb_ctx* ctx, int mode, int cells, int buckets);
+/* Large scenes (>= the BVH threshold): 1 (default) = uniform grid in shared memory walked by a 3-D DDA, 0 = binary BVH.  The
+ * grid falls back to the BVH when its lists do not fit 16-bit offsets.  Results do not depend on it. */
+int ptb_set_large_scene_mode(ptb_ctx* ctx, int mode);
+int ptb_set_grid_density(ptb_ctx* ctx, float cells_per_primitive);   /* grid resolution: target cells per primitive (default 2; at most 32 per axis) */
 /* Scenes with at least this many primitives are traced through the shared-memory BVH, smaller ones by the brute-force fold
  * (default 96).  Results do not depend on it (the hierarchy only removes primitives that fail the exact test). */
 int ptb_set_bvh_threshold(ptb_ctx* ctx, int primitives);
@@ -223,8 +227,10 @@ int ptb_kernel_launches(ptb_ctx* ctx);          /* CUDA kernels launched by this
 #define PTB_INFO_ALWAYS_TESTED 1  /* primitives outside the hierarchy (scene-sized or non-finite), tested for every ray */
 #define PTB_INFO_STAGED_BYTES 2   /* bytes of the scene block each CTA stages into shared memory */
 #define PTB_INFO_GRID_CTAS 3      /* CTAs of the persistent grid of the last launch */
-#define PTB_INFO_FOLD 4           /* how RayTrace() runs: 0 brute force, 1 BVH, 2 ray-classification table */
+#define PTB_INFO_FOLD 4           /* how RayTrace() runs: 0 brute force, 1 BVH, 2 ray-classification table, 3 uniform grid */
 #define PTB_INFO_RCT_KBYTES 5     /* size of the ray-classification table in KiB (0: none) */
+#define PTB_INFO_GRID_CELLS 6     /* cells of the shared-memory grid (0: none) */
+#define PTB_INFO_GRID_ITEMS 7     /* primitive references in the grid's cell lists */
 int ptb_scene_info(ptb_ctx* ctx, int what);
 float ptb_last_render_ms(ptb_ctx* ctx);         /* cudaEvent time of the last ptb_render[_frames] call (syncs) */
 /* Path statistics of the next renders: counters[0]=samples, [1]=RayTrace calls, [2]=hits (device atomics; slow). */
@@ -237,6 +243,7 @@ int ptb_read_stats(ptb_ctx* ctx, unsigned long long* counters3);
  *     5 min/max/rcp/sqrt probe (in 2n, out 4n)  6 RayTrace fold over the raw UBO bytes (proxy view; as 4)
  *     8 log (n -> n)  9 RayTrace fold through the BVH (scenes of >= 96 primitives; as 4; out[12i+3] = nodes visited)
  *     10 RayTrace fold through the ray-classification table (as 4; out[12i+3] = candidates left, 65 = full mask)
+ *     11 RayTrace fold through the uniform grid (large scenes; as 4; out[12i+3] = cells visited)
  *     7 group-cooperative fold of the frame tail: rays are processed k = in[6n] at a time per warp (in 6n+1, out 12n) */
 int ptb_debug_eval(ptb_ctx* ctx, int op, const float* in, int n, float* out);
 

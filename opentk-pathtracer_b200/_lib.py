@@ -74,6 +74,8 @@ SIGNATURES = {
     "ptb_kernel_launches": (C.c_int, [_P]),
     "ptb_scene_info": (C.c_int, [_P, C.c_int]),
     "ptb_set_bvh_threshold": (C.c_int, [_P, C.c_int]),
+    "ptb_set_large_scene_mode": (C.c_int, [_P, C.c_int]),
+    "ptb_set_grid_density": (C.c_int, [_P, C.c_float]),
     "ptb_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "ptb_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "ptb_set_precision": (C.c_int, [_P, C.c_int]),

@@ -88,6 +88,13 @@ struct ptb_ctx {
     int rct_n[3] = {};
     unsigned rct_sm0 = 0, rct_sm1 = 0;
     std::vector<unsigned char> rct_geometry;   // the geometry bytes the table was built from (material edits do not rebuild it)
+    // uniform grid for large scenes (trace_grid): the default above bvh_threshold; the BVH stays as the fallback / alternative
+    int large_mode = 1;              // 0 = BVH, 1 = grid
+    float grid_density = 2.0f;       // target cells per binned primitive (ptb_set_grid_density)
+    bool grid_on = false;
+    int grid_n[3] = {}, off_gcell = 0, off_gitem = 0;
+    float grid_lo[3] = {}, grid_hi[3] = {}, grid_cell[3] = {}, grid_inv[3] = {};
+    std::vector<unsigned short> grid_cell_start, grid_items;
     float4* d_env_faces = nullptr;   // unpadded 6*N*N
     float4* d_env = nullptr;         // padded 6*(N+2)^2
     int env_size = 0;
@@ -496,6 +503,83 @@ int build_rct(ptb_ctx* c)
     return PTB_OK;
 }
 
+// Uniform grid over the primitives' inflated boxes (see trace_grid).  Returns false when the scene does not fit the 16-bit
+// lists (the caller then builds the BVH instead).
+bool build_grid(ptb_ctx* c)
+{
+    c->grid_on = false; c->grid_cell_start.clear(); c->grid_items.clear();
+    c->bvh_nodes.clear(); c->bvh_pidx.clear(); c->n_nodes = 0; c->n_unbounded = 0; c->bvh_tau = 0.0f; c->bvh_D = 0.0f;
+    const int n = c->n_spheres + c->n_cuboids;
+    if (n < c->bvh_threshold || n >= 65535) return false;
+    std::vector<Box> boxes; std::vector<char> bounded;
+    raw_boxes(c, 0.0, 0.0, boxes, bounded);
+    std::vector<Box> finite;
+    for (int i = 0; i < n; ++i) if (bounded[i]) finite.push_back(boxes[i]);
+    if (finite.empty()) return false;
+    c->bvh_extent = scene_extent(finite);
+    const float D = required_extent(c, c->bvh_extent);
+    const double E = 4e-6 * (double)D * D, m = 1e-5 * (double)D + 1e-6;
+    raw_boxes(c, E, m, boxes, bounded);
+    double slo[3] = {1e300, 1e300, 1e300}, shi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; ++i) if (bounded[i]) for (int k = 0; k < 3; ++k) { slo[k] = std::min(slo[k], boxes[i].lo[k]); shi[k] = std::max(shi[k], boxes[i].hi[k]); }
+    std::vector<int> binned;
+    for (int i = 0; i < n; ++i) {
+        bool big = !bounded[i];
+        if (!big) for (int k = 0; k < 3; ++k) if (boxes[i].hi[k] - boxes[i].lo[k] > PTB_BVH_BIG * (shi[k] - slo[k])) big = true;
+        if (big && (int)c->bvh_pidx.size() < 64) c->bvh_pidx.push_back(i); else if (bounded[i]) binned.push_back(i); else c->bvh_pidx.push_back(i);
+    }
+    c->n_unbounded = (int)c->bvh_pidx.size();
+    c->bvh_D = D;
+    c->bvh_tau = 1e-4f * D;
+    // bounds of what is binned
+    double glo[3] = {1e300, 1e300, 1e300}, ghi[3] = {-1e300, -1e300, -1e300};
+    for (int i : binned) for (int k = 0; k < 3; ++k) { glo[k] = std::min(glo[k], boxes[i].lo[k]); ghi[k] = std::max(ghi[k], boxes[i].hi[k]); }
+    if (binned.empty()) for (int k = 0; k < 3; ++k) { glo[k] = 0.0; ghi[k] = 1.0; }
+    double ext[3], vol = 1.0;
+    for (int k = 0; k < 3; ++k) { ext[k] = std::max(ghi[k] - glo[k], 1e-3); vol *= ext[k]; }
+    const double target = std::min(8192.0, std::max(64.0, (double)c->grid_density * (double)binned.size()));
+    const double side = std::cbrt(vol / target);
+    // the grid margin: a primitive is listed in every cell its box comes within g of — g covers the rounding of the DDA
+    // (cell boundaries and accumulated exit parameters are off by far less than tau = 1e-4 D) and of the cell lookup
+    double cellmin = 1e300;
+    for (int k = 0; k < 3; ++k) {
+        int nk = (int)std::ceil(ext[k] / side);
+        nk = std::min(std::max(nk, 1), 32);
+        c->grid_n[k] = nk;
+        cellmin = std::min(cellmin, ext[k] / nk);
+    }
+    const double g = (double)c->bvh_tau + 1e-3 * cellmin;
+    for (int k = 0; k < 3; ++k) {
+        const double lo = glo[k] - 2.0 * g, hi = ghi[k] + 2.0 * g;
+        c->grid_lo[k] = (float)lo; c->grid_hi[k] = (float)hi;
+        c->grid_cell[k] = (float)((hi - lo) / c->grid_n[k]);
+        c->grid_inv[k] = (float)(c->grid_n[k] / (hi - lo));
+    }
+    const int ncell = c->grid_n[0] * c->grid_n[1] * c->grid_n[2];
+    std::vector<std::vector<unsigned short>> lists((size_t)ncell);
+    size_t total = 0;
+    for (int i : binned) {
+        int a[3], b[3];
+        for (int k = 0; k < 3; ++k) {
+            const double cs = (double)c->grid_cell[k];
+            a[k] = std::min(std::max((int)std::floor((boxes[i].lo[k] - g - (double)c->grid_lo[k]) / cs), 0), c->grid_n[k] - 1);
+            b[k] = std::min(std::max((int)std::floor((boxes[i].hi[k] + g - (double)c->grid_lo[k]) / cs), 0), c->grid_n[k] - 1);
+        }
+        for (int z = a[2]; z <= b[2]; ++z)
+            for (int y = a[1]; y <= b[1]; ++y)
+                for (int x = a[0]; x <= b[0]; ++x) { lists[((size_t)z * c->grid_n[1] + y) * c->grid_n[0] + x].push_back((unsigned short)i); ++total; }
+    }
+    if (total >= 65535) return false;
+    c->grid_cell_start.resize((size_t)ncell + 1);
+    for (int q = 0; q < ncell; ++q) {
+        c->grid_cell_start[q] = (unsigned short)c->grid_items.size();
+        c->grid_items.insert(c->grid_items.end(), lists[q].begin(), lists[q].end());      // ascending index inside a cell (binned is ascending)
+    }
+    c->grid_cell_start[ncell] = (unsigned short)c->grid_items.size();
+    c->grid_on = true;
+    return true;
+}
+
 void layout_block(ptb_ctx* c)
 {
     // float4 units: [spheres][1/r][cuboid lo][cuboid hi][BVH nodes][BVH index list] | [materials]
@@ -505,17 +589,19 @@ void layout_block(ptb_ctx* c)
     c->off_cmax = c->off_cmin + 1;                // slab bounds interleaved: lo0, hi0, lo1, hi1, ...
     c->off_nodes = c->off_cmin + 2 * nC;
     c->off_pidx = c->off_nodes + 2 * c->n_nodes;
-    c->off_mat = c->off_pidx + ((int)c->bvh_pidx.size() + 3) / 4;
+    c->off_gcell = c->off_pidx + ((int)c->bvh_pidx.size() + 3) / 4;
+    c->off_gitem = c->off_gcell + (c->grid_on ? ((int)c->grid_cell_start.size() + 7) / 8 : 0);
+    c->off_mat = c->off_gitem + (c->grid_on ? ((int)c->grid_items.size() + 7) / 8 : 0);
     c->block_bytes = (c->off_mat + (nS + nC) * 4) * 16;
     if (c->block_bytes < 16) c->block_bytes = 16;
     // with a BVH the materials stay in HBM / L2 (only the winner's 64 B are read per bounce) so more CTAs fit an SM
-    c->stage_bytes = c->n_nodes > 0 || c->n_unbounded > 0 ? std::max(16, c->off_mat * 16) : c->block_bytes;
+    c->stage_bytes = c->n_nodes > 0 || c->n_unbounded > 0 || c->grid_on ? std::max(16, c->off_mat * 16) : c->block_bytes;
 }
 
 int sync_scene(ptb_ctx* c)
 {
     if (!c->scene_dirty) return PTB_OK;
-    build_bvh(c);
+    if (!(c->large_mode == 1 && build_grid(c))) { c->grid_on = false; build_bvh(c); }
     layout_block(c);
     if (c->stage_bytes > kMaxSmem - 1024)
         return fail(PTB_E_INVALID, "scene block of %d bytes does not fit shared memory (%d spheres, %d cuboids)", c->block_bytes, c->n_spheres, c->n_cuboids);
@@ -547,7 +633,11 @@ int sync_scene(ptb_ctx* c)
     }
     if (c->n_nodes > 0) CU(cudaMemcpyAsync(c->d_block + c->off_nodes, c->bvh_nodes.data(), c->bvh_nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     if (!c->bvh_pidx.empty()) CU(cudaMemcpyAsync(c->d_block + c->off_pidx, c->bvh_pidx.data(), c->bvh_pidx.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    if (c->n_nodes > 0 || !c->bvh_pidx.empty()) CU(cudaStreamSynchronize(c->stream));     // the host vectors may be rebuilt before the copy ran
+    if (c->grid_on) {
+        CU(cudaMemcpyAsync(c->d_block + c->off_gcell, c->grid_cell_start.data(), c->grid_cell_start.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, c->stream));
+        if (!c->grid_items.empty()) CU(cudaMemcpyAsync(c->d_block + c->off_gitem, c->grid_items.data(), c->grid_items.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (c->n_nodes > 0 || !c->bvh_pidx.empty() || c->grid_on) CU(cudaStreamSynchronize(c->stream));     // the host vectors may be rebuilt before the copy ran
     c->scene_dirty = false;
     return mark_inputs(c);
 }
@@ -579,6 +669,8 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.scratch_stride = 0ull;
     P.ktime = nullptr;
     P.done_flag = nullptr; P.done_value = 0u;
+    P.off_gcell = c->off_gcell; P.off_gitem = c->off_gitem;
+    for (int k = 0; k < 3; ++k) { P.grid_n[k] = c->grid_n[k]; P.grid_lo[k] = c->grid_lo[k]; P.grid_hi[k] = c->grid_hi[k]; P.grid_cell[k] = c->grid_cell[k]; P.grid_inv[k] = c->grid_inv[k]; }
     P.rct = c->rct_on ? c->d_rct : nullptr;
     for (int k = 0; k < 3; ++k) { P.rct_lo[k] = c->rct_lo[k]; P.rct_inv[k] = c->rct_inv[k]; P.rct_n[k] = c->rct_n[k]; }
     P.rct_G = c->rct_G; P.rct_halfG = 0.5f * (float)c->rct_G;
@@ -607,7 +699,7 @@ unsigned long long xch_own_frames(const ptb_ctx* c, unsigned long long seq)
     return (seq + (unsigned long long)(c->world - 1 - c->rank)) / (unsigned long long)c->world;
 }
 
-int fold_of(const ptb_ctx* c) { return (c->n_nodes > 0 || c->n_unbounded > 0) ? 1 : (c->rct_on ? 2 : 0); }
+int fold_of(const ptb_ctx* c) { return c->grid_on ? 3 : ((c->n_nodes > 0 || c->n_unbounded > 0) ? 1 : (c->rct_on ? 2 : 0)); }
 
 template <int kFold, class F>
 int with_mega_fold(ptb_ctx* c, bool stats, F&& launch)
@@ -624,6 +716,7 @@ int with_mega(ptb_ctx* c, bool stats, F&& launch)
     switch (fold_of(c)) {
     case 1: return with_mega_fold<1>(c, stats, launch);
     case 2: return with_mega_fold<2>(c, stats, launch);
+    case 3: return with_mega_fold<3>(c, stats, launch);
     default: return with_mega_fold<0>(c, stats, launch);
     }
 }
@@ -662,7 +755,7 @@ int launch_frame(ptb_ctx* c)
         if (c->precision == PTB_PRECISION_FAST) {
             CU(ptb_fast_api::prepare(fold, smem, &with_ring, &without));
         } else {
-            const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, without) : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, without) : prepare_mega<0>(c, smem, with_ring, without));
+            const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, without) : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, without) : (fold == 3 ? prepare_mega<3>(c, smem, with_ring, without) : prepare_mega<0>(c, smem, with_ring, without)));
             if (rc != PTB_OK) return rc;
         }
         if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
@@ -744,6 +837,7 @@ int with_mega_batch(ptb_ctx* c, F&& launch)
     switch (fold_of(c)) {
     case 1: return c->mega_ring ? launch(megakernel<false, true, 1, true>) : launch(megakernel<false, false, 1, true>);
     case 2: return c->mega_ring ? launch(megakernel<false, true, 2, true>) : launch(megakernel<false, false, 2, true>);
+    case 3: return c->mega_ring ? launch(megakernel<false, true, 3, true>) : launch(megakernel<false, false, 3, true>);
     default: return c->mega_ring ? launch(megakernel<false, true, 0, true>) : launch(megakernel<false, false, 0, true>);
     }
 }
@@ -1119,7 +1213,7 @@ int ptb_render_frames(ptb_ctx* c, int n)
     if (n < 0) return fail(PTB_E_INVALID, "n < 0");
     if (!c->d_env) return fail(PTB_E_STATE, "Render() before an EnvironmentMap was set");
     CU(cudaSetDevice(c->device));
-    if (!c->scene_dirty && (c->n_nodes > 0 || c->n_unbounded > 0)) {
+    if (!c->scene_dirty && (c->n_nodes > 0 || c->n_unbounded > 0 || c->grid_on)) {
         // the BVH margins were sized for an extent D that includes the camera: a camera that left it forces a rebuild
         if (required_extent(c, c->bvh_extent) > c->bvh_D) c->scene_dirty = true;
     }
@@ -1610,6 +1704,22 @@ int ptb_set_ray_classification(ptb_ctx* c, int mode, int cells, int buckets)
     c->scene_dirty = true;
     return PTB_OK;
 }
+int ptb_set_grid_density(ptb_ctx* c, float cells_per_primitive)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (!(cells_per_primitive >= 0.05f && cells_per_primitive <= 64.0f)) return fail(PTB_E_INVALID, "density %g outside [0.05,64]", (double)cells_per_primitive);
+    c->grid_density = cells_per_primitive;
+    c->scene_dirty = true;
+    return PTB_OK;
+}
+int ptb_set_large_scene_mode(ptb_ctx* c, int mode)
+{
+    if (!c) return fail(PTB_E_INVALID, "ctx is null");
+    if (mode != 0 && mode != 1) return fail(PTB_E_INVALID, "mode %d outside [0,1]", mode);
+    c->large_mode = mode;
+    c->scene_dirty = true;
+    return PTB_OK;
+}
 int ptb_set_bvh_threshold(ptb_ctx* c, int primitives)
 {
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
@@ -1629,6 +1739,8 @@ int ptb_scene_info(ptb_ctx* c, int what)
     case PTB_INFO_STAGED_BYTES: return c->stage_bytes;
     case PTB_INFO_GRID_CTAS: return c->mega_grid;
     case PTB_INFO_FOLD: return fold_of(c);
+    case PTB_INFO_GRID_CELLS: return c->grid_on ? c->grid_n[0] * c->grid_n[1] * c->grid_n[2] : 0;
+    case PTB_INFO_GRID_ITEMS: return c->grid_on ? (int)c->grid_items.size() : 0;
     case PTB_INFO_RCT_KBYTES: return c->rct_on ? (int)(((size_t)c->rct_n[0] * c->rct_n[1] * c->rct_n[2] * 6 * c->rct_G * c->rct_G * 8) >> 10) : 0;
     default: return fail(PTB_E_INVALID, "unknown info %d", what);
     }
@@ -1668,7 +1780,7 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
     case 1: in_f = n; out_f = n; break;
     case 2: in_f = 1; out_f = n; break;
     case 3: in_f = 3 * (size_t)n; out_f = 3 * (size_t)n; break;
-    case 4: case 6: case 9: case 10: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
+    case 4: case 6: case 9: case 10: case 11: in_f = 6 * (size_t)n; out_f = 12 * (size_t)n; break;
     case 5: in_f = 2 * (size_t)n; out_f = 4 * (size_t)n; break;
     case 7: in_f = 6 * (size_t)n + 1; out_f = 12 * (size_t)n; break;
     case 8: in_f = n; out_f = n; break;
@@ -1687,16 +1799,18 @@ int ptb_debug_eval(ptb_ctx* c, int op, const float* in, int n, float* out)
         else if (op == 3) {
             if (!c->d_env) { rc = fail(PTB_E_STATE, "no environment map set"); break; }
             dbg_env_kernel<<<gb, tb, 0, c->stream>>>(c->d_env, c->env_size, d_in, n, d_out);
-        } else if (op == 4 || op == 6 || op == 9 || op == 10) {
+        } else if (op == 4 || op == 6 || op == 9 || op == 10 || op == 11) {
             rc = sync_scene(c);
             if (rc != PTB_OK) break;
             RenderParams P;
             fill_params(c, P);
             const int smem = op == 6 ? 0 : c->stage_bytes;
             if (op == 9 && c->n_nodes == 0 && c->n_unbounded == 0) { rc = fail(PTB_E_STATE, "the current scene has no BVH (fewer than %d primitives)", c->bvh_threshold); break; }
+            if (op == 9 && c->grid_on) { rc = fail(PTB_E_STATE, "the current scene is traced through the grid, not the BVH (ptb_set_large_scene_mode(0) selects the BVH)"); break; }
+            if (op == 11 && !c->grid_on) { rc = fail(PTB_E_STATE, "the current scene has no grid (fewer than %d primitives, or the BVH was selected)", c->bvh_threshold); break; }
             if (op == 10 && !c->rct_on) { rc = fail(PTB_E_STATE, "the current scene has no ray-classification table (more than 64 primitives, or switched off)"); break; }
             if (cudaFuncSetAttribute(dbg_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->stage_bytes) != cudaSuccess) { rc = fail(PTB_E_CUDA, "smem attr failed"); break; }
-            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : (op == 9 ? 2 : (op == 10 ? 3 : 0)));
+            dbg_trace_kernel<<<gb, tb, smem, c->stream>>>(P, d_in, n, d_out, op == 6 ? 1 : (op == 9 ? 2 : (op == 10 ? 3 : (op == 11 ? 4 : 0))));
         } else if (op == 5) dbg_arith_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 8) dbg_log_kernel<<<gb, tb, 0, c->stream>>>(d_in, n, d_out);
         else if (op == 7) {

@@ -30,6 +30,7 @@ cudaError_t with(int fold, bool ring, bool batch, F&& f)
     switch (fold) {
     case 1: return pick<1>(ring, batch, f);
     case 2: return pick<2>(ring, batch, f);
+    case 3: return pick<3>(ring, batch, f);
     default: return pick<0>(ring, batch, f);
     }
 }

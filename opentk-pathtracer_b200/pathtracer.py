@@ -337,6 +337,13 @@ class PathTracer:
         """Ray-classification table for scenes of <= 64 primitives (ptb_set_ray_classification); mode 0 = plain fold."""
         _lib.check(self._L.ptb_set_ray_classification(self._ctx, int(mode), int(cells), int(buckets)))
 
+    def SetLargeSceneMode(self, mode: int) -> None:
+        """Scenes above the BVH threshold: 1 = uniform grid + DDA (default), 0 = binary BVH (ptb_set_large_scene_mode)."""
+        _lib.check(self._L.ptb_set_large_scene_mode(self._ctx, int(mode)))
+
+    def SetGridDensity(self, cells_per_primitive: float) -> None:
+        _lib.check(self._L.ptb_set_grid_density(self._ctx, float(cells_per_primitive)))
+
     def SetBvhThreshold(self, primitives: int) -> None:
         _lib.check(self._L.ptb_set_bvh_threshold(self._ctx, int(primitives)))
 

@@ -140,10 +140,12 @@ def test_group_cooperative_fold_bit_exact(ptb, oracle, env256, camera):
         pt.Dispose()
 
 
-def test_bvh_fold_bit_exact(ptb, oracle, env256, camera):
-    """Scenes of >= 96 primitives go through the shared-memory BVH.  It may only remove primitives that fail the exact test,
-    so the fold must equal the oracle's brute-force fold bit for bit — including rays that start inside (overlapping)
-    primitives, axis-parallel rays, rays grazing box faces, far-away origins and degenerate / non-finite geometry."""
+@pytest.mark.parametrize("mode", [1, 0], ids=["grid", "bvh"])
+def test_large_scene_fold_bit_exact(ptb, oracle, env256, camera, mode):
+    """Scenes of >= 96 primitives go through a spatial structure in shared memory — a uniform grid walked by a DDA (default) or
+    a binary BVH.  Either may only skip primitives that fail the exact test, so the fold must equal the oracle's brute-force
+    fold bit for bit — including rays that start inside (overlapping) primitives, axis-parallel rays, rays grazing box faces,
+    far-away origins and degenerate / non-finite geometry."""
     rng = np.random.default_rng(17)
     for scene in (ptb.synthetic_scene(1024, 256), ptb.synthetic_scene(200, 60, seed=3)):
         if len(scene.spheres) == 200:      # poison a few primitives: NaN centre, infinite box, inverted box, zero radius
@@ -152,6 +154,7 @@ def test_bvh_fold_bit_exact(ptb, oracle, env256, camera):
             scene.cuboids[20].Dimensions = np.array([np.inf, 1, 1], np.float32)
             scene.cuboids[21].Dimensions = np.array([-1.0, 2.0, -0.5], np.float32)
         pt = make_tracer(ptb, env256, 16, 16, scene, camera)
+        pt.SetLargeSceneMode(mode)
         n = 60000
         o = (rng.random((n, 3)).astype(np.float32) - np.float32(0.5)) * np.array([44, 28, 28], np.float32) + np.array([0, 0, -10], np.float32)
         centres = np.stack([s.Position for s in scene.spheres])
@@ -167,23 +170,52 @@ def test_bvh_fold_bit_exact(ptb, oracle, env256, camera):
         d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
         d[-300:-200, 0] = 0; d[-200:-100, 1] = 0; d[-100:, :2] = 0; d[-100:, 2] = 1       # axis-parallel: infinite reciprocals
         o[-50:] *= np.float32(40.0)                                                          # far outside the scene
+        o[-1300:-300] = np.round(o[-1300:-300] / np.float32(0.25)) * np.float32(0.25)        # lattice points: cell boundaries, box faces
         rays = np.concatenate([o, d], 1).astype(np.float32)
         ref = oracle.ray_trace(rays, scene.ubo_bytes(), scene.max_spheres, len(scene.spheres), len(scene.cuboids))
         assert ref[:, 2].sum() > 3000 and ref[:, 0].sum() > 30000
-        got = pt.DebugEval(9, rays, n, 12 * n).reshape(-1, 12).copy()
-        # column 3 of probe 9 is the number of BVH nodes the ray visited: the probe must really have walked the hierarchy
-        # (round 1's probe silently took the brute-force fold), and a hierarchy that visits every node culls nothing
+        assert pt.SceneInfo(4) == (3 if mode else 1)
+        got = pt.DebugEval(11 if mode else 9, rays, n, 12 * n).reshape(-1, 12).copy()
+        # column 3 = BVH nodes / grid cells the ray visited: the probe must really have walked the structure (round 1's probe
+        # silently took the brute-force fold), and a structure that visits everything culls nothing
         visits = got[:, 3].copy()
         got[:, 3] = 0
         finite = np.isfinite(rays).all(axis=1)
-        assert (visits[finite] >= 1).all(), "a finite ray did not enter the BVH"
-        assert visits[finite].mean() < 0.5 * pt.BvhNodes, f"mean {visits[finite].mean():.1f} of {pt.BvhNodes} nodes visited: nothing is culled"
-        assert_same(got, ref, f"BVH fold, {len(scene.spheres)} spheres + {len(scene.cuboids)} cuboids")
+        total = pt.SceneInfo(6) if mode else pt.BvhNodes
+        assert total > 0
+        if mode == 0:
+            assert (visits[finite] >= 1).all(), "a finite ray did not enter the BVH"
+        else:
+            in_room = finite & (np.abs(rays[:, 0]) < 18) & (np.abs(rays[:, 1]) < 10) & (rays[:, 2] > -20) & (rays[:, 2] < 0)
+            assert (visits[in_room] >= 1).all(), "a ray that starts between the primitives did not enter the grid"
+        assert visits[finite].mean() < 0.5 * total, f"mean {visits[finite].mean():.1f} of {total} nodes / cells visited: nothing is culled"
+        assert_same(got, ref, f"{'grid' if mode else 'BVH'} fold, {len(scene.spheres)} spheres + {len(scene.cuboids)} cuboids")
+        with pytest.raises(ptb.PtbError):          # the other structure is not built
+            pt.DebugEval(9 if mode else 11, rays[:1], 1, 12)
         pt.Dispose()
     small = make_tracer(ptb, env256, 16, 16, ptb.load_default_scene(), camera)
-    with pytest.raises(ptb.PtbError):          # 55 primitives: brute force, no BVH to probe
-        small.DebugEval(9, np.zeros(6, np.float32), 1, 12)
+    with pytest.raises(ptb.PtbError):          # 55 primitives: no large-scene structure to probe
+        small.DebugEval(11 if mode else 9, np.zeros(6, np.float32), 1, 12)
     small.Dispose()
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["grid", "bvh"])
+def test_bvh_survives_camera_leaving_the_scene(ptb, oracle, env256, mode):
+    """The structures' safety margins scale with an extent that includes the camera; moving the camera far away must rebuild them."""
+    scene = ptb.synthetic_scene(160, 40, seed=8)
+    sc = ptb.scene
+    pt = ptb.PathTracer(env256, 96, 54, 8, 1, 20.0, 0.14, max_spheres=scene.max_spheres, max_cuboids=scene.max_cuboids)
+    pt.SetLargeSceneMode(mode)
+    pt.LoadScene(scene)
+    for pos in ([-17.14, 3.53, -8.62], [-900.0, 40.0, 700.0], [3.0e4, 10.0, -2.0e4], [-17.14, 3.53, -8.62]):
+        cam = sc.Camera(np.array(pos, np.float32), np.array([0, 1, 0], np.float32), -32.2, 0.8)
+        cam_target = sc.Camera(np.array(pos, np.float32), np.array([0, 1, 0], np.float32),
+                               float(np.degrees(np.arctan2(-10 - pos[2], -pos[0]))), float(np.degrees(np.arctan2(-pos[1], np.hypot(pos[0], pos[2] + 10)))))
+        for c in (cam, cam_target):
+            pt.SetCamera(c); pt.ResetRenderer(); pt.Render()
+            ref = oracle_render(oracle, sc, scene, c, env256, 96, 54, 1, depth=8)
+            assert_same(pt.Result, ref, f"camera at {pos}")
+    pt.Dispose()
 
 
 def test_ray_classification_fold_bit_exact(ptb, oracle, env256, camera):
@@ -543,11 +575,13 @@ def test_dof_sweep_parity(ptb, oracle, env256, default_scene, camera):
             pt.Dispose()
 
 
-def test_synthetic_scene_parity(ptb, oracle, env256, camera):
-    """C3: 1024 spheres + 256 cuboids, rayDepth 8 (capacities 1024/256 move the cuboid base to 81 920)."""
+@pytest.mark.parametrize("mode", [1, 0], ids=["grid", "bvh"])
+def test_synthetic_scene_parity(ptb, oracle, env256, camera, mode):
+    """C3: 1024 spheres + 256 cuboids, rayDepth 8 (capacities 1024/256 move the cuboid base to 81 920), grid and BVH."""
     syn = ptb.synthetic_scene(1024, 256)
     W, H = 160, 90
     pt = make_tracer(ptb, env256, W, H, syn, camera, depth=8)
+    pt.SetLargeSceneMode(mode)
     ref = np.zeros((H, W, 4), np.float32)
     for f in range(2):
         pt.Render()
