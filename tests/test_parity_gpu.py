@@ -563,6 +563,25 @@ def test_1080p_crop_parity(ptb, oracle, env256, default_scene, camera):
     pt.Dispose()
 
 
+def test_c2_full_size_to_1024_spp(ptb, oracle, env256, default_scene, camera):
+    """BASELINE config 2 itself: 1920x1080, frames 0..1023 at SPP 1, running mean.  The GPU renders the whole progressive
+    render (batched launches, the path the bench times); the oracle follows three 8-row bands (sky / spheres / floor) through
+    all 1024 frames.  Bit-exact: per-channel MSE exactly 0 on 46 080 pixels x 1024 frames."""
+    W, H, FRAMES = 1920, 1080, 1024
+    pt = make_tracer(ptb, env256, W, H, default_scene, camera)
+    pt.Render(FRAMES)
+    got = pt.Result
+    assert pt.Samples == FRAMES
+    bands = [(40, 48), (536, 544), (1000, 1008)]
+    ref = np.zeros((H, W, 4), np.float32)
+    for b in bands:
+        oracle_render(oracle, ptb.scene, default_scene, camera, env256, W, H, FRAMES, image=ref, rows=b)
+    for b in bands:
+        assert_same(got[b[0]:b[1]], ref[b[0]:b[1]], f"1080p rows {b} after {FRAMES} frames")
+    assert np.isfinite(got).all()
+    pt.Dispose()
+
+
 def test_dof_sweep_parity(ptb, oracle, env256, default_scene, camera):
     """C5: ApertureDiameter x FocalLength grid at reduced size."""
     W, H = 96, 54
