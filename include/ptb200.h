@@ -76,6 +76,12 @@ int ptb_set_environment_srgb8(ptb_ctx* ctx, int face_size, const unsigned char* 
  * light_pos / light_intensity / i_steps / j_steps are that shader's uniforms. */
 int ptb_generate_atmosphere(ptb_ctx* ctx, int face_size, const void* ubo, int ubo_size, const float* light_pos,
                             float light_intensity, int i_steps, int j_steps);
+/* The same pass for live regeneration (the GUI re-runs it on every slider tick, up to 2048^2 faces; Gui.cs:93-143): the same
+ * loops with special-function exp / sqrt / 1/x and fused multiply-adds — a third of the instructions; agrees with
+ * ptb_generate_atmosphere (which stays bit-exact with the shader and is this one's checker) to ~1e-5 relative.  Both reuse the
+ * cubemap buffers when the size is unchanged.  Not for parity runs. */
+int ptb_generate_atmosphere_fast(ptb_ctx* ctx, int face_size, const void* ubo, int ubo_size, const float* light_pos,
+                                 float light_intensity, int i_steps, int j_steps);
 /* Copies the current environment map (unpadded, 6*face_size^2*4 floats) back to the host. */
 int ptb_read_environment(ptb_ctx* ctx, float* six_faces);
 int ptb_environment_size(ptb_ctx* ctx);

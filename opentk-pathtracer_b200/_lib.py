@@ -32,6 +32,7 @@ SIGNATURES = {
     "ptb_tonemap_rgba8": (C.c_int, [_P, C.c_void_p]),
     "ptb_tonemap_device": (C.c_int, [_P, C.c_void_p]),
     "ptb_generate_atmosphere": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int, _FP, C.c_float, C.c_int, C.c_int]),
+    "ptb_generate_atmosphere_fast": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_int, _FP, C.c_float, C.c_int, C.c_int]),
     "ptb_read_environment": (C.c_int, [_P, _FP]),
     "ptb_environment_size": (C.c_int, [_P]),
     "ptb_render": (C.c_int, [_P]),

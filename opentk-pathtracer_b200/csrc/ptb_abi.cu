@@ -95,6 +95,7 @@ struct ptb_ctx {
     int grid_n[3] = {}, off_gcell = 0, off_gitem = 0;
     float grid_lo[3] = {}, grid_hi[3] = {}, grid_cell[3] = {}, grid_inv[3] = {};
     std::vector<unsigned short> grid_cell_start, grid_items;
+    size_t env_faces_bytes = 0, env_padded_bytes = 0;
     float4* d_env_faces = nullptr;   // unpadded 6*N*N
     float4* d_env = nullptr;         // padded 6*(N+2)^2
     int env_size = 0;
@@ -1128,8 +1129,12 @@ static int install_environment(ptb_ctx* c, int N)
 {
     // d_env_faces already holds 6*N*N texels on the stream; (re)build the padded copy
     const int P = N + 2;
-    if (c->d_env) { CU(cudaFree(c->d_env)); c->d_env = nullptr; }
-    CU(cudaMalloc(&c->d_env, (size_t)6 * P * P * sizeof(float4)));
+    const size_t padded = (size_t)6 * P * P * sizeof(float4);
+    if (c->env_padded_bytes != padded) {
+        if (c->d_env) { CU(cudaFree(c->d_env)); c->d_env = nullptr; c->env_padded_bytes = 0; }
+        CU(cudaMalloc(&c->d_env, padded));
+        c->env_padded_bytes = padded;
+    }
     dim3 block(16, 16, 1), grid((P + 15) / 16, (P + 15) / 16, 6);
     pad_cubemap_kernel<<<grid, block, 0, c->stream>>>(c->d_env_faces, N, c->d_env);
     c->launches++;
@@ -1143,10 +1148,11 @@ int ptb_set_environment_rgba32f(ptb_ctx* c, int face_size, const float* six_face
     if (!c || !six_faces) return fail(PTB_E_INVALID, "null argument");
     if (face_size < 1 || face_size > 8192) return fail(PTB_E_INVALID, "face size %d outside [1,8192]", face_size);
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }      // frames in flight on the trace streams still sample the old map
     const size_t bytes = (size_t)6 * face_size * face_size * sizeof(float4);
-    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; }
+    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; c->env_faces_bytes = 0; }
     CU(cudaMalloc(&c->d_env_faces, bytes));
+    c->env_faces_bytes = bytes;
     CU(cudaMemcpyAsync(c->d_env_faces, six_faces, bytes, cudaMemcpyHostToDevice, c->stream));
     return install_environment(c, face_size);
 }
@@ -1158,8 +1164,9 @@ int ptb_set_environment_srgb8(ptb_ctx* c, int face_size, const unsigned char* si
     CU(cudaSetDevice(c->device));
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     const size_t n = (size_t)6 * face_size * face_size;
-    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; }
+    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; c->env_faces_bytes = 0; }
     CU(cudaMalloc(&c->d_env_faces, n * sizeof(float4)));
+    c->env_faces_bytes = n * sizeof(float4);
     uchar4* d_raw = nullptr;
     CU(cudaMalloc(&d_raw, n * sizeof(uchar4)));
     int rc = PTB_OK;
@@ -1174,27 +1181,44 @@ int ptb_set_environment_srgb8(ptb_ctx* c, int face_size, const unsigned char* si
     return install_environment(c, face_size);
 }
 
-int ptb_generate_atmosphere(ptb_ctx* c, int face_size, const void* ubo, int ubo_size, const float* light_pos, float light_intensity, int i_steps, int j_steps)
+static int generate_atmosphere(ptb_ctx* c, int face_size, const void* ubo, int ubo_size, const float* light_pos, float light_intensity, int i_steps, int j_steps, bool fast)
 {
     if (!c || !ubo || !light_pos) return fail(PTB_E_INVALID, "null argument");
     if (face_size < 1 || face_size > 8192) return fail(PTB_E_INVALID, "face size %d outside [1,8192]", face_size);
     if (ubo_size < 448) return fail(PTB_E_INVALID, "AtmosphericDataUBO needs 448 bytes, got %d", ubo_size);
     if (i_steps < 0 || j_steps < 0) return fail(PTB_E_INVALID, "negative step count");
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));
+    { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }      // frames in flight still sample the old map
     const size_t bytes = (size_t)6 * face_size * face_size * sizeof(float4);
-    if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; }
-    CU(cudaMalloc(&c->d_env_faces, bytes));
+    if (c->env_faces_bytes != bytes) {      // a slider tick regenerates at the same size: keep the buffers (cudaMalloc of a 2048^2 map costs more than the kernel)
+        if (c->d_env_faces) { CU(cudaFree(c->d_env_faces)); c->d_env_faces = nullptr; c->env_faces_bytes = 0; }
+        CU(cudaMalloc(&c->d_env_faces, bytes));
+        c->env_faces_bytes = bytes;
+    }
     AtmosParams A;
     memcpy(A.ubo, ubo, 448);
     A.light[0] = light_pos[0]; A.light[1] = light_pos[1]; A.light[2] = light_pos[2];
     A.intensity = light_intensity < 0.0f ? 0.0f : light_intensity;   // AtmosphericScatterer.cs:52
     A.i_steps = i_steps; A.j_steps = j_steps; A.size = face_size;
-    dim3 block(8, 8, 1), grid((face_size + 7) / 8, (face_size + 7) / 8, 6);   // AtmosphericScatterer.cs:109
-    atmosphere_kernel<<<grid, block, 0, c->stream>>>(A, c->d_env_faces);
-    c->launches++;
+    if (fast) {
+        const unsigned n = 6u * (unsigned)face_size * (unsigned)face_size;
+        atmosphere_fast_kernel<<<(n + 255u) / 256u, 256, 0, c->stream>>>(A, c->d_env_faces);
+        c->launches++;
+    } else {
+        dim3 block(8, 8, 1), grid((face_size + 7) / 8, (face_size + 7) / 8, 6);   // AtmosphericScatterer.cs:109
+        atmosphere_kernel<<<grid, block, 0, c->stream>>>(A, c->d_env_faces);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     return install_environment(c, face_size);
+}
+int ptb_generate_atmosphere(ptb_ctx* c, int face_size, const void* ubo, int ubo_size, const float* light_pos, float light_intensity, int i_steps, int j_steps)
+{
+    return generate_atmosphere(c, face_size, ubo, ubo_size, light_pos, light_intensity, i_steps, j_steps, false);
+}
+int ptb_generate_atmosphere_fast(ptb_ctx* c, int face_size, const void* ubo, int ubo_size, const float* light_pos, float light_intensity, int i_steps, int j_steps)
+{
+    return generate_atmosphere(c, face_size, ubo, ubo_size, light_pos, light_intensity, i_steps, j_steps, true);
 }
 
 int ptb_read_environment(ptb_ctx* c, float* six_faces)

@@ -68,6 +68,7 @@ class AtmosphericScatterer:
         if size <= 0:
             raise ValueError("size must be positive")
         self._tracer, self.Size = tracer, int(size)
+        self.Fast = False            # True: the live-regeneration kernel (ptb_generate_atmosphere_fast); parity runs keep False
         self.Time = 0.5
         self.ISteps = 50
         self.JSteps = 15
@@ -87,7 +88,7 @@ class AtmosphericScatterer:
         return _scene.atmosphere_light_pos(self.Time)
 
     def Render(self) -> None:
-        self._tracer.GenerateAtmosphere(self.Size, int(self.ISteps), int(self.JSteps), float(self.Time), self._lightIntensity)
+        self._tracer.GenerateAtmosphere(self.Size, int(self.ISteps), int(self.JSteps), float(self.Time), self._lightIntensity, fast=self.Fast)
 
     def SetSize(self, size: int) -> None:
         if size <= 0:
@@ -195,11 +196,13 @@ class PathTracer:
         self._env = None
 
     def GenerateAtmosphere(self, size: int = 256, iSteps: int = 50, jSteps: int = 15, time: float = 0.5,
-                           lightIntensity: float = 15.0) -> None:
-        """AtmosphericScatterer(size).Render() on the GPU, result bound as the EnvironmentMap (MainWindow.cs:174-175,189)."""
+                           lightIntensity: float = 15.0, fast: bool = False) -> None:
+        """AtmosphericScatterer(size).Render() on the GPU, result bound as the EnvironmentMap (MainWindow.cs:174-175,189).
+        fast=True: the live-regeneration kernel (tabulated secondary loop, ~1e-4 relative to the exact one)."""
         ubo = _scene.atmosphere_ubo_bytes()
         lp = np.ascontiguousarray(_scene.atmosphere_light_pos(time), dtype=np.float32)
-        _lib.check(self._L.ptb_generate_atmosphere(self._ctx, size, C.create_string_buffer(ubo, len(ubo)), len(ubo),
+        fn = self._L.ptb_generate_atmosphere_fast if fast else self._L.ptb_generate_atmosphere
+        _lib.check(fn(self._ctx, size, C.create_string_buffer(ubo, len(ubo)), len(ubo),
                                                    lp.ctypes.data_as(C.POINTER(C.c_float)), float(lightIntensity), iSteps, jSteps))
         self._env = None
 

@@ -869,6 +869,31 @@ def test_atmosphere_kernel_bit_exact(ptb, oracle, env256, default_scene, camera)
     pt.Dispose()
 
 
+def test_fast_atmosphere_against_the_exact_kernel(ptb, env256, default_scene, camera):
+    """ptb_generate_atmosphere_fast (the same loops with special-function exp / sqrt / rcp and fused multiply-adds)
+    against ptb_generate_atmosphere (bit-exact with the shader): several sun positions, step counts and sizes.  Tolerance: 1e-3
+    of the map's brightest texel per channel, mean relative error below 1e-4 (the inputs are ~6.4e6 m: a single-precision
+    square root of a squared radius carries ~1 m of noise into exp(-h / 1200 m), in either kernel)."""
+    pt = make_tracer(ptb, env256, 32, 32, default_scene, camera)
+    for size, i_steps, j_steps, time, intensity in ((64, 50, 15, 0.5, 15.0), (96, 30, 8, 0.3, 15.0), (48, 100, 40, 0.07, 22.0), (40, 20, 10, 0.75, 15.0), (33, 12, 3, 0.62, 5.0)):
+        pt.GenerateAtmosphere(size, i_steps, j_steps, time, intensity)
+        exact = pt.ReadEnvironment()[..., :3].astype(np.float64)
+        pt.GenerateAtmosphere(size, i_steps, j_steps, time, intensity, fast=True)
+        fast = pt.ReadEnvironment()[..., :3].astype(np.float64)
+        assert np.isfinite(fast).all()
+        scale = max(exact.max(), 1e-3)          # (a sun far below the horizon leaves the whole map at ~0)
+        err = np.abs(fast - exact)
+        assert err.max() <= 1e-3 * scale, f"size {size} time {time}: max error {err.max():.3e} vs brightest texel {scale:.3e}"
+        lit = exact > 1e-3 * scale
+        if lit.any():
+            assert (err[lit] / exact[lit]).mean() < 1e-4, f"size {size} time {time}: mean relative error {(err[lit] / exact[lit]).mean():.2e}"
+    # and it renders: same image statistics through either environment
+    pt.GenerateAtmosphere(64, 50, 15, 0.5, 15.0); pt.ResetRenderer(); pt.Render(8); a = pt.Result[..., :3].mean()
+    pt.GenerateAtmosphere(64, 50, 15, 0.5, 15.0, fast=True); pt.ResetRenderer(); pt.Render(8); b = pt.Result[..., :3].mean()
+    assert abs(a - b) < 1e-3 * a
+    pt.Dispose()
+
+
 def test_statistics_counters(ptb, oracle, env256, default_scene, camera):
     pt = make_tracer(ptb, env256, 128, 128, default_scene, camera)
     pt.SetStats(True)
