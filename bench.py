@@ -296,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ precision gate (outside every timed region)
     gate = None
     precision = args.precision
-    if precision in ("auto", "fast"):
+    if precision in ("auto", "fast") and not (args.no_gate and precision == "fast"):
         n_gate = cfg["gate_frames"]
         imgs = {}
         for prec in (ptb200.PRECISION_EXACT, ptb200.PRECISION_FAST):
@@ -655,6 +655,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="auto", choices=["auto", "fast", "exact"])
+    ap.add_argument("--no-gate", action="store_true", help="profiling aid: skip the fast-vs-exact check (with --precision fast|exact); a bench line without the gate says so")
     ap.add_argument("--profile", action="store_true", help="profiling aid: only warm-up + timed steps (for runs under ncu); prints no bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
