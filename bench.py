@@ -383,7 +383,9 @@ def run_ours(args, rank, world, local_rank):
     shared = None
     if world > 1 and os.environ.get("PTB_E2E", "scatter") == "scatter":
         try:
-            shared = D.SharedHostFrame(W * H * 12, 2, rank, world)
+            # NUMA placement: every rank first-touches the pages of its own stripes from the CPUs next to its GPU
+            shared = D.SharedHostFrame(W * H * 12, 2, rank, world, stripe_bytes=STRIPE_ROWS * W * 12,
+                                       numa_cpus=D.gpu_numa_cpus(physical_gpu_index(local_rank)))
         except Exception as exc:      # noqa: BLE001  (collective: raised on every rank or on none)
             if rank == 0:
                 print(f"shared host frame unavailable ({exc}); e2e falls back to rank 0's copy of the assembled image", file=sys.stderr, flush=True)
@@ -578,6 +580,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": W * H * (12 if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else 16), "steps": e2e_steps,
                 "format": "RGB32F" if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else "RGBA32F",
                 "last_frame_on_host_equals_device_image": e2e_verified,
+                "host_frame_numa": getattr(shared, "numa", None) if shared is not None else None,
                 "note": ("one Render() per step (no batching: every frame is read back): InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), the frame read back to pinned host memory as RGB32F "
                          "(colour floats bit for bit; the constant alpha 1.0 of compute.glsl:129 is not shipped) through the pipelined read-back (snapshot/pack kernel on the render stream + copy stream, "
                          "overlapping the next Render()); one sync after the last step, inside the timed region; PCIe-bound. "

@@ -289,6 +289,29 @@ class TiledPathTracer:
         return self._finish_gather()
 
 
+def gpu_numa_cpus(device_index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when that cannot be told (no NVML, no sysfs, single node)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        return cpus or None
+    except Exception:      # noqa: BLE001
+        return None
+
+
 class SharedHostFrame:
     """`buffers` full-frame host images in ONE pinned mapping shared by every rank of the node (a /dev/shm file, mapped and
     cudaHostRegister'ed by each process), the destination of PathTracer.ReadResultScatterAsync: each GPU writes its stripes
@@ -296,8 +319,13 @@ class SharedHostFrame:
 
     Collective: every rank of the default process group must construct it together.  Raises on any rank => raises on all."""
 
-    def __init__(self, frame_bytes: int, buffers: int, rank: int, world: int, register: bool = True):
-        """register=False maps the frame without pinning it for CUDA (CPU-only tests of the collective set-up)."""
+    def __init__(self, frame_bytes: int, buffers: int, rank: int, world: int, register: bool = True, stripe_bytes: int = 0,
+                 numa_cpus=None):
+        """register=False maps the frame without pinning it for CUDA (CPU-only tests of the collective set-up).
+        stripe_bytes > 0: NUMA placement — before the buffer is pinned, every rank touches the pages of its own stripes
+        (stripe s of `stripe_bytes` bytes belongs to rank s % world) while running on `numa_cpus` (the CPUs next to its GPU,
+        see gpu_numa_cpus), so the pages a GPU writes over PCIe live in the memory of its own socket.  Without it the whole
+        frame sits on whichever node pinned it first and half the GPUs write across the socket interconnect."""
         import os
         import secrets
 
@@ -328,6 +356,9 @@ class SharedHostFrame:
         try:
             if ok and self.path:
                 self.tensor = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
+                self.numa = self._first_touch(rank, world, int(stripe_bytes), numa_cpus) if stripe_bytes > 0 else "off"
+                if world > 1 and stripe_bytes > 0:
+                    dist.barrier()         # every page has its owner before anybody pins the whole mapping
                 if register:
                     rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 1)     # 1 = cudaHostRegisterPortable
                     if int(rc) != 0:
@@ -352,6 +383,34 @@ class SharedHostFrame:
         if not all_ok:
             self.close()
             raise RuntimeError(f"shared host frame unavailable on some rank ({err or 'see the other ranks'})")
+
+    def _first_touch(self, rank: int, world: int, stripe_bytes: int, numa_cpus) -> str:
+        """Writes one byte into every page of this rank's stripes (all buffers), pinned to `numa_cpus` while doing so."""
+        import os
+        old = None
+        note = "first touch without CPU binding"
+        try:
+            if numa_cpus:
+                old = os.sched_getaffinity(0)
+                allowed = set(numa_cpus) & set(old)
+                if allowed:
+                    os.sched_setaffinity(0, allowed)
+                    note = f"first touch on CPUs {min(allowed)}-{max(allowed)}"
+            view = self.tensor.numpy()
+            page = 4096
+            for b in range(self.buffers):
+                base = b * self.stride
+                s = rank
+                while s * stripe_bytes < self.frame_bytes:
+                    lo = base + s * stripe_bytes
+                    hi = min(base + (s + 1) * stripe_bytes, base + self.frame_bytes)
+                    first = (lo + page - 1) // page * page if s > 0 else lo // page * page     # a page shared with the previous stripe is its owner's
+                    view[first:hi:page] = 0
+                    s += world
+        finally:
+            if old is not None:
+                os.sched_setaffinity(0, old)
+        return note
 
     def ptr(self, k: int) -> int:
         return self.tensor.data_ptr() + (k % self.buffers) * self.stride

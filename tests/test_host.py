@@ -432,7 +432,7 @@ def test_the_references_own_skybox_through_oracle_and_compiled_shader(ptb, oracl
 def test_atmospheric_scatterer_mirror_defaults_and_clamp(ptb):
     """AtmosphericScatterer.cs:11-57,91-94 — property surface without a GPU (Render() is exercised by the GPU tests)."""
     class FakeTracer:
-        def GenerateAtmosphere(self, *a):
+        def GenerateAtmosphere(self, *a, fast=False):
             self.args = a
     t = FakeTracer()
     a = ptb.AtmosphericScatterer(t, 256)
