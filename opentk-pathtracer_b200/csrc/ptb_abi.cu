@@ -148,6 +148,7 @@ struct ptb_ctx {
     // the trace of batch k+1
     cudaGraphicsResource* gl_result = nullptr;   // PathTracer.Result registered through CUDA-GL interop (ptb_register_gl_texture)
     unsigned* d_done = nullptr;      // [kBatchSets] "batch traced" flags (written by the trace's last CTA) + [kBatchSets] a sticky error word
+    int defer_finish = 1;            // SPP == 1: finished pixels go through the warp's completion queue (PTB_DEFER=0 switches it off for A/B runs)
     int blend_ctas = 64;             // grid of the batch blend kernels (a background kernel beside the next batch's trace)
     int batch = 16;
     float4* d_batch_scratch[kBatchSets] = {};
@@ -156,7 +157,7 @@ struct ptb_ctx {
     cudaEvent_t ev_batch_trace[kBatchSets] = {}, ev_batch_blend[kBatchSets] = {};
     bool batch_blend_recorded[kBatchSets] = {};
     unsigned long long batch_seq = 0;
-    bool mega_ring = true;
+    bool mega_ring = true, mega_defer = true;
     int mega_fold_set = -1;
     // ptb_set_kernel_timing: an event pair around every megakernel launch, on the stream it runs on
     bool kt_on = false;
@@ -669,6 +670,7 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.batch = 1;
     P.scratch_stride = 0ull;
     P.ktime = nullptr;
+    P.defer_finish = (c->spp == 1 && c->defer_finish) ? 1 : 0;
     P.done_flag = nullptr; P.done_value = 0u;
     P.off_gcell = c->off_gcell; P.off_gitem = c->off_gitem;
     for (int k = 0; k < 3; ++k) { P.grid_n[k] = c->grid_n[k]; P.grid_lo[k] = c->grid_lo[k]; P.grid_hi[k] = c->grid_hi[k]; P.grid_cell[k] = c->grid_cell[k]; P.grid_inv[k] = c->grid_inv[k]; }
@@ -702,15 +704,21 @@ unsigned long long xch_own_frames(const ptb_ctx* c, unsigned long long seq)
 
 int fold_of(const ptb_ctx* c) { return c->grid_on ? 3 : ((c->n_nodes > 0 || c->n_unbounded > 0) ? 1 : (c->rct_on ? 2 : 0)); }
 
-template <int kFold, class F>
-int with_mega_fold(ptb_ctx* c, bool stats, F&& launch)
-{
-    if (c->mega_ring) return stats ? launch(megakernel<true, true, kFold>) : launch(megakernel<false, true, kFold>);
-    return stats ? launch(megakernel<true, false, kFold>) : launch(megakernel<false, false, kFold>);
-}
 // One megakernel launch of the current configuration (exact or fast translation unit) on `stream`.
 int launch_mega(ptb_ctx* c, const RenderParams& P, bool batch, int smem, cudaStream_t stream);
 
+// ring mode of the next launch: 0 no ring, 1 ring, 2 ring + completion queue (SPP 1, no statistics)
+int ring_mode(const ptb_ctx* c, bool stats) { return !c->mega_ring ? 0 : ((c->mega_defer && c->spp == 1 && c->defer_finish && !stats) ? 2 : 1); }
+
+template <int kFold, class F>
+int with_mega_fold(ptb_ctx* c, bool stats, F&& launch)
+{
+    switch (ring_mode(c, stats)) {
+    case 2: return launch(megakernel<false, 2, kFold>);
+    case 1: return stats ? launch(megakernel<true, 1, kFold>) : launch(megakernel<false, 1, kFold>);
+    default: return stats ? launch(megakernel<true, 0, kFold>) : launch(megakernel<false, 0, kFold>);
+    }
+}
 template <class F>
 int with_mega(ptb_ctx* c, bool stats, F&& launch)
 {
@@ -723,16 +731,19 @@ int with_mega(ptb_ctx* c, bool stats, F&& launch)
 }
 
 template <int kFold>
-int prepare_mega(ptb_ctx* c, int smem, int& with_ring, int& without)
+int prepare_mega(ptb_ctx* c, int smem, int& with_ring, int& with_queue, int& without)
 {
-    CU(cudaFuncSetAttribute(megakernel<false, true, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(megakernel<true, true, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(megakernel<false, false, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(megakernel<true, false, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(megakernel<false, true, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(megakernel<false, false, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, true, kFold>, kMegaThreads, smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, false, kFold>, kMegaThreads, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, 2, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, 1, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<true, 1, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, 0, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<true, 0, kFold>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, 2, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, 1, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(megakernel<false, 0, kFold, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_queue, megakernel<false, 2, kFold>, kMegaThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_ring, megakernel<false, 1, kFold>, kMegaThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&without, megakernel<false, 0, kFold>, kMegaThreads, smem));
     return PTB_OK;
 }
 
@@ -752,15 +763,18 @@ int launch_frame(ptb_ctx* c)
     const int smem = c->stage_bytes;
     const int fold = fold_of(c);
     if (c->mega_smem_set != smem || c->mega_fold_set != fold || c->mega_precision_set != c->precision) {
-        int with_ring = 0, without = 0;
+        int with_ring = 0, with_queue = 0, without = 0;
         if (c->precision == PTB_PRECISION_FAST) {
-            CU(ptb_fast_api::prepare(fold, smem, &with_ring, &without));
+            CU(ptb_fast_api::prepare(fold, smem, &with_ring, &with_queue, &without));
         } else {
-            const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, without) : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, without) : (fold == 3 ? prepare_mega<3>(c, smem, with_ring, without) : prepare_mega<0>(c, smem, with_ring, without)));
+            const int rc = fold == 1 ? prepare_mega<1>(c, smem, with_ring, with_queue, without)
+                         : (fold == 2 ? prepare_mega<2>(c, smem, with_ring, with_queue, without)
+                         : (fold == 3 ? prepare_mega<3>(c, smem, with_ring, with_queue, without) : prepare_mega<0>(c, smem, with_ring, with_queue, without)));
             if (rc != PTB_OK) return rc;
         }
         if (without < 1) return fail(PTB_E_CUDA, "megakernel does not fit an SM with %d bytes of shared memory", smem);
         c->mega_ring = with_ring >= without;          // the ring must not cost a resident CTA
+        c->mega_defer = c->mega_ring && with_queue >= with_ring;      // nor may the completion queue
         c->mega_grid = std::max(c->sm_count, c->sm_count * (c->mega_ring ? with_ring : without) / c->grid_divisor);
         c->mega_smem_set = smem;
         c->mega_fold_set = fold;
@@ -832,14 +846,23 @@ int launch_frame(ptb_ctx* c)
 }
 
 // ---- frame batching (ptb_set_batch) -----------------------------------------------------------------------------------
+template <int kFold, class F>
+int with_mega_batch_fold(ptb_ctx* c, F&& launch)
+{
+    switch (ring_mode(c, false)) {
+    case 2: return launch(megakernel<false, 2, kFold, true>);
+    case 1: return launch(megakernel<false, 1, kFold, true>);
+    default: return launch(megakernel<false, 0, kFold, true>);
+    }
+}
 template <class F>
 int with_mega_batch(ptb_ctx* c, F&& launch)
 {
     switch (fold_of(c)) {
-    case 1: return c->mega_ring ? launch(megakernel<false, true, 1, true>) : launch(megakernel<false, false, 1, true>);
-    case 2: return c->mega_ring ? launch(megakernel<false, true, 2, true>) : launch(megakernel<false, false, 2, true>);
-    case 3: return c->mega_ring ? launch(megakernel<false, true, 3, true>) : launch(megakernel<false, false, 3, true>);
-    default: return c->mega_ring ? launch(megakernel<false, true, 0, true>) : launch(megakernel<false, false, 0, true>);
+    case 1: return with_mega_batch_fold<1>(c, launch);
+    case 2: return with_mega_batch_fold<2>(c, launch);
+    case 3: return with_mega_batch_fold<3>(c, launch);
+    default: return with_mega_batch_fold<0>(c, launch);
     }
 }
 
@@ -867,7 +890,7 @@ int launch_mega(ptb_ctx* c, const RenderParams& P, bool batch, int smem, cudaStr
     RenderParams Pt = P;
     Pt.ktime = slot >= 0 ? c->d_kt + 2 * slot : nullptr;
     if (c->precision == PTB_PRECISION_FAST) {
-        CU(ptb_fast_api::launch(&Pt, fold_of(c), c->mega_ring, batch, c->mega_grid, smem, stream));
+        CU(ptb_fast_api::launch(&Pt, fold_of(c), ring_mode(c, false), batch, c->mega_grid, smem, stream));
     } else {
         const int rc = batch ? with_mega_batch(c, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(Pt); return PTB_OK; })
                              : with_mega(c, c->stats_on, [&](auto k) { k<<<c->mega_grid, kMegaThreads, smem, stream>>>(Pt); return PTB_OK; });
@@ -1014,6 +1037,7 @@ int ptb_create(ptb_ctx** out, int width, int height, int max_spheres, int max_cu
     if (!c) return fail(PTB_E_NOMEM, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (getenv("PTB_DEFER")) c->defer_finish = atoi(getenv("PTB_DEFER")) != 0;
     c->width = width; c->height = height;
     c->max_spheres = max_spheres; c->max_cuboids = max_cuboids;
     c->objects.assign((size_t)max_spheres * kSphereStride + (size_t)max_cuboids * kCuboidStride + 16, 0);

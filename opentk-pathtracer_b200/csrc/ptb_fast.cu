@@ -18,14 +18,14 @@ namespace ptb_fast_api {
 namespace {
 
 template <int kFold, class F>
-cudaError_t pick(bool ring, bool batch, F&& f)
+cudaError_t pick(int ring, bool batch, F&& f)
 {
     using namespace ptb_fast;
-    if (batch) return ring ? f(megakernel<false, true, kFold, true>) : f(megakernel<false, false, kFold, true>);
-    return ring ? f(megakernel<false, true, kFold, false>) : f(megakernel<false, false, kFold, false>);
+    if (batch) return ring == 2 ? f(megakernel<false, 2, kFold, true>) : (ring == 1 ? f(megakernel<false, 1, kFold, true>) : f(megakernel<false, 0, kFold, true>));
+    return ring == 2 ? f(megakernel<false, 2, kFold, false>) : (ring == 1 ? f(megakernel<false, 1, kFold, false>) : f(megakernel<false, 0, kFold, false>));
 }
 template <class F>
-cudaError_t with(int fold, bool ring, bool batch, F&& f)
+cudaError_t with(int fold, int ring, bool batch, F&& f)
 {
     switch (fold) {
     case 1: return pick<1>(ring, batch, f);
@@ -40,19 +40,21 @@ cudaError_t with(int fold, bool ring, bool batch, F&& f)
 size_t params_size() { return sizeof(ptb_fast::RenderParams); }
 int threads() { return ptb_fast::kMegaThreads; }
 
-cudaError_t prepare(int fold, int smem, int* with_ring, int* without)
+cudaError_t prepare(int fold, int smem, int* with_ring, int* with_queue, int* without)
 {
     cudaError_t e = cudaSuccess;
-    for (int ring = 0; ring < 2 && e == cudaSuccess; ++ring)
+    for (int ring = 0; ring < 3 && e == cudaSuccess; ++ring)
         for (int batch = 0; batch < 2 && e == cudaSuccess; ++batch)
-            e = with(fold, ring != 0, batch != 0, [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+            e = with(fold, ring, batch != 0, [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (e != cudaSuccess) return e;
-    e = with(fold, true, false, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_ring, k, ptb_fast::kMegaThreads, smem); });
+    e = with(fold, 2, false, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_queue, k, ptb_fast::kMegaThreads, smem); });
     if (e != cudaSuccess) return e;
-    return with(fold, false, false, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(without, k, ptb_fast::kMegaThreads, smem); });
+    e = with(fold, 1, false, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_ring, k, ptb_fast::kMegaThreads, smem); });
+    if (e != cudaSuccess) return e;
+    return with(fold, 0, false, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(without, k, ptb_fast::kMegaThreads, smem); });
 }
 
-cudaError_t launch(const void* render_params, int fold, bool ring, bool batch, int grid, int smem, cudaStream_t stream)
+cudaError_t launch(const void* render_params, int fold, int ring, bool batch, int grid, int smem, cudaStream_t stream)
 {
     ptb_fast::RenderParams P;
     memcpy(&P, render_params, sizeof P);          // ptb::RenderParams and ptb_fast::RenderParams are the same declaration

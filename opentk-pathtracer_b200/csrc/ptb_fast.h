@@ -6,6 +6,7 @@
 namespace ptb_fast_api {
 size_t params_size();                                                     // sizeof(RenderParams) as ptb_fast.cu sees it
 int threads();
-cudaError_t prepare(int fold, int smem, int* with_ring, int* without);     // shared-memory attributes + occupancy
-cudaError_t launch(const void* render_params, int fold, bool ring, bool batch, int grid, int smem, cudaStream_t stream);
+// ring: 0 no primary-ray ring, 1 ring, 2 ring + completion queue (SPP 1)
+cudaError_t prepare(int fold, int smem, int* with_ring, int* with_queue, int* without);     // shared-memory attributes + occupancy
+cudaError_t launch(const void* render_params, int fold, int ring, bool batch, int grid, int smem, cudaStream_t stream);
 } // namespace ptb_fast_api

@@ -60,6 +60,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v)
 
 constexpr int kMegaThreads = PTB_THREADS;
 constexpr int kQueue = 64;          // primary-ray ring entries per warp (two tiles)
+constexpr int kDoneWords = 11;      // completion-queue entry: direction, throughput, radiance (3 floats each), px | lrow << 16, frame slot | needs-env << 8
 
 // ------------------------------------------------------------------------------------------------------------
 // Launch parameters (by value: they live in the constant bank; UBO 0 is small enough to ride along).
@@ -101,6 +102,7 @@ struct RenderParams {
     float rct_halfG;
     unsigned rct_sm0, rct_sm1;                      // which bits of the mask's low / high word are spheres
     unsigned long long* ktime;                      // optional {min CTA start, max CTA end} in globaltimer ns (ptb_set_kernel_timing)
+    int defer_finish;                               // megakernel with the ring, SPP == 1: finished pixels go through the warp's completion queue
     unsigned* done_flag;                            // optional: the last CTA out stores done_value here (release): the batch's blend
     unsigned done_value;                            //   kernel, already resident, spins on it instead of waiting for a stream event
     // uniform grid for large scenes (megakernel<kFold = 3>): cell_start[] (u16) at off_gcell, items[] (u16) at off_gitem (float4 units)
@@ -366,6 +368,17 @@ __device__ __forceinline__ V3 env_lookup(const float4* __restrict__ env, int N, 
     return mix(top, bot, beta);
 }
 
+// pt:177 — radiance += texture(env, dir).rgb * throughput, written once for the two places a miss is shaded (in the bounce loop,
+// or later from the completion queue) so that the fast build contracts it the same way in both.
+__device__ __forceinline__ V3 add_environment(V3 rad, V3 env, V3 thr)
+{
+#ifdef PTB_FAST
+    return mk(__fmaf_rn(env.x, thr.x, rad.x), __fmaf_rn(env.y, thr.y, rad.y), __fmaf_rn(env.z, thr.z, rad.z));
+#else
+    return rad + env * thr;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // One lane's path state.
 struct Path {
@@ -407,9 +420,12 @@ __device__ __forceinline__ void primary_ray(const RenderParams& P, Path& p)
 }
 
 // pt:140-180 — one iteration of the bounce loop for one lane, after the closest-hit fold gave (T, prim, inside).
-// Returns true while the sample continues.
+// Returns kContinue while the sample continues, kDone when it ended on a surface, kMissed when the ray left the scene; with
+// `defer_env` a miss leaves the environment lookup (pt:177) to the caller.
+constexpr int kContinue = 0, kDone = 1, kMissed = 2;
 template <class Scene>
-__device__ __forceinline__ bool shade(const RenderParams& P, const Scene& sc, Path& p, float T, int prim, bool inside, unsigned long long* stats)
+__device__ __forceinline__ int shade(const RenderParams& P, const Scene& sc, Path& p, float T, int prim, bool inside, unsigned long long* stats,
+                                     bool defer_env = false)
 {
     if (stats) atomicAdd(stats + 1, 1ull);
     if (T != kFloatMax) {
@@ -470,12 +486,12 @@ __device__ __forceinline__ bool shade(const RenderParams& P, const Scene& sc, Pa
         if (!refractive) p.thr = p.thr * mk(m0.x, m0.y, m0.z);
         p.thr = p.thr * rcp(prob);
         const float q = fmax_(p.thr.x, fmax_(p.thr.y, p.thr.z));
-        if (rand01(p.rng) > q) return false;
+        if (rand01(p.rng) > q) return kDone;
         p.thr = p.thr * rcp(q);
-        return ++p.depth < P.ray_depth;
+        return ++p.depth < P.ray_depth ? kContinue : kDone;
     }
-    p.rad = p.rad + env_lookup(P.env, P.env_size, p.d) * p.thr;          // pt:177
-    return false;
+    if (!defer_env) p.rad = add_environment(p.rad, env_lookup(P.env, P.env_size, p.d), p.thr);          // pt:177
+    return kMissed;
 }
 
 template <class Scene>
@@ -485,7 +501,7 @@ __device__ __forceinline__ bool bounce(const RenderParams& P, const Scene& sc, P
     int prim;
     bool inside;
     trace_any(sc, p.o, p.d, T, prim, inside);
-    return shade(P, sc, p, T, prim, inside, stats);
+    return shade(P, sc, p, T, prim, inside, stats) == kContinue;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1007,12 +1023,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // so lanes move from the last pixels of one frame straight into the next frame and only the last frame of a batch drains.
 // The slot travels in bits 12..15 of the ring's pixel word (the host batches only images up to 4096 pixels wide).
 // kFold: 0 = brute-force fold, 1 = shared-memory BVH, 3 = shared-memory grid (large scenes), 2 = ray-classification table (<= 64 primitives).
-template <bool kStats, bool kRing, int kFold, bool kBatch = false>
+// kRing: 0 = idle lanes generate their primary ray in place; 1 = primary rays staged through the per-warp ring; 2 = ring + the
+// completion queue (SPP == 1 only: the host selects it, P.defer_finish documents it).
+template <bool kStats, int kRingMode, int kFold, bool kBatch = false>
 __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const __grid_constant__ RenderParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    constexpr bool kRing = kRingMode != 0;
+    constexpr bool kDefer = kRingMode == 2;
     __shared__ uint32_t s_ring[kRing ? (kMegaThreads / 32) * 8 * kQueue : 1];
+    // Completion queue (per warp, kDoneWords x 64 entries; SPP == 1 only).  A sample that ends — on a surface, or by leaving the
+    // scene with the environment lookup still to do — parks (direction, throughput, radiance, pixel) here and frees its lane at
+    // once; when 32 entries have gathered, the whole warp shades them together: the cubemap lookup and the pixel store then run
+    // with 32 lanes instead of the ~9 that happen to miss in one iteration of the bounce loop.
+    __shared__ uint32_t s_done[kDefer ? (kMegaThreads / 32) * kDoneWords * kQueue : 1];
     float4* sblock = reinterpret_cast<float4*>(smem_raw);
 
     if (P.ktime && threadIdx.x == 0) atomicMin(P.ktime, global_ns());      // launch timing: when the first CTA starts
@@ -1042,6 +1067,26 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
     // that happen to be idle in every iteration of the bounce loop.
     uint32_t* ring = s_ring + (kRing ? (threadIdx.x >> 5) * 8 * kQueue : 0);   // [8][kQueue]: o.xyz d.xyz rng px|lrow<<16
     unsigned q_head = 0, q_count = 0;                                           // warp-uniform
+    uint32_t* doneq = s_done + (kDefer ? (threadIdx.x >> 5) * kDoneWords * kQueue : 0);
+    unsigned dq_count = 0;                                                      // warp-uniform
+    constexpr bool defer = kDefer;
+    // shades `n` queued completions, entries [first, first + n), one per lane
+    auto flush_done = [&](unsigned first, unsigned n) {
+        if (lane < n) {
+            const unsigned e = first + lane;
+            Path f;
+            f.d = mk(__uint_as_float(doneq[0 * kQueue + e]), __uint_as_float(doneq[1 * kQueue + e]), __uint_as_float(doneq[2 * kQueue + e]));
+            f.thr = mk(__uint_as_float(doneq[3 * kQueue + e]), __uint_as_float(doneq[4 * kQueue + e]), __uint_as_float(doneq[5 * kQueue + e]));
+            f.rad = mk(__uint_as_float(doneq[6 * kQueue + e]), __uint_as_float(doneq[7 * kQueue + e]), __uint_as_float(doneq[8 * kQueue + e]));
+            const uint32_t xy = doneq[9 * kQueue + e], fw = doneq[10 * kQueue + e];
+            f.px = (int)(xy & 0xffffu); f.lrow = (int)(xy >> 16); f.fb = (int)(fw & 0xffu);
+            if (fw >> 8) f.rad = add_environment(f.rad, env_lookup(P.env, P.env_size, f.d), f.thr);      // pt:177
+            f.irr = mk(0.0f, 0.0f, 0.0f) + f.rad;                                            // pt:109,123 with SPP == 1
+            if constexpr (kBatch) finish_pixel(P, f, (size_t)f.fb * (size_t)P.scratch_stride);
+            else finish_pixel(P, f);
+        }
+        __syncwarp();
+    };
 
     Path p;
     bool alive = false;         // lane owns an unfinished pixel
@@ -1159,18 +1204,38 @@ __global__ void __launch_bounds__(kMegaThreads, PTB_MIN_BLOCKS) megakernel(const
             else if constexpr (kFold == 2) trace_rct(P, sc, p.o, p.d, T, prim, inside);
             else trace_any(sc, p.o, p.d, T, prim, inside);
         }
-        if (alive) {
-            const bool go = P.ray_depth > 0 ? shade(P, sc, p, T, prim, inside, stats) : false;
-            if (!go) {
-                p.irr = p.irr + p.rad;                // pt:123
-                if (++p.sample < P.spp) fresh = true;
-                else {
-                    if constexpr (kBatch) finish_pixel(P, p, (size_t)p.fb * (size_t)P.scratch_stride);
-                    else finish_pixel(P, p);
+        int ended = kContinue;
+        if (alive) ended = P.ray_depth > 0 ? shade(P, sc, p, T, prim, inside, stats, defer) : kDone;
+        if constexpr (defer) {
+            // SPP == 1: the sample was the pixel's only one.  Park it and free the lane; 32 parked completions are shaded together.
+            const bool park = alive && ended != kContinue;
+            const unsigned pm = __ballot_sync(0xffffffffu, park);
+            if (pm != 0u) {
+                if (park) {
+                    const unsigned e = dq_count + (unsigned)__popc(pm & lt_mask);
+                    doneq[0 * kQueue + e] = __float_as_uint(p.d.x); doneq[1 * kQueue + e] = __float_as_uint(p.d.y); doneq[2 * kQueue + e] = __float_as_uint(p.d.z);
+                    doneq[3 * kQueue + e] = __float_as_uint(p.thr.x); doneq[4 * kQueue + e] = __float_as_uint(p.thr.y); doneq[5 * kQueue + e] = __float_as_uint(p.thr.z);
+                    doneq[6 * kQueue + e] = __float_as_uint(p.rad.x); doneq[7 * kQueue + e] = __float_as_uint(p.rad.y); doneq[8 * kQueue + e] = __float_as_uint(p.rad.z);
+                    doneq[9 * kQueue + e] = (uint32_t)p.px | ((uint32_t)p.lrow << 16);
+                    doneq[10 * kQueue + e] = (kBatch ? (uint32_t)p.fb : 0u) | (ended == kMissed && P.ray_depth > 0 ? 0x100u : 0u);
                     alive = false;
                 }
+                dq_count += (unsigned)__popc(pm);
+                __syncwarp();
+                if (dq_count >= 32u) { dq_count -= 32u; flush_done(dq_count, 32u); }
+            }
+        } else if (alive && ended != kContinue) {
+            p.irr = p.irr + p.rad;                // pt:123
+            if (++p.sample < P.spp) fresh = true;
+            else {
+                if constexpr (kBatch) finish_pixel(P, p, (size_t)p.fb * (size_t)P.scratch_stride);
+                else finish_pixel(P, p);
+                alive = false;
             }
         }
+    }
+    if constexpr (defer) {
+        if (dq_count != 0u) flush_done(0u, dq_count);          // what is still parked when the warp runs out of work
     }
 
     // ---- last CTA out re-arms the counters for the next launch
