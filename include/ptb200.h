@@ -210,7 +210,8 @@ int ptb_set_precision(ptb_ctx* ctx, int precision);
 int ptb_precision(ptb_ctx* ctx);
 /* Ray classification for scenes of 4..64 primitives (default on): rays are classed by origin cell x direction bucket and a
  * table gives each class the set of primitives any of its rays can hit; RayTrace() then tests only those, in index order.
- * cells = grid cells along the longest scene axis (default 13), buckets = direction buckets per cube-face axis (default 12).
+ * cells = grid cells along the longest scene axis (default 18; fewer when the table would exceed 64 MiB), buckets = direction
+ * buckets per cube-face axis (default 16): 32.5 MB for the default scene.
  * The table is rebuilt on the GPU when geometry changes (not on material edits).  Results do not depend on it. */
 int ptb_set_ray_classification(ptb_ctx* ctx, int mode, int cells, int buckets);
 /* Large scenes (>= the BVH threshold): 1 (default) = uniform grid in shared memory walked by a 3-D DDA, 0 = binary BVH.  The

@@ -336,7 +336,7 @@ class PathTracer:
     def Precision(self) -> int:
         return _lib.check(self._L.ptb_precision(self._ctx))
 
-    def SetRayClassification(self, mode: int = 1, cells: int = 13, buckets: int = 12) -> None:
+    def SetRayClassification(self, mode: int = 1, cells: int = 18, buckets: int = 16) -> None:
         """Ray-classification table for scenes of <= 64 primitives (ptb_set_ray_classification); mode 0 = plain fold."""
         _lib.check(self._L.ptb_set_ray_classification(self._ctx, int(mode), int(cells), int(buckets)))
 
