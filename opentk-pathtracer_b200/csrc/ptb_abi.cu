@@ -154,7 +154,7 @@ struct ptb_ctx {
     float4* d_batch_scratch[kBatchSets] = {};
     size_t batch_scratch_frames = 0, batch_scratch_stride = 0;     // frames per set / float4 elements per frame
     unsigned int* d_batch_counters[kBatchSets] = {};
-    cudaEvent_t ev_batch_trace[kBatchSets] = {}, ev_batch_blend[kBatchSets] = {};
+    cudaEvent_t ev_batch_blend[kBatchSets] = {};
     bool batch_blend_recorded[kBatchSets] = {};
     unsigned long long batch_seq = 0;
     bool mega_ring = true, mega_defer = true;
@@ -163,7 +163,7 @@ struct ptb_ctx {
     bool kt_on = false;
     unsigned long long* d_kt = nullptr;        // 8 x {min CTA start, max CTA end}
     unsigned long long* h_kt = nullptr;        // pinned: [0..15] results, [16..17] the initial pair {~0, 0}
-    cudaEvent_t kt_a[8] = {}, kt_b[8] = {};
+    cudaEvent_t kt_b[8] = {};             // recorded behind each timed launch's read-back: its results are on the host
     int kt_frames[8] = {};
     bool kt_used[8] = {};
     unsigned kt_next = 0;
@@ -939,7 +939,6 @@ int ensure_batch(ptb_ctx* c, int frames)
         if (!c->d_batch_counters[s]) {
             CU(cudaMalloc(&c->d_batch_counters[s], 2 * sizeof(unsigned int)));
             CU(cudaMemsetAsync(c->d_batch_counters[s], 0, 2 * sizeof(unsigned int), c->stream));
-            CU(cudaEventCreateWithFlags(&c->ev_batch_trace[s], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->ev_batch_blend[s], cudaEventDisableTiming));
             { const int rc = mark_inputs(c); if (rc != PTB_OK) return rc; }
         }
@@ -975,7 +974,6 @@ int launch_batch(ptb_ctx* c, int frames)
     P.done_value = (unsigned)(c->batch_seq + 1ull);
     const int rc = launch_mega(c, P, true, smem, ts);
     if (rc != PTB_OK) return rc;
-    CU(cudaEventRecord(c->ev_batch_trace[s], ts));
     cudaStream_t bs = c->blend_stream;
     if (c->seen_version[kMaxOverlap] != c->inputs_version) { CU(cudaStreamWaitEvent(bs, c->ev_inputs, 0)); c->seen_version[kMaxOverlap] = c->inputs_version; }
     const size_t n = (size_t)c->local_rows * c->width;
@@ -1079,7 +1077,6 @@ void ptb_destroy(ptb_ctx* c)
     }
     for (int i = 0; i < kBatchSets; ++i) {
         cudaFree(c->d_batch_scratch[i]); cudaFree(c->d_batch_counters[i]);
-        if (c->ev_batch_trace[i]) cudaEventDestroy(c->ev_batch_trace[i]);
         if (c->ev_batch_blend[i]) cudaEventDestroy(c->ev_batch_blend[i]);
     }
     exchange_close(c);
@@ -1092,7 +1089,7 @@ void ptb_destroy(ptb_ctx* c)
     cudaFree(c->d_image); cudaFree(c->d_counters); cudaFree(c->d_stats);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_stage[i]); if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
-    for (int i = 0; i < 8; ++i) { if (c->kt_a[i]) cudaEventDestroy(c->kt_a[i]); if (c->kt_b[i]) cudaEventDestroy(c->kt_b[i]); }
+    for (int i = 0; i < 8; ++i) if (c->kt_b[i]) cudaEventDestroy(c->kt_b[i]);
     cudaFree(c->d_kt); if (c->h_kt) cudaFreeHost(c->h_kt);
     cudaFree(c->d_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1716,7 +1713,7 @@ int ptb_set_kernel_timing(ptb_ctx* c, int enabled)
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     { const int rc = sync_all(c); if (rc != PTB_OK) return rc; }
     for (int i = 0; i < 8; ++i) {
-        if (enabled && !c->kt_a[i]) { CU(cudaEventCreate(&c->kt_a[i])); CU(cudaEventCreate(&c->kt_b[i])); }
+        if (enabled && !c->kt_b[i]) CU(cudaEventCreateWithFlags(&c->kt_b[i], cudaEventDisableTiming));
         if (enabled && !c->d_kt) {
             CU(cudaMalloc(&c->d_kt, 16 * sizeof(unsigned long long)));
             CU(cudaMallocHost(&c->h_kt, 18 * sizeof(unsigned long long)));

@@ -51,3 +51,29 @@ def test_committed_b200_lines_carry_the_contract_keys():
         assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         if n == 1:
             assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_committed_round2_lines_carry_the_contract_keys():
+    """This round's B200 lines (the final kernel, one GPU and eight): every contract key, a roofline whose fraction follows from
+    its own numbers and whose kernel time fits the step, a passed precision gate, a verified read-back and — at N > 1 — the
+    exchanged frame checked against one GPU rendering alone."""
+    for name, n, cfg in (("r02_bench_c2_n1_final.json", 1, "c2"), ("r02_bench_c4_n1_final.json", 1, "c4"), ("r02_bench_c3_n1_final.json", 1, "c3"),
+                         ("r02_bench_c2_n8_final.json", 8, "c2"), ("r02_bench_c4_n8_final.json", 8, "c4")):
+        d = _last_json_line(open(os.path.join(ROOT, "profiles", name)).read())
+        assert BASE_KEYS | {"roofline", "clocks", "precision_gate", "exact", "exchange_check"} <= set(d), name
+        assert d["n_gpus"] == n and d["scaling"] == "strong" and d["data"] == "synthetic" and d["config"]["name"] == cfg
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel_ms", "kernel_ms_per_launch", "frames_per_launch"} <= set(r)
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["bound"] == "hbm"
+        assert r["kernel_ms"] <= d["ms_per_step"] * 1.08, name              # consecutive launches overlap a little in the drain
+        g = d["precision_gate"]
+        assert g["tolerance"] == 1e-6 and g["passed"] == (max(g["per_channel_mse_fast_vs_exact"]) < 1e-6)
+        assert ("fast" in d["config"]["precision"][:5]) == g["passed"]       # the fast build is quoted only inside the tolerance
+        assert (d["exact"] is None) == (not g["passed"])
+        e = d["e2e"]
+        assert e["value"] > 0 and e["last_frame_on_host_equals_device_image"] is True
+        assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["exchange_check"] is None
+        else:
+            assert d["exchange_check"]["exchange_equals_single_gpu"] is True
