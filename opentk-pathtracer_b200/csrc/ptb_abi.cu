@@ -92,7 +92,8 @@ struct ptb_ctx {
     int large_mode = 1;              // 0 = BVH, 1 = grid
     float grid_density = 4.0f;       // target cells per binned primitive (ptb_set_grid_density; C3: 1 / 2 / 4 / 8 -> 990 / 1007 / 1030 / 886 Msamples/s)
     bool grid_on = false;
-    int grid_n[3] = {}, off_gcell = 0, off_gitem = 0;
+    int grid_n[3] = {}, off_gcell = 0, off_gsph = 0, off_gitem = 0;
+    std::vector<unsigned char> grid_cell_spheres;
     float grid_lo[3] = {}, grid_hi[3] = {}, grid_cell[3] = {}, grid_inv[3] = {};
     std::vector<unsigned short> grid_cell_start, grid_items;
     size_t env_faces_bytes = 0, env_padded_bytes = 0;
@@ -513,7 +514,7 @@ int build_rct(ptb_ctx* c)
 // lists (the caller then builds the BVH instead).
 bool build_grid(ptb_ctx* c)
 {
-    c->grid_on = false; c->grid_cell_start.clear(); c->grid_items.clear();
+    c->grid_on = false; c->grid_cell_start.clear(); c->grid_items.clear(); c->grid_cell_spheres.clear();
     c->bvh_nodes.clear(); c->bvh_pidx.clear(); c->n_nodes = 0; c->n_unbounded = 0; c->bvh_tau = 0.0f; c->bvh_D = 0.0f;
     const int n = c->n_spheres + c->n_cuboids;
     if (n < c->bvh_threshold || n >= 65535) return false;
@@ -576,9 +577,16 @@ bool build_grid(ptb_ctx* c)
                 for (int x = a[0]; x <= b[0]; ++x) { lists[((size_t)z * c->grid_n[1] + y) * c->grid_n[0] + x].push_back((unsigned short)i); ++total; }
     }
     if (total >= 65535) return false;
+    // per cell an offset into the item list and the number of its items that are spheres (items ascend, so the spheres come
+    // first): the kernel runs two uniform loops per cell instead of one loop that branches on the primitive type
     c->grid_cell_start.resize((size_t)ncell + 1);
+    c->grid_cell_spheres.assign((size_t)ncell, 0);
     for (int q = 0; q < ncell; ++q) {
         c->grid_cell_start[q] = (unsigned short)c->grid_items.size();
+        size_t n_sph = 0;
+        for (unsigned short v : lists[q]) if ((int)v < c->n_spheres) ++n_sph;
+        if (n_sph > 255) return false;
+        c->grid_cell_spheres[q] = (unsigned char)n_sph;
         c->grid_items.insert(c->grid_items.end(), lists[q].begin(), lists[q].end());      // ascending index inside a cell (binned is ascending)
     }
     c->grid_cell_start[ncell] = (unsigned short)c->grid_items.size();
@@ -588,20 +596,24 @@ bool build_grid(ptb_ctx* c)
 
 void layout_block(ptb_ctx* c)
 {
-    // float4 units: [spheres][1/r][cuboid lo][cuboid hi][BVH nodes][BVH index list] | [materials]
+    // float4 units: [spheres][slabs][BVH nodes][always-tested list + BVH leaves][grid offsets][grid sphere counts][grid items] | [1/r][materials]
+    // (what follows the bar is needed once per hit: small scenes stage it too, large scenes leave it in HBM / L2)
     const int nS = c->n_spheres, nC = c->n_cuboids;
-    c->off_aux = (nS + 3) & ~3;                 // the sphere array is padded to a multiple of four (never-hit dummies)
-    c->off_cmin = c->off_aux + (nS + 3) / 4;
+    const int n4 = (nS + 3) & ~3;                 // the sphere array is padded to a multiple of four (never-hit dummies)
+    c->off_cmin = n4;
     c->off_cmax = c->off_cmin + 1;                // slab bounds interleaved: lo0, hi0, lo1, hi1, ...
     c->off_nodes = c->off_cmin + 2 * nC;
     c->off_pidx = c->off_nodes + 2 * c->n_nodes;
     c->off_gcell = c->off_pidx + ((int)c->bvh_pidx.size() + 3) / 4;
-    c->off_gitem = c->off_gcell + (c->grid_on ? ((int)c->grid_cell_start.size() + 7) / 8 : 0);
-    c->off_mat = c->off_gitem + (c->grid_on ? ((int)c->grid_items.size() + 7) / 8 : 0);
+    c->off_gsph = c->off_gcell + (c->grid_on ? ((int)c->grid_cell_start.size() + 7) / 8 : 0);
+    c->off_gitem = c->off_gsph + (c->grid_on ? ((int)c->grid_cell_spheres.size() + 15) / 16 : 0);
+    const int off_tail = c->off_gitem + (c->grid_on ? ((int)c->grid_items.size() + 7) / 8 : 0);
+    c->off_aux = off_tail;
+    c->off_mat = c->off_aux + (nS + 3) / 4;
     c->block_bytes = (c->off_mat + (nS + nC) * 4) * 16;
     if (c->block_bytes < 16) c->block_bytes = 16;
     // with a BVH the materials stay in HBM / L2 (only the winner's 64 B are read per bounce) so more CTAs fit an SM
-    c->stage_bytes = c->n_nodes > 0 || c->n_unbounded > 0 || c->grid_on ? std::max(16, c->off_mat * 16) : c->block_bytes;
+    c->stage_bytes = c->n_nodes > 0 || c->n_unbounded > 0 || c->grid_on ? std::max(16, c->off_aux * 16) : c->block_bytes;
 }
 
 int sync_scene(ptb_ctx* c)
@@ -641,6 +653,7 @@ int sync_scene(ptb_ctx* c)
     if (!c->bvh_pidx.empty()) CU(cudaMemcpyAsync(c->d_block + c->off_pidx, c->bvh_pidx.data(), c->bvh_pidx.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (c->grid_on) {
         CU(cudaMemcpyAsync(c->d_block + c->off_gcell, c->grid_cell_start.data(), c->grid_cell_start.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_block + c->off_gsph, c->grid_cell_spheres.data(), c->grid_cell_spheres.size(), cudaMemcpyHostToDevice, c->stream));
         if (!c->grid_items.empty()) CU(cudaMemcpyAsync(c->d_block + c->off_gitem, c->grid_items.data(), c->grid_items.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, c->stream));
     }
     if (c->n_nodes > 0 || !c->bvh_pidx.empty() || c->grid_on) CU(cudaStreamSynchronize(c->stream));     // the host vectors may be rebuilt before the copy ran
@@ -676,7 +689,7 @@ void fill_params(ptb_ctx* c, RenderParams& P)
     P.ktime = nullptr;
     P.defer_finish = (c->spp == 1 && c->defer_finish) ? 1 : 0;
     P.done_flag = nullptr; P.done_value = 0u;
-    P.off_gcell = c->off_gcell; P.off_gitem = c->off_gitem;
+    P.off_gcell = c->off_gcell; P.off_gsph = c->off_gsph; P.off_gitem = c->off_gitem;
     for (int k = 0; k < 3; ++k) { P.grid_n[k] = c->grid_n[k]; P.grid_lo[k] = c->grid_lo[k]; P.grid_hi[k] = c->grid_hi[k]; P.grid_cell[k] = c->grid_cell[k]; P.grid_inv[k] = c->grid_inv[k]; }
     P.rct = c->rct_on ? c->d_rct : nullptr;
     for (int k = 0; k < 3; ++k) { P.rct_lo[k] = c->rct_lo[k]; P.rct_inv[k] = c->rct_inv[k]; P.rct_n[k] = c->rct_n[k]; }

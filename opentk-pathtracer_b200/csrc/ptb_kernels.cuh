@@ -106,7 +106,7 @@ struct RenderParams {
     unsigned* done_flag;                            // optional: the last CTA out stores done_value here (release): the batch's blend
     unsigned done_value;                            //   kernel, already resident, spins on it instead of waiting for a stream event
     // uniform grid for large scenes (megakernel<kFold = 3>): cell_start[] (u16) at off_gcell, items[] (u16) at off_gitem (float4 units)
-    int off_gcell, off_gitem, grid_n[3];
+    int off_gcell, off_gsph, off_gitem, grid_n[3];
     float grid_lo[3], grid_hi[3], grid_cell[3], grid_inv[3];
     float rct_nf[3];                                // cells per axis as floats (range test of the cell coordinates)
     unsigned long long rct_valid;                   // the mask of every existing primitive: what an unclassifiable ray tests
@@ -123,7 +123,8 @@ struct PackedScene {           // SoA block in shared memory
     float tau;                 // slack on ray parameters in the conservative box tests
     int nS, nC, off_aux, off_cmin, off_cmax, off_mat;
     __device__ __forceinline__ float4 sphere(int i) const { return base[i]; }                 // (c, r*r)
-    __device__ __forceinline__ float sphere_rcp_r(int i) const { return reinterpret_cast<const float*>(base + off_aux)[i]; }
+    // 1 / radius, needed once per hit: with the materials in the shared block for small scenes, with them in HBM / L2 for large ones
+    __device__ __forceinline__ float sphere_rcp_r(int i) const { return reinterpret_cast<const float*>(mats + off_aux)[i]; }
     // slab bounds are interleaved (lo0, hi0, lo1, hi1, ...; off_cmax == off_cmin + 1): one address computation per cuboid
     __device__ __forceinline__ float4 cmin(int i) const { return base[off_cmin + 2 * i]; }
     __device__ __forceinline__ float4 cmax(int i) const { return base[off_cmax + 2 * i]; }
@@ -679,73 +680,108 @@ __device__ __forceinline__ void trace_bvh(const PackedScene& sc, V3 o, V3 d, flo
 // node, and all lanes of a warp run the same short loop body: C3 spends ~x.x k instead of 11.8 k lane-instructions per sample.
 struct GridView {
     const unsigned short* cell_start;      // n_cells + 1 offsets into items
+    const unsigned char* cell_spheres;     // per cell: how many of its items are spheres (items ascend, so they come first)
     const unsigned short* items;
     int nx, ny, nz;
     float lo[3], inv_cell[3], cell[3], hi[3];
 };
-__device__ __forceinline__ void grid_pass(const PackedScene& sc, const GridView& G, V3 o, V3 d, const RayInv& ri, int after, float limit, float best,
-                                          uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx, float& k_t2, int* visits = nullptr)
-{
-    key = 0xffffffffu; idx = 0x7fffffff; t1b = kFloatMax; t2b = 0.0f; k_idx = -1; k_t2 = 0.0f;
-    for (int u = 0; u < sc.n_unbounded; ++u) bvh_consider(sc, sc.pidx[u], o, d, ri, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
-    // the part of the ray inside the grid: [tn, tf] (NaN-dropping min/max: an axis-parallel ray inside the slab gives -inf / +inf)
-    const V3 inv = ri.inv;
-    const float ax = (G.lo[0] - o.x) * inv.x, bx = (G.hi[0] - o.x) * inv.x;
-    const float ay = (G.lo[1] - o.y) * inv.y, by = (G.hi[1] - o.y) * inv.y;
-    const float az = (G.lo[2] - o.z) * inv.z, bz = (G.hi[2] - o.z) * inv.z;
-    const float tn = fmax_(0.0f, fmax_(fmin_(ax, bx), fmax_(fmin_(ay, by), fmin_(az, bz))));
-    const float tf = fmin_(fmax_(ax, bx), fmin_(fmax_(ay, by), fmax_(az, bz)));
-    if (!(tn <= tf)) return;
-    const V3 p = mk(__fmaf_rn(d.x, tn, o.x), __fmaf_rn(d.y, tn, o.y), __fmaf_rn(d.z, tn, o.z));
-    int ix = min(G.nx - 1, max(0, __float2int_rd((p.x - G.lo[0]) * G.inv_cell[0])));
-    int iy = min(G.ny - 1, max(0, __float2int_rd((p.y - G.lo[1]) * G.inv_cell[1])));
-    int iz = min(G.nz - 1, max(0, __float2int_rd((p.z - G.lo[2]) * G.inv_cell[2])));
-    const int sx = d.x > 0.0f ? 1 : -1, sy = d.y > 0.0f ? 1 : -1, sz = d.z > 0.0f ? 1 : -1;
-    const float inf = __uint_as_float(0x7f800000u);
-    // parameter at which the ray leaves the current cell along each axis; a zero component never leaves
-    float tx = d.x != 0.0f ? (G.lo[0] + (float)(ix + (sx > 0 ? 1 : 0)) * G.cell[0] - o.x) * inv.x : inf;
-    float ty = d.y != 0.0f ? (G.lo[1] + (float)(iy + (sy > 0 ? 1 : 0)) * G.cell[1] - o.y) * inv.y : inf;
-    float tz = d.z != 0.0f ? (G.lo[2] + (float)(iz + (sz > 0 ? 1 : 0)) * G.cell[2] - o.z) * inv.z : inf;
-    const float dx = G.cell[0] * fabsf(inv.x), dy = G.cell[1] * fabsf(inv.y), dz = G.cell[2] * fabsf(inv.z);
-    for (int guard = G.nx + G.ny + G.nz + 3; guard > 0; --guard) {
-        const int cell = (iz * G.ny + iy) * G.nx + ix;
-        const int first = G.cell_start[cell], last = G.cell_start[cell + 1];
-        if (visits) ++*visits;
-        for (int j = first; j < last; ++j) bvh_consider(sc, G.items[j], o, d, ri, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
-        const float t_exit = fmin_(tx, fmin_(ty, tz));
-        if (best + sc.tau < t_exit) break;                  // nothing nearer can start in a cell that begins at or after t_exit
-        if (tx <= ty && tx <= tz) { ix += sx; if ((unsigned)ix >= (unsigned)G.nx) break; tx += dx; }
-        else if (ty <= tz) { iy += sy; if ((unsigned)iy >= (unsigned)G.ny) break; ty += dy; }
-        else { iz += sz; if ((unsigned)iz >= (unsigned)G.nz) break; tz += dz; }
-    }
-}
 __device__ __forceinline__ GridView make_grid_view(const RenderParams& P, const float4* smem_block)
 {
     GridView G;
     G.cell_start = reinterpret_cast<const unsigned short*>(smem_block + P.off_gcell);
+    G.cell_spheres = reinterpret_cast<const unsigned char*>(smem_block + P.off_gsph);
     G.items = reinterpret_cast<const unsigned short*>(smem_block + P.off_gitem);
     G.nx = P.grid_n[0]; G.ny = P.grid_n[1]; G.nz = P.grid_n[2];
     for (int k = 0; k < 3; ++k) { G.lo[k] = P.grid_lo[k]; G.hi[k] = P.grid_hi[k]; G.cell[k] = P.grid_cell[k]; G.inv_cell[k] = P.grid_inv[k]; }
     return G;
+}
+// closed-form accumulation of one candidate's (t1, t2): K = the largest containing index, else the first-index argmin of t1
+__device__ __forceinline__ void grid_accumulate(int i, float a1, float a2, float limit, uint32_t& key, int& idx, float& t1b, float& t2b, int& k_idx,
+                                                float& k_t2, float& best)
+{
+    if (a1 < 0.0f) { if (i > k_idx) { k_idx = i; k_t2 = a2; } }
+    else if (a1 < limit) {
+        const uint32_t kk = __float_as_uint(a1) & 0x7fffffffu;
+        if (kk < key || (kk == key && i < idx)) { key = kk; idx = i; t1b = a1; t2b = a2; best = fmin_(best, a1); }
+    }
 }
 __device__ __forceinline__ void trace_grid(const PackedScene& sc, const GridView& G, V3 o, V3 d, float& T, int& prim, bool& inside, int* visits = nullptr)
 {
     // non-finite rays take the plain fold, as in trace_bvh
     const float fin = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
     if (!(fin <= kFloatMax)) { trace(sc, o, d, T, prim, inside); return; }
-    const RayInv inv = ray_inverse(o, d);
-    uint32_t key; int idx, k_idx; float t1, t2, k_t2;
-    grid_pass(sc, G, o, d, inv, -1, kFloatMax, kFloatMax, key, idx, t1, t2, k_idx, k_t2, visits);
-    if (k_idx < 0) {
-        const bool found = key != 0xffffffffu;
-        T = found ? t1 : kFloatMax; prim = found ? idx : -1; inside = found && (t1 == t2);
-        return;
+    const RayInv ri = ray_inverse(o, d);
+    const V3 inv = ri.inv;
+    // the part of the ray inside the grid: [tn, tf] (NaN-dropping min/max: an axis-parallel ray inside the slab gives -inf / +inf)
+    const float gax = (G.lo[0] - o.x) * inv.x, gbx = (G.hi[0] - o.x) * inv.x;
+    const float gay = (G.lo[1] - o.y) * inv.y, gby = (G.hi[1] - o.y) * inv.y;
+    const float gaz = (G.lo[2] - o.z) * inv.z, gbz = (G.hi[2] - o.z) * inv.z;
+    const float tn = fmax_(0.0f, fmax_(fmin_(gax, gbx), fmax_(fmin_(gay, gby), fmin_(gaz, gbz))));
+    const float tf = fmin_(fmax_(gax, gbx), fmin_(fmax_(gay, gby), fmax_(gaz, gbz)));
+    const bool enters = tn <= tf;
+    const V3 p = mk(__fmaf_rn(d.x, tn, o.x), __fmaf_rn(d.y, tn, o.y), __fmaf_rn(d.z, tn, o.z));
+    const int ix0 = min(G.nx - 1, max(0, __float2int_rd((p.x - G.lo[0]) * G.inv_cell[0])));
+    const int iy0 = min(G.ny - 1, max(0, __float2int_rd((p.y - G.lo[1]) * G.inv_cell[1])));
+    const int iz0 = min(G.nz - 1, max(0, __float2int_rd((p.z - G.lo[2]) * G.inv_cell[2])));
+    const int sx = d.x > 0.0f ? 1 : -1, sy = d.y > 0.0f ? 1 : -1, sz = d.z > 0.0f ? 1 : -1;
+    const float inf = __uint_as_float(0x7f800000u);
+    // parameter at which the ray leaves its first cell along each axis; a zero component never leaves
+    const float tx0 = d.x != 0.0f ? (G.lo[0] + (float)(ix0 + (sx > 0 ? 1 : 0)) * G.cell[0] - o.x) * inv.x : inf;
+    const float ty0 = d.y != 0.0f ? (G.lo[1] + (float)(iy0 + (sy > 0 ? 1 : 0)) * G.cell[1] - o.y) * inv.y : inf;
+    const float tz0 = d.z != 0.0f ? (G.lo[2] + (float)(iz0 + (sz > 0 ? 1 : 0)) * G.cell[2] - o.z) * inv.z : inf;
+    const float dx = G.cell[0] * fabsf(inv.x), dy = G.cell[1] * fabsf(inv.y), dz = G.cell[2] * fabsf(inv.z);
+
+    // pass 0 finds K and the first-index argmin of the entry distance; pass 1 (only when K exists) looks at later primitives that
+    // beat t2_K.  One loop body for both passes: the walk is the same, only (after, limit, best) differ — and the code is half the
+    // size, which matters: the first version of this kernel spent more issue slots waiting for instructions than for data.
+    int after = -1, K = -1;
+    float limit = kFloatMax, best = kFloatMax, t2K = 0.0f;
+    uint32_t key; int idx, k_idx; float t1b, t2b, k_t2;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        key = 0xffffffffu; idx = 0x7fffffff; t1b = kFloatMax; t2b = 0.0f; k_idx = -1; k_t2 = 0.0f;
+        for (int u = 0; u < sc.n_unbounded; ++u) bvh_consider(sc, sc.pidx[u], o, d, ri, after, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
+        if (enters) {
+            int ix = ix0, iy = iy0, iz = iz0;
+            float tx = tx0, ty = ty0, tz = tz0;
+            for (int guard = G.nx + G.ny + G.nz + 3; guard > 0; --guard) {
+                const int cell = (iz * G.ny + iy) * G.nx + ix;
+                const int first = G.cell_start[cell], last = G.cell_start[cell + 1], mid = first + G.cell_spheres[cell];
+                if (visits) ++*visits;
+                for (int j = first; j < mid; ++j) {                 // the cell's spheres
+                    const int i = G.items[j];
+                    float b, disc;
+                    sphere_terms(sc.base[i], o, d, b, disc);
+                    if (i > after && !(disc < 0.0f)) {
+                        const float sq = fsqrt(disc);
+                        const float a1 = -b - sq, a2 = -b + sq;
+                        if (a1 <= a2 && a2 > 0.0f) grid_accumulate(i, a1, a2, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
+                    }
+                }
+                for (int j = mid; j < last; ++j) {                  // then its cuboids
+                    const int i = G.items[j];
+                    float a1, a2;
+                    slab_terms(sc.cmin(i - sc.nS), sc.cmax(i - sc.nS), o, ri, a1, a2);
+                    if (i > after && a1 <= a2 && a2 > 0.0f) grid_accumulate(i, a1, a2, limit, key, idx, t1b, t2b, k_idx, k_t2, best);
+                }
+                const float t_exit = fmin_(tx, fmin_(ty, tz));
+                if (best + sc.tau < t_exit) break;                  // nothing nearer can start in a cell that begins at or after t_exit
+                if (tx <= ty && tx <= tz) { ix += sx; if ((unsigned)ix >= (unsigned)G.nx) break; tx += dx; }
+                else if (ty <= tz) { iy += sy; if ((unsigned)iy >= (unsigned)G.ny) break; ty += dy; }
+                else { iz += sz; if ((unsigned)iz >= (unsigned)G.nz) break; tz += dz; }
+            }
+        }
+        if (pass == 0) {
+            if (k_idx < 0) {
+                const bool found = key != 0xffffffffu;
+                T = found ? t1b : kFloatMax; prim = found ? idx : -1; inside = found && (t1b == t2b);
+                return;
+            }
+            K = k_idx; t2K = k_t2;
+            after = K; limit = inf; best = t2K;
+        }
     }
-    const int K = k_idx;
-    const float t2K = k_t2;
-    int k2; float k2t;
-    grid_pass(sc, G, o, d, inv, K, __uint_as_float(0x7f800000u), t2K, key, idx, t1, t2, k2, k2t, visits);
-    if (key != 0xffffffffu && t1 < t2K) { T = t1; prim = idx; inside = (t1 == t2); }
+    if (key != 0xffffffffu && t1b < t2K) { T = t1b; prim = idx; inside = (t1b == t2b); }
     else { T = t2K; prim = K; inside = true; }
 }
 
