@@ -217,7 +217,7 @@ int ptb_set_ray_classification(ptb_ctx* ctx, int mode, int cells, int buckets);
 /* Large scenes (>= the BVH threshold): 1 (default) = uniform grid in shared memory walked by a 3-D DDA, 0 = binary BVH.  The
  * grid falls back to the BVH when its lists do not fit 16-bit offsets.  Results do not depend on it. */
 int ptb_set_large_scene_mode(ptb_ctx* ctx, int mode);
-int ptb_set_grid_density(ptb_ctx* ctx, float cells_per_primitive);   /* grid resolution: target cells per primitive (default 4; at most 32 per axis) */
+int ptb_set_grid_density(ptb_ctx* ctx, float cells_per_primitive);   /* grid resolution: target cells per primitive (default 3; at most 32 per axis) */
 /* Scenes with at least this many primitives are traced through the shared-memory BVH, smaller ones by the brute-force fold
  * (default 96).  Results do not depend on it (the hierarchy only removes primitives that fail the exact test). */
 int ptb_set_bvh_threshold(ptb_ctx* ctx, int primitives);

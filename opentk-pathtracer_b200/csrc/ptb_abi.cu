@@ -90,7 +90,7 @@ struct ptb_ctx {
     std::vector<unsigned char> rct_geometry;   // the geometry bytes the table was built from (material edits do not rebuild it)
     // uniform grid for large scenes (trace_grid): the default above bvh_threshold; the BVH stays as the fallback / alternative
     int large_mode = 1;              // 0 = BVH, 1 = grid
-    float grid_density = 4.0f;       // target cells per binned primitive (ptb_set_grid_density; C3: 1 / 2 / 4 / 8 -> 990 / 1007 / 1030 / 886 Msamples/s)
+    float grid_density = 3.0f;       // target cells per binned primitive (ptb_set_grid_density; C3: 2 / 3 / 4 / 6 -> 1247 / 1271 / 1254 / 1115 Msamples/s)
     bool grid_on = false;
     int grid_n[3] = {}, off_gcell = 0, off_gsph = 0, off_gitem = 0;
     std::vector<unsigned char> grid_cell_spheres;
