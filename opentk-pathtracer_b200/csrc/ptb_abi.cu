@@ -1472,6 +1472,11 @@ int ptb_synchronize(ptb_ctx* c)
     if (!c) return fail(PTB_E_INVALID, "ctx is null");
     CU(cudaStreamSynchronize(c->stream));
     if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
+    if (c->d_done) {       // the batch blends' sticky flag: a blend that gave up waiting for its trace
+        unsigned gave_up = 0;
+        CU(cudaMemcpy(&gave_up, c->d_done + kBatchSets, sizeof gave_up, cudaMemcpyDeviceToHost));
+        if (gave_up) return fail(PTB_E_STATE, "a batch blend kernel gave up waiting for its trace (ten-minute time-out): the image is incomplete");
+    }
     return PTB_OK;
 }
 

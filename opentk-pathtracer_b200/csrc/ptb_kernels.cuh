@@ -975,7 +975,9 @@ __device__ __forceinline__ void wait_for_trace(const BatchWait& Wt)
         const unsigned long long t0 = global_ns();
         while ((int)(ld_acquire_gpu(Wt.flag) - Wt.value) < 0) {
             __nanosleep(500);
-            if (global_ns() - t0 > 20000000000ull) { atomicExch(Wt.error, 1u); break; }
+            // ten minutes: far beyond any batch (the host only launches this kernel behind a trace that did launch); a trace that
+            // never finishes must not wedge the GPU for ever, so the wait gives up and raises the sticky flag ptb_synchronize reports
+            if (global_ns() - t0 > 600000000000ull) { atomicExch(Wt.error, 1u); break; }
         }
     }
     __syncthreads();
