@@ -487,6 +487,23 @@ def run_ours(args, rank, world, local_rank):
     except Exception as exc:      # noqa: BLE001
         e2e_verified = f"check failed to run: {exc}"
 
+    # what this box's PCIe link gives a plain pinned device->host copy (outside every timed region): the ceiling of
+    # the e2e number, and it varies between boxes of the pool (57 GB/s on most, ~20 GB/s seen on one)
+    pcie_gbps = None
+    if rank == 0:
+        try:
+            probe_d = torch.empty(128 << 20, dtype=torch.uint8, device=dev)
+            probe_h = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+            probe_h.copy_(probe_d, non_blocking=True); torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(4):
+                probe_h.copy_(probe_d, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            pcie_gbps = 4 * (128 << 20) / (time.perf_counter() - t0) / 1e9
+            del probe_d, probe_h
+        except Exception:      # noqa: BLE001
+            pcie_gbps = None
+
     # N = 1: the same end-to-end loop in the other two read-back formats (PCIe is the bound: 16 / 12 / 4 bytes per pixel)
     e2e_formats = None
     if tiled is None:
@@ -580,6 +597,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": W * H * (12 if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else 16), "steps": e2e_steps,
                 "format": "RGB32F" if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else "RGBA32F",
                 "last_frame_on_host_equals_device_image": e2e_verified,
+                "pcie_d2h_gbps": pcie_gbps,
                 "host_frame_numa": getattr(shared, "numa", None) if shared is not None else None,
                 "note": ("one Render() per step (no batching: every frame is read back): InvView+ViewPos SubData (80 B host->library; the 144 B UBO rides in the kernel parameters), Render(), the frame read back to pinned host memory as RGB32F "
                          "(colour floats bit for bit; the constant alpha 1.0 of compute.glsl:129 is not shipped) through the pipelined read-back (snapshot/pack kernel on the render stream + copy stream, "
