@@ -447,3 +447,87 @@ def test_atmospheric_scatterer_mirror_defaults_and_clamp(ptb):
     assert lp.dtype == np.float32 and lp[0] == 0 and abs(float(lp[1]) - 149600000e3) < 1e6 and abs(float(lp[2])) < 1e5   # noon: sun at the zenith
     with pytest.raises(ValueError):
         ptb.AtmosphericScatterer(t, 0)
+
+
+# ------------------------------------------------------------------------------- fused exchange: the host-side slot bookkeeping
+class _FakeExchangeLib:
+    """Stands in for libptb200's exchange entry points (include/ptb200.h: ptb_exchange_pending / _acquire / _release /
+    _root, ptb_render_frames' refusal when a call would wait for its own releases) so TiledPathTracer's chunking can be
+    checked without a GPU.  Frame q is assembled on rank q % world with rotating roots, on rank 0 otherwise."""
+
+    def __init__(self, rank, world, slots, rotate):
+        self.rank, self.world, self.slots, self.rotate = rank, world, slots, rotate
+        self.seq = 0               # frames rendered so far (every rank renders every frame)
+        self.owned = []            # frames this rank is the root of, rendered and not yet acquired
+        self.held = None           # the acquired frame
+        self.in_ring = 0           # own frames occupying a slot (rendered, not yet released)
+        self.log = []
+
+    def root_of(self, q):
+        return q % self.world if self.rotate else 0
+
+    def render(self, n):
+        mine = [q for q in range(self.seq, self.seq + n) if self.root_of(q) == self.rank]
+        if self.in_ring + len(mine) > self.slots:
+            return -3              # PTB_E_STATE: the call would wait for releases that cannot be enqueued before it returns
+        self.log.append(("render", n))
+        self.seq += n
+        self.owned += mine
+        self.in_ring += len(mine)
+        return 0
+
+    def ptb_exchange_pending(self, ctx):
+        return len(self.owned)
+
+    def ptb_exchange_acquire(self, ctx, out):
+        assert self.held is None and self.owned
+        self.held = self.owned.pop(0)
+        out._obj.value = 0x1000 + (self.held // (self.world if self.rotate else 1)) % self.slots
+        return 0
+
+    def ptb_exchange_release(self, ctx):
+        assert self.held is not None
+        self.log.append(("release", self.held))
+        self.held = None
+        self.in_ring -= 1
+        return 0
+
+    def ptb_exchange_root(self, ctx, q):
+        return self.root_of(self.seq - 1 if q < 0 else q)
+
+
+@pytest.mark.parametrize("rank,world,slots,rotate,frames", [(1, 2, 4, True, 37), (0, 8, 8, True, 200), (0, 4, 32, False, 100),
+                                                            (3, 4, 32, False, 100), (2, 3, 1, True, 7)])
+def test_step_batch_never_outruns_the_slot_ring(ptb, rank, world, slots, rotate, frames):
+    """distributed.TiledPathTracer.step_batch: chunks are sized so that no Render() call waits for a release that is only
+    enqueued after it returns (ptb_abi.cu ptb_render_frames), every frame this rank is the root of is
+    handed to the consumer exactly once and in order, and last_root() names the rank holding the newest frame."""
+    import importlib
+    D = importlib.import_module(ptb.__name__ + ".distributed")
+    lib = _FakeExchangeLib(rank, world, slots, rotate)
+
+    class Tracer:
+        _L, _ctx = lib, None
+
+        def Render(self, n=1):
+            rc = lib.render(n)
+            assert rc == 0, "TiledPathTracer asked for more frames than the slot ring can hold"
+
+    tp = object.__new__(D.TiledPathTracer)
+    tp.tracer, tp.rank, tp.world, tp.fused, tp.rotate, tp.slots = Tracer(), rank, world, True, rotate, slots
+    tp.height, tp.width, tp.channels, tp.device = 2, 2, 3, None
+    tp._last_full = None
+    tp._slot_tensors = {0x1000 + s: ("slot", s) for s in range(slots)}      # pre-wrapped: no CUDA array interface on CPU
+    seen = []
+    last = tp.step_batch(frames, consumer=seen.append)
+    owned = [q for q in range(frames) if lib.root_of(q) == rank]
+    assert [e[1] for e in lib.log if e[0] == "release"] == owned
+    assert len(seen) == len(owned) and lib.in_ring == 0 and lib.seq == frames
+    if owned:
+        assert last == seen[-1] == ("slot", (owned[-1] // (world if rotate else 1)) % slots)
+    else:
+        assert last is None
+    assert max(n for kind, n in lib.log if kind == "render") <= slots * (world if rotate else 1)
+    assert tp.last_root() == lib.root_of(frames - 1)
+    tp.render(5)                                                            # render() goes through the same chunking when fused
+    assert lib.seq == frames + 5 and lib.in_ring == 0
