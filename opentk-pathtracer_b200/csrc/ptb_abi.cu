@@ -145,8 +145,8 @@ struct ptb_ctx {
     int mega_grid = 0;
     int grid_divisor = 1;            // ptb_set_grid_divisor: launch 1/d of the resident CTA slots per frame (experiments)
     // frame batching (ptb_set_batch): up to `batch` consecutive frames of one ptb_render_frames call are traced by ONE
-    // megakernel launch into a set of per-frame scratch images; two sets alternate so that the blends of batch k run beside
-    // the trace of batch k+1
+    // megakernel launch into a set of per-frame scratch images; kBatchSets sets rotate so that the blend of batch k runs
+    // beside the trace of batch k+1
     cudaGraphicsResource* gl_result = nullptr;   // PathTracer.Result registered through CUDA-GL interop (ptb_register_gl_texture)
     unsigned* d_done = nullptr;      // [kBatchSets] "batch traced" flags (written by the trace's last CTA) + [kBatchSets] a sticky error word
     int defer_finish = 1;            // SPP == 1: finished pixels go through the warp's completion queue (PTB_DEFER=0 switches it off for A/B runs)
@@ -160,7 +160,7 @@ struct ptb_ctx {
     unsigned long long batch_seq = 0;
     bool mega_ring = true, mega_defer = true;
     int mega_fold_set = -1;
-    // ptb_set_kernel_timing: an event pair around every megakernel launch, on the stream it runs on
+    // ptb_set_kernel_timing: every megakernel launch brackets itself on the device (first CTA start, last CTA end, %globaltimer)
     bool kt_on = false;
     unsigned long long* d_kt = nullptr;        // 8 x {min CTA start, max CTA end}
     unsigned long long* h_kt = nullptr;        // pinned: [0..15] results, [16..17] the initial pair {~0, 0}
