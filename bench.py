@@ -526,6 +526,26 @@ def run_ours(args, rank, world, local_rank):
             e2e_formats[name] = {"value": samples_per_step * n_alt / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s",
                                  "d2h_bytes_per_step": W * H * (16 if fmt == ptb200.FORMAT_RGBA32F else 4)}
 
+        # A host that does not look at every frame: one Render(BATCH) call and ONE lossless read-back per call.  At
+        # thousands of frames per second no display consumes each frame (the reference's window shows at most one per
+        # monitor refresh, MainWindow.cs:44-56 under GameWindow.Run); informational, the `e2e` key stays one read per frame.
+        def step_batch_read():
+            pt.BasicDataUBO.SubData(64, 64, inv_view)
+            pt.BasicDataUBO.SubData(128, 16, view_pos)
+            pt.Render(BATCH)
+            pt.ReadResultAsync(host_bufs[0].data_ptr(), ptb200.FORMAT_RGB32F)
+        for _ in range(3):
+            step_batch_read()
+        pt.Synchronize()
+        n_alt = max(4, min(args.steps // BATCH, 40))
+        t0 = time.perf_counter()
+        for _ in range(n_alt):
+            step_batch_read()
+        pt.Synchronize()
+        e2e_formats[f"RGB32F_one_readback_per_{BATCH}_frames"] = {
+            "value": samples_per_step * BATCH * n_alt / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s", "d2h_bytes_per_step": W * H * 12 / BATCH,
+            "note": f"one Render({BATCH}) call + one RGB32F read-back per call: a host that displays every {BATCH}th frame"}
+
     # ------------------------------------------------------------------ N > 1: the exchanged frame against ONE GPU rendering alone
     exchange_check = None
     log("e2e done; exchange check")
