@@ -594,6 +594,16 @@ def run_ours(args, rank, world, local_rank):
     achieved = algo_bytes / (kern_launch_ms * 1e-3) / 1e9
     ncu = ncu_summary() if (world == 1 and args.config == "c2") else {}
     prec_name = "fast" if headline == ptb200.PRECISION_FAST else "exact"
+    # The bound that actually limits the pass (DESIGN.md §4 Roofline): warp-instructions issued per second against
+    # SMs x 4 schedulers x 1 instruction/clock at the clock sampled during the timed region.  The instruction count is the
+    # committed ncu capture's (same kernel, same launch shape: deterministic work), the duration is this run's live figure.
+    issue = None
+    if ncu.get("inst_executed_per_launch") and prec_name == "fast" and ncu.get("frames_per_launch") == frames_per_launch and kern_launch_ms:
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        issue_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 4 * sm_mhz * 1e6
+        issue_rate = float(ncu["inst_executed_per_launch"]) / (kern_launch_ms * 1e-3)
+        issue = {"achieved": issue_rate / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-instructions/s", "frac": issue_rate / issue_peak,
+                 "note": "instructions per launch from the committed ncu capture / this run's live launch duration; peak = SMs x 4 schedulers x SM clock under load"}
     line = {
         "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -612,7 +622,8 @@ def run_ours(args, rank, world, local_rank):
                      "kernel_timing": "device-side bracket of every megakernel launch (first CTA start -> last CTA end, %globaltimer) in the same batched / pipelined / tiled mode as `value` (ptb_set_kernel_timing), max over ranks; kernel_ms is per frame; consecutive launches overlap in the drain of the previous grid, so kernel_ms can exceed ms_per_step by that overlap",
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "note": "the pass is FP32-issue-bound, not HBM-bound: thousands of lane-instructions per 32 B of image traffic (DESIGN.md); `traffic` and ncu_capture come from the committed single-GPU c2 capture named in profiles/ncu_summary.json and are attached to that configuration only",
-                     "ncu_capture": ({k: ncu.get(k) for k in ("source", "kernel", "smsp_issue_active_pct", "inst_executed_per_launch", "thread_inst_per_sample", "frames_per_launch")} if ncu else None)},
+                     "ncu_capture": ({k: ncu.get(k) for k in ("source", "kernel", "smsp_issue_active_pct", "inst_executed_per_launch", "thread_inst_per_sample", "frames_per_launch")} if ncu else None),
+                     "issue": issue},
         "e2e": {"value": samples_per_step * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": (80 + 144) * world,
                 "d2h_bytes_per_step": W * H * (12 if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else 16), "steps": e2e_steps,
                 "format": "RGB32F" if (rgb_e2e or (tiled is not None and tiled.channels == 3)) else "RGBA32F",
